@@ -1,0 +1,148 @@
+/*
+ * ldiff.h — C ABI of libldiff_sm100.so, the B200 (sm_100a) implementation of the
+ * L-Diffusion sampling-and-feature hot path.
+ *
+ * The reference (Lweihan/LDiffusion) is pure Python and has no FFI of its own:
+ * its seams are Python call signatures.  Each entry point below replaces the
+ * inline eager-tensor code at the cited reference lines (paths relative to the
+ * reference checkout); INTEGRATION.md shows the ctypes stub a maintainer adds.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless named host_*;
+ *  - `stream` is a cudaStream_t passed as void*; every call only enqueues work
+ *    on it and returns (no allocation, no synchronisation, no global state);
+ *  - `dtype` is LDIFF_F32 / LDIFF_BF16 / LDIFF_U8: the STORAGE type of the
+ *    floating tensors; arithmetic is always fp32, in the order documented in
+ *    DESIGN.md (bit-exact against oracle/ in fp32);
+ *  - return value: 0 on success, a negative LDIFF_E* code otherwise
+ *    (ldiff_strerror gives the text).  Argument errors that the reference
+ *    raises as ValueError stay in the Python host layer;
+ *  - data errors that only the device can see (a predicted label >= K, an
+ *    instance id outside the LUT) are reported through an `int* status` word in
+ *    device memory that the kernel ORs bits into; the host reads it when it
+ *    reads the result.
+ */
+#ifndef LDIFF_H_
+#define LDIFF_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LDIFF_ABI_VERSION 1
+
+enum { LDIFF_F32 = 0, LDIFF_BF16 = 1, LDIFF_U8 = 2 };
+
+enum {
+  LDIFF_OK = 0,
+  LDIFF_EINVAL = -1,       /* bad argument value */
+  LDIFF_EALIGN = -2,       /* pointer not aligned as required (16 bytes) */
+  LDIFF_ELAUNCH = -3,      /* CUDA reported an error at launch */
+  LDIFF_EUNSUPPORTED = -4  /* valid but unsupported combination */
+};
+
+/* bits ORed into *status by kernels */
+enum { LDIFF_STATUS_PRED_RANGE = 1, LDIFF_STATUS_INST_RANGE = 2 };
+
+int ldiff_abi_version(void);
+const char* ldiff_strerror(int code);
+/* number of kernels this library has launched in the calling process */
+int64_t ldiff_launch_count(void);
+
+/* ---- a-1  Laplace forward noising ---------------------------------------
+ * replaces ldiffusion.py:234-237 (and the sampler inside
+ * torch.distributions.Laplace.rsample):  out = x + noise,
+ * noise = 0 - (b * sign(u)) * log1p(-|u|).
+ * Exactly one source of randomness is used:
+ *   noise_in != NULL : injected noise (parity mode; out = x + noise_in, one add)
+ *   u_in     != NULL : injected uniforms in (-1,1)
+ *   otherwise        : Philox4x32-10, key = seed, element i takes word i%4 of
+ *                      counter offset + i/4 (restated in oracle/laplace.py)
+ * noise_out (optional) receives the fp32/bf16 noise that was added. */
+int ldiff_laplace_qsample(const void* x, void* out, const void* noise_in, const void* u_in,
+                          void* noise_out, float b, uint64_t seed, uint64_t offset,
+                          int64_t n, int dtype, void* stream);
+
+/* ---- a-2  PLMS reverse step ----------------------------------------------
+ * replaces scheduler.step(...).prev_sample at segmentor.py:102-104, :443-445,
+ * :525-527, utils.py:200-202, pixel_latent_vector.py:77-79, sample.py:62-64
+ * (diffusers PNDMScheduler.step_plms + _get_prev_sample).
+ *   mode 0: eh = e0
+ *        1: eh = (e0 + e1) / 2
+ *        2: eh = (3 e0 - e1) / 2
+ *        3: eh = (23 e0 - 16 e1 + 5 e2) / 12
+ *        4: eh = (1/24) (55 e0 - 59 e1 + 37 e2 - 9 e3)
+ *   prev = sample_coeff * sample - (alpha_diff * eh) / denom
+ * e0 is the newest model output, e1..e3 older ones; the three scalars are
+ * computed on the host in fp32 exactly as the reference's 0-dim tensors are. */
+int ldiff_plms_step(const void* sample, const void* e0, const void* e1, const void* e2,
+                    const void* e3, int mode, float sample_coeff, float alpha_diff, float denom,
+                    void* prev_sample, int64_t n, int dtype, void* stream);
+
+/* ---- a-3  decode tail -> uint8 RGB + PIL gray ----------------------------
+ * replaces diffusers decode_latents' tail + numpy_to_pil + PIL convert("L") +
+ * the per-pixel stacking loop (pixel_latent_vector.py:80-93,
+ * segmentor.py:105-108,446-448,528-530, utils.py:203-205).
+ * img: [B,3,H,W] planar fp32/bf16.  rgb_hwc (optional): uint8 [B,H,W,3].
+ * gray (optional): plane b is written at gray + b*gray_batch_stride, H*W bytes
+ * (slot i of a [B,n+1,H,W] pixel-vector tensor: the concat is free). */
+int ldiff_decode_tail_gray(const void* img, uint8_t* rgb_hwc, uint8_t* gray, int B, int H, int W,
+                           int64_t gray_batch_stride, int dtype, void* stream);
+
+/* ---- a-4  bilinear lift + gray + concat ----------------------------------
+ * replaces F.interpolate(mode='bilinear', align_corners=False) (+ weighted gray
+ * + torch.cat) at ldiffusion.py:224-226, :240-251 (same primitive at
+ * conductor.py:135).  Source [B,C,h,w] planar (strides in elements); result is
+ * written into channels [dst_channel, dst_channel + (gray ? 1 : C)) of a
+ * [B,Ctot,H,W] planar destination.  gray != 0 requires C == 3 and applies
+ * 0.2989 R + 0.5870 G + 0.1140 B after the lift.  A u8 destination truncates. */
+int ldiff_bilinear_lift(const void* src, int src_dtype, int C, int h, int w,
+                        int64_t src_batch_stride, int64_t src_channel_stride,
+                        void* dst, int dst_dtype, int Ctot, int dst_channel, int H, int W,
+                        int B, int gray, void* stream);
+
+/* ---- a-5  classifier head + argmax ---------------------------------------
+ * tissue form, replaces conductor.py:127 (1x1 conv 256->K), :135 (bilinear lift
+ * to the input size) and segmentor.py:536 (argmax(softmax)) without ever
+ * materialising full-resolution logits. */
+/* feat [B,Cin,h*w] planar fp32/bf16, weight [K,Cin] same dtype, bias fp32 [K]
+ * (or NULL) -> logits fp32 [B,K,h*w].  bf16 runs on tcgen05 tensor cores. */
+int ldiff_head_logits(const void* feat, const void* weight, const float* bias, float* logits,
+                      int B, int Cin, int K, int hw, int dtype, void* stream);
+/* logits fp32 [B,K,h,w] -> uint8 mask [B,H,W] */
+int ldiff_lift_argmax(const float* logits, uint8_t* mask, int B, int K, int h, int w, int H, int W,
+                      void* stream);
+/* cell form, replaces conductor.py:218-221: per-instance Linear(Cin,K) ->
+ * softmax[:,1:] -> top-1 (+1); writes lut[inst_ids[i]] = class.
+ * inst_feats [N,Cin] row-major fp32/bf16; inst_ids int32 [N]; lut uint8. */
+int ldiff_cell_classify(const void* inst_feats, const void* weight, const float* bias,
+                        const int32_t* inst_ids, uint8_t* lut, int lut_size, float* logits_out,
+                        int N, int Cin, int K, int dtype, int* status, void* stream);
+/* replaces the painting loop conductor.py:224-231 (+ segmentor.py:536):
+ * mask[b,p] = lut[b*lut_stride + inst[b,p]]; ids outside [0,lut_size) -> 0 and
+ * LDIFF_STATUS_INST_RANGE. */
+int ldiff_lut_paint(const int32_t* inst, const uint8_t* lut, uint8_t* mask, int64_t n_per_image,
+                    int B, int lut_size, int64_t lut_stride, int* status, void* stream);
+/* first-maximum argmax over the channel axis of [B,K,HW] (the argmax taken
+ * inside utils.py:56, :85, evaluate.py:12, :30 on one-hot / logit inputs). */
+int ldiff_argmax_channels(const void* x, uint8_t* out, int B, int K, int64_t hw, int dtype,
+                          void* stream);
+
+/* ---- a-6  confusion matrix -----------------------------------------------
+ * replaces the K^2+8K masked-sum passes of utils.py:55-104 and
+ * evaluate.py:11-45.  C is int64 [(K+1),K], row = gt class (row K = gt outside
+ * [0,K)), column = predicted class; the kernel ACCUMULATES into C (caller
+ * zeroes it; it may be the buffer handed to ncclAllReduce).  gt_lut (optional,
+ * 256 bytes) maps raw gray levels to classes first (dataset.py:10-32,48-63).
+ * pred >= K sets LDIFF_STATUS_PRED_RANGE (the reference's one_hot raises). */
+int ldiff_confusion_hist(const uint8_t* pred, const uint8_t* gt, const uint8_t* gt_lut,
+                         int64_t* C, int64_t n, int K, int* status, void* stream);
+/* int64 labels -> uint8 (values outside [0,254] become 255 = "other") */
+int ldiff_labels_to_u8(const int64_t* in, uint8_t* out, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LDIFF_H_ */

@@ -1,0 +1,375 @@
+// a-5 classifier head: low-res logits -> bilinear lift -> argmax(softmax) mask,
+// the cell-level instance classifier + LUT painting, and the channel argmax the
+// metric functions take of their one-hot inputs (sm_100a).
+//
+// Full-resolution logits are never materialised: lift_argmax_kernel keeps, per
+// output column, the horizontally-lifted logits of the two source rows in
+// registers and turns every output row into one mul + one fma + a running
+// top-2 per class, writing only the uint8 mask (1 byte/pixel).
+//
+// Decision rule (bit-exact against oracle/head.py::softmax_argmax_spec):
+// argmax(softmax(x)) equals the first argmax(x) unless rounding merges two
+// probabilities, which needs a top-2 gap below ~2e-7; pixels whose gap is
+// <= kTieGap re-evaluate the pinned softmax (exp in fp64 rounded to fp32,
+// sequential fp32 sum, fp32 division, first maximum).
+#include "common.cuh"
+
+namespace ldiff {
+
+struct AxisH { float scale; int in, out; };
+struct TapH { int i0, i1; float l0, l1; };
+
+__device__ __forceinline__ TapH tap(const AxisH& a, int dst) {
+  TapH t;
+  if (a.in == a.out) { t.i0 = t.i1 = dst; t.l0 = 1.f; t.l1 = 0.f; return t; }
+  float src = fmaxf(__fmaf_rn(a.scale, (float)dst + 0.5f, -0.5f), 0.f);
+  t.i0 = min((int)floorf(src), a.in - 1);
+  t.i1 = min(t.i0 + 1, a.in - 1);
+  t.l1 = fminf(fmaxf(__fsub_rn(src, (float)t.i0), 0.f), 1.f);
+  t.l0 = __fsub_rn(1.f, t.l1);
+  return t;
+}
+
+__device__ __forceinline__ float lerp2(float w0, float a, float w1, float b) {
+  return __fmaf_rn(w0, a, __fmul_rn(w1, b));
+}
+
+constexpr float kTieGap = 1e-5f;
+
+// pinned softmax + first-max argmax over v[lo..K)
+template <int KT>
+__device__ __noinline__ int softmax_argmax_exact(const float (&v)[KT], int K, int lo) {
+  float m = v[0];
+  for (int k = 1; k < K; ++k) m = fmaxf(m, v[k]);
+  float e[KT];
+  float s = 0.f;
+  for (int k = 0; k < K; ++k) {
+    e[k] = (float)exp((double)__fsub_rn(v[k], m));
+    s = __fadd_rn(s, e[k]);
+  }
+  int best = lo;
+  float pb = __fdiv_rn(e[lo], s);
+  for (int k = lo + 1; k < K; ++k) {
+    const float p = __fdiv_rn(e[k], s);
+    if (p > pb) { pb = p; best = k; }
+  }
+  return best;
+}
+
+// ----------------------------------------------------------------------------
+// logits fp32 [B,K,h,w] -> mask uint8 [B,H,W]; K <= KT.  One thread per output
+// column, a band of output rows per block-y.
+template <int KT>
+__global__ void __launch_bounds__(256)
+lift_argmax_kernel(const float* __restrict__ logits, uint8_t* __restrict__ mask, int K, AxisH ay,
+                   AxisH ax, int band) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= ax.out) return;
+  const int b = blockIdx.z;
+  const int Y0 = blockIdx.y * band, Y1 = min(Y0 + band, ay.out);
+  const TapH tx = tap(ax, x);
+  const int64_t plane = (int64_t)ay.in * ax.in;
+  const float* lb = logits + (int64_t)b * K * plane;
+  uint8_t* out = mask + (int64_t)b * ay.out * ax.out + x;
+
+  float T[KT], U[KT];
+  int cy0 = -1, cy1 = -1;
+  for (int y = Y0; y < Y1; ++y) {
+    const TapH ty = tap(ay, y);
+    if (ty.i0 != cy0 || ty.i1 != cy1) {
+      cy0 = ty.i0; cy1 = ty.i1;
+#pragma unroll
+      for (int k = 0; k < KT; ++k) {
+        if (k < K) {
+          const float* r0 = lb + k * plane + (int64_t)cy0 * ax.in;
+          const float* r1 = lb + k * plane + (int64_t)cy1 * ax.in;
+          T[k] = lerp2(tx.l0, __ldg(r0 + tx.i0), tx.l1, __ldg(r0 + tx.i1));
+          U[k] = lerp2(tx.l0, __ldg(r1 + tx.i0), tx.l1, __ldg(r1 + tx.i1));
+        }
+      }
+    }
+    float best = lerp2(ty.l0, T[0], ty.l1, U[0]);
+    float second = -INFINITY;
+    int idx = 0;
+#pragma unroll
+    for (int k = 1; k < KT; ++k) {
+      if (k < K) {
+        const float v = lerp2(ty.l0, T[k], ty.l1, U[k]);
+        if (v > best) { second = best; best = v; idx = k; }
+        else second = fmaxf(second, v);
+      }
+    }
+    if (__fsub_rn(best, second) <= kTieGap) {          // rare: pinned softmax decides
+      float v[KT];
+#pragma unroll
+      for (int k = 0; k < KT; ++k) v[k] = (k < K) ? lerp2(ty.l0, T[k], ty.l1, U[k]) : 0.f;
+      idx = softmax_argmax_exact<KT>(v, K, 0);
+    }
+    out[(int64_t)y * ax.out] = (uint8_t)idx;
+  }
+}
+
+// any K <= 255: one thread per output pixel, nothing cached (cold path)
+__global__ void __launch_bounds__(256)
+lift_argmax_generic_kernel(const float* __restrict__ logits, uint8_t* __restrict__ mask, int K,
+                           AxisH ay, AxisH ax, int B) {
+  const int64_t HW = (int64_t)ay.out * ax.out, total = HW * B;
+  const int64_t plane = (int64_t)ay.in * ax.in;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / HW);
+    const int64_t p = i - b * HW;
+    const int y = (int)(p / ax.out), x = (int)(p - (int64_t)y * ax.out);
+    const TapH ty = tap(ay, y), tx = tap(ax, x);
+    const float* lb = logits + (int64_t)b * K * plane;
+    auto value = [&](int k) {
+      const float* r0 = lb + k * plane + (int64_t)ty.i0 * ax.in;
+      const float* r1 = lb + k * plane + (int64_t)ty.i1 * ax.in;
+      return lerp2(ty.l0, lerp2(tx.l0, __ldg(r0 + tx.i0), tx.l1, __ldg(r0 + tx.i1)), ty.l1,
+                   lerp2(tx.l0, __ldg(r1 + tx.i0), tx.l1, __ldg(r1 + tx.i1)));
+    };
+    float best = value(0), second = -INFINITY;
+    int idx = 0;
+    for (int k = 1; k < K; ++k) {
+      const float v = value(k);
+      if (v > best) { second = best; best = v; idx = k; }
+      else second = fmaxf(second, v);
+    }
+    if (__fsub_rn(best, second) <= kTieGap) {
+      float s = 0.f;
+      for (int k = 0; k < K; ++k) s = __fadd_rn(s, (float)exp((double)__fsub_rn(value(k), best)));
+      float pb = -1.f;
+      for (int k = 0; k < K; ++k) {
+        const float pk = __fdiv_rn((float)exp((double)__fsub_rn(value(k), best)), s);
+        if (pk > pb) { pb = pk; idx = k; }
+      }
+    }
+    mask[i] = (uint8_t)idx;
+  }
+}
+
+// ----------------------------------------------------------------------------
+// CUDA-core contraction (fp32 storage, or any dtype when tensor cores do not
+// apply): feat [B,Cin,hw] planar, weight [K,Cin] -> logits fp32 [B,K,hw].
+// One thread per pixel, weights broadcast from shared memory, sequential fp32
+// FMA over channels, bias added last.
+template <typename T, int KT>
+__global__ void __launch_bounds__(128)
+head_logits_simt_kernel(const T* __restrict__ feat, const T* __restrict__ weight,
+                        const float* __restrict__ bias, float* __restrict__ logits, int Cin, int K,
+                        int hw) {
+  extern __shared__ float wsm[];                      // [Cin][KT]
+  for (int i = threadIdx.x; i < Cin * KT; i += blockDim.x) {
+    const int c = i / KT, k = i - c * KT;
+    wsm[i] = (k < K) ? to_f32(weight[(int64_t)k * Cin + c]) : 0.f;
+  }
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= hw) return;
+  const T* f = feat + (int64_t)b * Cin * hw + p;
+  float acc[KT];
+#pragma unroll
+  for (int k = 0; k < KT; ++k) acc[k] = 0.f;
+  for (int c = 0; c < Cin; ++c) {
+    const float v = to_f32(f[(int64_t)c * hw]);
+    const float4* wr = reinterpret_cast<const float4*>(wsm + c * KT);
+#pragma unroll
+    for (int q = 0; q < KT / 4; ++q) {
+      const float4 w4 = wr[q];
+      acc[4 * q] = fmaf(w4.x, v, acc[4 * q]);
+      acc[4 * q + 1] = fmaf(w4.y, v, acc[4 * q + 1]);
+      acc[4 * q + 2] = fmaf(w4.z, v, acc[4 * q + 2]);
+      acc[4 * q + 3] = fmaf(w4.w, v, acc[4 * q + 3]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < KT; ++k)
+    if (k < K) logits[((int64_t)b * K + k) * hw + p] = acc[k] + (bias ? bias[k] : 0.f);
+}
+
+// ----------------------------------------------------------------------------
+// cell form: one warp per instance
+template <typename T, int KT>
+__global__ void __launch_bounds__(256)
+cell_classify_kernel(const T* __restrict__ feats, const T* __restrict__ weight,
+                     const float* __restrict__ bias, const int32_t* __restrict__ ids,
+                     uint8_t* __restrict__ lut, int lut_size, float* __restrict__ logits_out, int N,
+                     int Cin, int K, int* __restrict__ status) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= N) return;
+  float acc[KT];
+#pragma unroll
+  for (int k = 0; k < KT; ++k) acc[k] = 0.f;
+  for (int c = lane; c < Cin; c += 32) {
+    const float v = to_f32(feats[(int64_t)warp * Cin + c]);
+#pragma unroll
+    for (int k = 0; k < KT; ++k)
+      if (k < K) acc[k] = fmaf(to_f32(__ldg(weight + (int64_t)k * Cin + c)), v, acc[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < KT; ++k)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+  if (lane == 0) {
+    float v[KT];
+#pragma unroll
+    for (int k = 0; k < KT; ++k) v[k] = (k < K) ? acc[k] + (bias ? bias[k] : 0.f) : 0.f;
+    if (logits_out)
+      for (int k = 0; k < K; ++k) logits_out[(int64_t)warp * K + k] = v[k];
+    // softmax(...)[:, 1:] -> top-1 -> +1  (conductor.py:219-221)
+    const int cls = (K > 1) ? softmax_argmax_exact<KT>(v, K, 1) : 0;
+    const int id = ids[warp];
+    if (id >= 0 && id < lut_size) lut[id] = (uint8_t)cls;
+    else atomicOr(status, LDIFF_STATUS_INST_RANGE);
+  }
+}
+
+// mask[b,p] = lut[b][inst[b,p]], 16 pixels per thread
+__global__ void __launch_bounds__(256)
+lut_paint_kernel(const int32_t* __restrict__ inst, const uint8_t* __restrict__ lut,
+                 uint8_t* __restrict__ mask, int64_t n, int lut_size, int64_t lut_stride,
+                 int* __restrict__ status) {
+  const int b = blockIdx.y;
+  const uint8_t* l = lut + b * lut_stride;
+  const int32_t* in = inst + b * n;
+  uint8_t* out = mask + b * n;
+  int bad = 0;
+  auto look = [&](int id) -> uint32_t {
+    if ((unsigned)id < (unsigned)lut_size) return __ldg(l + id);
+    bad = 1;
+    return 0u;
+  };
+  const int64_t nvec = n >> 4;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec;
+       v += (int64_t)gridDim.x * blockDim.x) {
+    const int4* p = reinterpret_cast<const int4*>(in) + 4 * v;
+    int4 q[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) q[j] = __ldcs(p + j);
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      w[j] = look(q[j].x) | (look(q[j].y) << 8) | (look(q[j].z) << 16) | (look(q[j].w) << 24);
+    __stcs(reinterpret_cast<uint4*>(out) + v, make_uint4(w[0], w[1], w[2], w[3]));
+  }
+  const int64_t t = (nvec << 4) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) out[t] = (uint8_t)look(in[t]);
+  if (bad) atomicOr(status, LDIFF_STATUS_INST_RANGE);
+}
+
+// first-max argmax over channels of [B,K,hw]; one pixel per thread
+template <typename T>
+__global__ void __launch_bounds__(256)
+argmax_channels_kernel(const T* __restrict__ x, uint8_t* __restrict__ out, int K, int64_t hw,
+                       int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / hw, p = i - b * hw;
+    const T* xb = x + b * K * hw + p;
+    float best = to_f32(xb[0]);
+    int idx = 0;
+    for (int k = 1; k < K; ++k) {
+      const float v = to_f32(xb[(int64_t)k * hw]);
+      if (v > best) { best = v; idx = k; }
+    }
+    out[i] = (uint8_t)idx;
+  }
+}
+
+int launch_head_logits_tc(const void* feat, const void* weight, const float* bias, float* logits,
+                          int B, int Cin, int K, int hw, cudaStream_t st);   // head_tc.cu
+
+}  // namespace ldiff
+
+using namespace ldiff;
+
+extern "C" int ldiff_lift_argmax(const float* logits, uint8_t* mask, int B, int K, int h, int w,
+                                 int H, int W, void* stream) {
+  if (!logits || !mask || B < 0 || K < 1 || K > 255 || h < 1 || w < 1 || H < 1 || W < 1)
+    return LDIFF_EINVAL;
+  if (B == 0) return LDIFF_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  AxisH ay{(float)h / (float)H, h, H}, ax{(float)w / (float)W, w, W};
+  if (K <= 16) {
+    const int band = 32;
+    dim3 grid((W + 255) / 256, (H + band - 1) / band, B);
+    if (K <= 8) lift_argmax_kernel<8><<<grid, 256, 0, st>>>(logits, mask, K, ay, ax, band);
+    else lift_argmax_kernel<16><<<grid, 256, 0, st>>>(logits, mask, K, ay, ax, band);
+  } else {
+    const int64_t total = (int64_t)H * W * B;
+    lift_argmax_generic_kernel<<<grid_for(total, 256, 8), 256, 0, st>>>(logits, mask, K, ay, ax, B);
+  }
+  return check_launch();
+}
+
+extern "C" int ldiff_head_logits(const void* feat, const void* weight, const float* bias,
+                                 float* logits, int B, int Cin, int K, int hw, int dtype,
+                                 void* stream) {
+  if (!feat || !weight || !logits || B < 0 || Cin < 1 || K < 1 || hw < 1) return LDIFF_EINVAL;
+  if (K > 32) return LDIFF_EUNSUPPORTED;
+  if (B == 0) return LDIFF_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == LDIFF_BF16) {
+    const int rc = launch_head_logits_tc(feat, weight, bias, logits, B, Cin, K, hw, st);
+    if (rc != LDIFF_EUNSUPPORTED) return rc;          // shapes the tensor-core tile cannot take
+  }
+  dim3 grid((hw + 127) / 128, B);
+#define HL(T, KT)                                                                              \
+  head_logits_simt_kernel<T, KT><<<grid, 128, (size_t)Cin * KT * sizeof(float), st>>>(         \
+      (const T*)feat, (const T*)weight, bias, logits, Cin, K, hw)
+  if ((size_t)Cin * 32 * sizeof(float) > 48 * 1024) return LDIFF_EUNSUPPORTED;
+  if (dtype == LDIFF_F32) { if (K <= 16) HL(float, 16); else HL(float, 32); }
+  else if (dtype == LDIFF_BF16) { if (K <= 16) HL(__nv_bfloat16, 16); else HL(__nv_bfloat16, 32); }
+  else return LDIFF_EUNSUPPORTED;
+#undef HL
+  return check_launch();
+}
+
+extern "C" int ldiff_cell_classify(const void* inst_feats, const void* weight, const float* bias,
+                                   const int32_t* inst_ids, uint8_t* lut, int lut_size,
+                                   float* logits_out, int N, int Cin, int K, int dtype, int* status,
+                                   void* stream) {
+  if (!inst_feats || !weight || !inst_ids || !lut || !status || N < 0 || Cin < 1 || K < 1 ||
+      lut_size < 1)
+    return LDIFF_EINVAL;
+  if (K > 32) return LDIFF_EUNSUPPORTED;
+  if (N == 0) return LDIFF_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = (N * 32 + 255) / 256;
+#define CC(T, KT)                                                                                 \
+  cell_classify_kernel<T, KT><<<grid, 256, 0, st>>>((const T*)inst_feats, (const T*)weight, bias, \
+                                                    inst_ids, lut, lut_size, logits_out, N, Cin, K, status)
+  if (dtype == LDIFF_F32) { if (K <= 16) CC(float, 16); else CC(float, 32); }
+  else if (dtype == LDIFF_BF16) { if (K <= 16) CC(__nv_bfloat16, 16); else CC(__nv_bfloat16, 32); }
+  else return LDIFF_EUNSUPPORTED;
+#undef CC
+  return check_launch();
+}
+
+extern "C" int ldiff_lut_paint(const int32_t* inst, const uint8_t* lut, uint8_t* mask,
+                               int64_t n_per_image, int B, int lut_size, int64_t lut_stride,
+                               int* status, void* stream) {
+  if (!inst || !lut || !mask || !status || n_per_image < 0 || B < 0 || lut_size < 1) return LDIFF_EINVAL;
+  if (n_per_image == 0 || B == 0) return LDIFF_OK;
+  if (!aligned16(inst) || !aligned16(mask) || (B > 1 && (n_per_image % 16))) return LDIFF_EALIGN;
+  const int64_t items = (n_per_image >> 4) > (n_per_image & 15) ? (n_per_image >> 4) : (n_per_image & 15);
+  dim3 grid(grid_for(items, 256, 8), B);
+  lut_paint_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(inst, lut, mask, n_per_image, lut_size,
+                                                           lut_stride, status);
+  return check_launch();
+}
+
+extern "C" int ldiff_argmax_channels(const void* x, uint8_t* out, int B, int K, int64_t hw, int dtype,
+                                     void* stream) {
+  if (!x || !out || B < 0 || K < 1 || K > 255 || hw < 0) return LDIFF_EINVAL;
+  if (B == 0 || hw == 0) return LDIFF_OK;
+  const int64_t total = hw * B;
+  const int grid = grid_for(total, 256, 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == LDIFF_F32) argmax_channels_kernel<float><<<grid, 256, 0, st>>>((const float*)x, out, K, hw, total);
+  else if (dtype == LDIFF_BF16)
+    argmax_channels_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, out, K, hw, total);
+  else return LDIFF_EUNSUPPORTED;
+  return check_launch();
+}

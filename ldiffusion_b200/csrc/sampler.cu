@@ -1,0 +1,220 @@
+// a-1 Laplace forward noising and a-2 PLMS reverse step (sm_100a).
+//
+// Both are streaming elementwise kernels over a latent tensor: 128-bit loads
+// and stores with streaming cache hints, 8 elements per thread per iteration,
+// grid-stride over a grid sized to the SM count.  All arithmetic uses the _rn
+// intrinsics in the order of the reference's eager op chain so that no FMA
+// contraction changes a rounding (bit-exact against oracle/ in fp32).
+#include "common.cuh"
+
+namespace ldiff {
+
+// ---------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11), counter-based: no state in memory.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+
+// 23 random bits -> odd multiple of 2^-23 in (-1, 1); every step exact in fp32
+__device__ __forceinline__ float uniform_pm1(uint32_t w) {
+  return (float)(2 * (int)(w >> 9) + 1 - (1 << 23)) * 1.1920928955078125e-07f;
+}
+
+// torch.distributions.Laplace.rsample with loc = 0:
+//   noise = 0 - (scale * sign(u)) * log1p(-|u|)
+__device__ __forceinline__ float laplace_from_uniform(float u, float b) {
+  const float sgn = (u > 0.f) ? 1.f : ((u < 0.f) ? -1.f : 0.f);
+  const float t = __fmul_rn(b, sgn);
+  const float l = log1pf(-fabsf(u));
+  return __fsub_rn(0.f, __fmul_rn(t, l));
+}
+
+enum { SRC_PHILOX = 0, SRC_UNIFORM = 1, SRC_NOISE = 2 };
+
+template <typename T, int SRC, bool EMIT>
+__global__ void __launch_bounds__(256)
+laplace_qsample_kernel(const T* __restrict__ x, T* __restrict__ out, const T* __restrict__ inj,
+                       T* __restrict__ noise_out, float b, uint2 key, uint64_t offset, int64_t n) {
+  const int64_t nvec = n >> 3;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+    const int64_t base = v << 3;
+    float xv[8], nz[8];
+    Vec8<T>::load(x + base, xv);
+    if (SRC == SRC_PHILOX) {
+      const uint64_t c0 = offset + (uint64_t)(base >> 2);
+      const uint4 r0 = philox4x32_10(make_uint4((uint32_t)c0, (uint32_t)(c0 >> 32), 0u, 0u), key);
+      const uint64_t c1 = c0 + 1;
+      const uint4 r1 = philox4x32_10(make_uint4((uint32_t)c1, (uint32_t)(c1 >> 32), 0u, 0u), key);
+      const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) nz[i] = laplace_from_uniform(uniform_pm1(w[i]), b);
+    } else {
+      Vec8<T>::load(inj + base, nz);
+      if (SRC == SRC_UNIFORM) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) nz[i] = laplace_from_uniform(nz[i], b);
+      }
+    }
+    if (EMIT) Vec8<T>::store(noise_out + base, nz);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) xv[i] = __fadd_rn(xv[i], nz[i]);
+    Vec8<T>::store(out + base, xv);
+  }
+  // scalar tail (n % 8 elements), one thread each
+  const int64_t t = (nvec << 3) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) {
+    float nzs;
+    if (SRC == SRC_PHILOX) {
+      const uint64_t c = offset + (uint64_t)(t >> 2);
+      const uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0u, 0u), key);
+      const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+      nzs = laplace_from_uniform(uniform_pm1(w[t & 3]), b);
+    } else {
+      nzs = to_f32(inj[t]);
+      if (SRC == SRC_UNIFORM) nzs = laplace_from_uniform(nzs, b);
+    }
+    if (EMIT) noise_out[t] = from_f32<T>(nzs);
+    out[t] = from_f32<T>(__fadd_rn(to_f32(x[t]), nzs));
+  }
+}
+
+template <typename T>
+static int launch_qsample(const void* x, void* out, const void* noise_in, const void* u_in,
+                          void* noise_out, float b, uint64_t seed, uint64_t offset, int64_t n,
+                          cudaStream_t st) {
+  const int threads = 256;
+  const int64_t items = (n >> 3) > (n & 7) ? (n >> 3) : (n & 7);
+  const int grid = grid_for(items, threads, 8);
+  const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  const T* xs = (const T*)x;
+  T* os = (T*)out;
+  T* no = (T*)noise_out;
+#define LQ(SRC, EMIT, INJ) \
+  laplace_qsample_kernel<T, SRC, EMIT><<<grid, threads, 0, st>>>(xs, os, (const T*)(INJ), no, b, key, offset, n)
+  if (noise_in) {
+    if (no) LQ(SRC_NOISE, true, noise_in); else LQ(SRC_NOISE, false, noise_in);
+  } else if (u_in) {
+    if (no) LQ(SRC_UNIFORM, true, u_in); else LQ(SRC_UNIFORM, false, u_in);
+  } else {
+    if (no) LQ(SRC_PHILOX, true, nullptr); else LQ(SRC_PHILOX, false, nullptr);
+  }
+#undef LQ
+  return check_launch();
+}
+
+// ---------------------------------------------------------------------------
+// PLMS step: prev = sc * x - (dA * eh) / denom, eh = Adams-Bashforth combination
+// ---------------------------------------------------------------------------
+template <int MODE>
+__device__ __forceinline__ float plms_eps(float e0, float e1, float e2, float e3) {
+  if (MODE == 0) return e0;
+  if (MODE == 1) return __fmul_rn(__fadd_rn(e0, e1), 0.5f);                       // (a + b) / 2
+  if (MODE == 2) return __fmul_rn(__fsub_rn(__fmul_rn(3.f, e0), e1), 0.5f);       // (3a - b) / 2
+  if (MODE == 3)
+    return __fdiv_rn(__fadd_rn(__fsub_rn(__fmul_rn(23.f, e0), __fmul_rn(16.f, e1)),
+                               __fmul_rn(5.f, e2)), 12.f);
+  const float c24 = (float)(1.0 / 24.0);
+  return __fmul_rn(c24, __fsub_rn(__fadd_rn(__fsub_rn(__fmul_rn(55.f, e0), __fmul_rn(59.f, e1)),
+                                            __fmul_rn(37.f, e2)), __fmul_rn(9.f, e3)));
+}
+
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256)
+plms_step_kernel(const T* __restrict__ x, const T* __restrict__ e0, const T* __restrict__ e1,
+                 const T* __restrict__ e2, const T* __restrict__ e3, float sc, float dA,
+                 float denom, T* __restrict__ out, int64_t n) {
+  const int64_t nvec = n >> 3;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+    const int64_t base = v << 3;
+    float xv[8], a[8], b[8], c[8], d[8];
+    Vec8<T>::load(x + base, xv);
+    Vec8<T>::load(e0 + base, a);
+    if (MODE >= 1) Vec8<T>::load(e1 + base, b);
+    if (MODE >= 3) Vec8<T>::load(e2 + base, c);
+    if (MODE >= 4) Vec8<T>::load(e3 + base, d);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float eh = plms_eps<MODE>(a[i], MODE >= 1 ? b[i] : 0.f, MODE >= 3 ? c[i] : 0.f,
+                                      MODE >= 4 ? d[i] : 0.f);
+      xv[i] = __fsub_rn(__fmul_rn(sc, xv[i]), __fdiv_rn(__fmul_rn(dA, eh), denom));
+    }
+    Vec8<T>::store(out + base, xv);
+  }
+  const int64_t t = (nvec << 3) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) {
+    const float eh = plms_eps<MODE>(to_f32(e0[t]), MODE >= 1 ? to_f32(e1[t]) : 0.f,
+                                    MODE >= 3 ? to_f32(e2[t]) : 0.f, MODE >= 4 ? to_f32(e3[t]) : 0.f);
+    out[t] = from_f32<T>(__fsub_rn(__fmul_rn(sc, to_f32(x[t])), __fdiv_rn(__fmul_rn(dA, eh), denom)));
+  }
+}
+
+template <typename T>
+static int launch_plms(const void* x, const void* e0, const void* e1, const void* e2, const void* e3,
+                       int mode, float sc, float dA, float denom, void* out, int64_t n,
+                       cudaStream_t st) {
+  const int threads = 256;
+  const int64_t items = (n >> 3) > (n & 7) ? (n >> 3) : (n & 7);
+  const int grid = grid_for(items, threads, 8);
+#define PS(M) \
+  plms_step_kernel<T, M><<<grid, threads, 0, st>>>((const T*)x, (const T*)e0, (const T*)e1, \
+                                                   (const T*)e2, (const T*)e3, sc, dA, denom, (T*)out, n)
+  switch (mode) {
+    case 0: PS(0); break;
+    case 1: PS(1); break;
+    case 2: PS(2); break;
+    case 3: PS(3); break;
+    default: PS(4); break;
+  }
+#undef PS
+  return check_launch();
+}
+
+}  // namespace ldiff
+
+using namespace ldiff;
+
+extern "C" int ldiff_laplace_qsample(const void* x, void* out, const void* noise_in, const void* u_in,
+                                     void* noise_out, float b, uint64_t seed, uint64_t offset,
+                                     int64_t n, int dtype, void* stream) {
+  if (!x || !out || n < 0 || (noise_in && u_in)) return LDIFF_EINVAL;
+  if (n == 0) return LDIFF_OK;
+  if (!aligned16(x) || !aligned16(out) || !aligned16(noise_in) || !aligned16(u_in) ||
+      !aligned16(noise_out))
+    return LDIFF_EALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == LDIFF_F32)
+    return launch_qsample<float>(x, out, noise_in, u_in, noise_out, b, seed, offset, n, st);
+  if (dtype == LDIFF_BF16)
+    return launch_qsample<__nv_bfloat16>(x, out, noise_in, u_in, noise_out, b, seed, offset, n, st);
+  return LDIFF_EUNSUPPORTED;
+}
+
+extern "C" int ldiff_plms_step(const void* sample, const void* e0, const void* e1, const void* e2,
+                               const void* e3, int mode, float sample_coeff, float alpha_diff,
+                               float denom, void* prev_sample, int64_t n, int dtype, void* stream) {
+  if (!sample || !e0 || !prev_sample || n < 0 || mode < 0 || mode > 4) return LDIFF_EINVAL;
+  if ((mode >= 1 && !e1) || (mode >= 3 && !e2) || (mode >= 4 && !e3)) return LDIFF_EINVAL;
+  if (n == 0) return LDIFF_OK;
+  if (!aligned16(sample) || !aligned16(e0) || !aligned16(e1) || !aligned16(e2) || !aligned16(e3) ||
+      !aligned16(prev_sample))
+    return LDIFF_EALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == LDIFF_F32)
+    return launch_plms<float>(sample, e0, e1, e2, e3, mode, sample_coeff, alpha_diff, denom,
+                              prev_sample, n, st);
+  if (dtype == LDIFF_BF16)
+    return launch_plms<__nv_bfloat16>(sample, e0, e1, e2, e3, mode, sample_coeff, alpha_diff, denom,
+                                      prev_sample, n, st);
+  return LDIFF_EUNSUPPORTED;
+}

@@ -1,0 +1,357 @@
+"""torch-facing operators of the hot path.
+
+Every operator is a ``torch.library`` custom op (namespace ``ldiff``) whose
+implementation is one call into the C ABI of ``libldiff_sm100.so`` on the
+caller's current CUDA stream.  Tensors must live on a CUDA device: there is no
+CPU implementation and none is dispatched to.
+"""
+from typing import Optional, Sequence
+
+import torch
+from torch import Tensor
+
+from . import _cabi
+from ._cabi import BF16, F32, U8, LdiffError, check
+
+_DT = {torch.float32: F32, torch.bfloat16: BF16, torch.uint8: U8}
+
+
+def _dt(t: Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise TypeError(f"ldiff: unsupported dtype {t.dtype}") from None
+
+
+def _cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise LdiffError("ldiff operators run on CUDA tensors only (no CPU fallback)")
+
+
+def _ptr(t: Optional[Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream(t: Tensor):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _dense(t: Tensor, what: str):
+    if not t.is_contiguous():
+        raise ValueError(f"ldiff: {what} must be contiguous")
+
+
+_status_words = {}
+
+
+def status_word(device) -> Tensor:
+    """Per-device int32 word the kernels OR data-error bits into."""
+    device = torch.device(device)
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    w = _status_words.get(key)
+    if w is None:
+        w = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", key))
+        _status_words[key] = w
+    return w
+
+
+def check_status(device):
+    """Synchronising read of the status word; raises like the reference does."""
+    w = status_word(device)
+    bits = int(w.item())
+    if bits:
+        w.zero_()
+        if bits & _cabi.STATUS_PRED_RANGE:
+            # F.one_hot at evaluate.py:70 raises this for a predicted label >= K
+            raise RuntimeError("Class values must be smaller than num_classes.")
+        if bits & _cabi.STATUS_INST_RANGE:
+            raise RuntimeError("ldiff: instance id outside the class LUT")
+
+
+# ---------------------------------------------------------------------------
+# custom ops (out-variants: the wrapper below allocates)
+# ---------------------------------------------------------------------------
+
+@torch.library.custom_op("ldiff::laplace_qsample", mutates_args=("out", "noise_out"))
+def _laplace_qsample(x: Tensor, out: Tensor, noise: Optional[Tensor], u: Optional[Tensor],
+                     noise_out: Optional[Tensor], b: float, seed: int, offset: int) -> None:
+    _cuda(x, out, noise, u, noise_out)
+    check(_cabi.lib().ldiff_laplace_qsample(_ptr(x), _ptr(out), _ptr(noise), _ptr(u), _ptr(noise_out),
+                                            b, seed, offset, x.numel(), _dt(x), _stream(x)))
+
+
+@torch.library.custom_op("ldiff::plms_step", mutates_args=("out",))
+def _plms_step(sample: Tensor, eps: Sequence[Tensor], mode: int, sample_coeff: float,
+               alpha_diff: float, denom: float, out: Tensor) -> None:
+    _cuda(sample, out, *eps)
+    e = [_ptr(t) for t in eps] + [None] * (4 - len(eps))
+    check(_cabi.lib().ldiff_plms_step(_ptr(sample), e[0], e[1], e[2], e[3], mode, sample_coeff,
+                                      alpha_diff, denom, _ptr(out), sample.numel(), _dt(sample),
+                                      _stream(sample)))
+
+
+@torch.library.custom_op("ldiff::decode_tail_gray", mutates_args=("rgb", "gray"))
+def _decode_tail_gray(img: Tensor, rgb: Optional[Tensor], gray: Optional[Tensor]) -> None:
+    _cuda(img, rgb, gray)
+    B, _, H, W = img.shape
+    gstride = gray.stride(0) if gray is not None else 0
+    check(_cabi.lib().ldiff_decode_tail_gray(_ptr(img), _ptr(rgb), _ptr(gray), B, H, W, gstride,
+                                             _dt(img), _stream(img)))
+
+
+@torch.library.custom_op("ldiff::bilinear_lift", mutates_args=("dst",))
+def _bilinear_lift(src: Tensor, dst: Tensor, dst_channel: int, gray: bool) -> None:
+    _cuda(src, dst)
+    B, C, h, w = src.shape
+    _, Ctot, H, W = dst.shape
+    check(_cabi.lib().ldiff_bilinear_lift(_ptr(src), _dt(src), C, h, w, src.stride(0), src.stride(1),
+                                          _ptr(dst), _dt(dst), Ctot, dst_channel, H, W, B,
+                                          1 if gray else 0, _stream(src)))
+
+
+@torch.library.custom_op("ldiff::head_logits", mutates_args=("logits",))
+def _head_logits(feat: Tensor, weight: Tensor, bias: Optional[Tensor], logits: Tensor) -> None:
+    _cuda(feat, weight, bias, logits)
+    B, Cin = feat.shape[:2]
+    hw = feat[0, 0].numel()
+    check(_cabi.lib().ldiff_head_logits(_ptr(feat), _ptr(weight), _ptr(bias), _ptr(logits), B, Cin,
+                                        weight.shape[0], hw, _dt(feat), _stream(feat)))
+
+
+@torch.library.custom_op("ldiff::lift_argmax", mutates_args=("mask",))
+def _lift_argmax(logits: Tensor, mask: Tensor) -> None:
+    _cuda(logits, mask)
+    B, K, h, w = logits.shape
+    _, H, W = mask.shape
+    check(_cabi.lib().ldiff_lift_argmax(_ptr(logits), _ptr(mask), B, K, h, w, H, W, _stream(logits)))
+
+
+@torch.library.custom_op("ldiff::cell_classify", mutates_args=("lut", "logits_out", "status"))
+def _cell_classify(feats: Tensor, weight: Tensor, bias: Optional[Tensor], inst_ids: Tensor,
+                   lut: Tensor, logits_out: Optional[Tensor], status: Tensor) -> None:
+    _cuda(feats, weight, bias, inst_ids, lut, logits_out, status)
+    N, Cin = feats.shape
+    check(_cabi.lib().ldiff_cell_classify(_ptr(feats), _ptr(weight), _ptr(bias), _ptr(inst_ids),
+                                          _ptr(lut), lut.numel(), _ptr(logits_out), N, Cin,
+                                          weight.shape[0], _dt(feats), _ptr(status), _stream(feats)))
+
+
+@torch.library.custom_op("ldiff::lut_paint", mutates_args=("mask", "status"))
+def _lut_paint(inst: Tensor, lut: Tensor, mask: Tensor, status: Tensor) -> None:
+    _cuda(inst, lut, mask, status)
+    B = inst.shape[0]
+    n = inst[0].numel()
+    lut_stride = lut.stride(0) if lut.dim() == 2 else 0
+    check(_cabi.lib().ldiff_lut_paint(_ptr(inst), _ptr(lut), _ptr(mask), n, B, lut.shape[-1],
+                                      lut_stride, _ptr(status), _stream(inst)))
+
+
+@torch.library.custom_op("ldiff::argmax_channels", mutates_args=("out",))
+def _argmax_channels(x: Tensor, out: Tensor) -> None:
+    _cuda(x, out)
+    B, K = x.shape[:2]
+    check(_cabi.lib().ldiff_argmax_channels(_ptr(x), _ptr(out), B, K, x[0, 0].numel(), _dt(x),
+                                            _stream(x)))
+
+
+@torch.library.custom_op("ldiff::confusion_hist", mutates_args=("C", "status"))
+def _confusion_hist(pred: Tensor, gt: Tensor, gt_lut: Optional[Tensor], C: Tensor, K: int,
+                    status: Tensor) -> None:
+    _cuda(pred, gt, gt_lut, C, status)
+    check(_cabi.lib().ldiff_confusion_hist(_ptr(pred), _ptr(gt), _ptr(gt_lut), _ptr(C), pred.numel(),
+                                           K, _ptr(status), _stream(pred)))
+
+
+@torch.library.custom_op("ldiff::labels_to_u8", mutates_args=("out",))
+def _labels_to_u8(x: Tensor, out: Tensor) -> None:
+    _cuda(x, out)
+    check(_cabi.lib().ldiff_labels_to_u8(_ptr(x), _ptr(out), x.numel(), _stream(x)))
+
+
+# ---------------------------------------------------------------------------
+# functional wrappers
+# ---------------------------------------------------------------------------
+
+def laplace_qsample(x: Tensor, b: float, *, noise: Optional[Tensor] = None, u: Optional[Tensor] = None,
+                    seed: int = 0, offset: int = 0, return_noise: bool = False, out: Optional[Tensor] = None):
+    """noisy = x + Laplace(0, b) noise  (ldiffusion.py:234-237).
+
+    ``noise``: injected noise tensor (parity mode);  ``u``: injected uniforms in
+    (-1, 1);  otherwise Philox(seed, offset).  Element i of the flattened tensor
+    consumes word i%4 of Philox counter ``offset + i//4``: advance ``offset`` by
+    ``ceil(numel/4)`` between calls to continue the stream.
+    """
+    _dense(x, "x")
+    if noise is not None and u is not None:
+        raise ValueError("pass at most one of noise / u")
+    for t in (noise, u):
+        if t is not None and (t.shape != x.shape or t.dtype != x.dtype or not t.is_contiguous()):
+            raise ValueError("injected tensor must match x in shape, dtype and be contiguous")
+    out = torch.empty_like(x) if out is None else out
+    nz = torch.empty_like(x) if return_noise else None
+    torch.ops.ldiff.laplace_qsample(x, out, noise, u, nz, float(b), int(seed), int(offset))
+    return (out, nz) if return_noise else out
+
+
+def plms_step(sample: Tensor, eps: Sequence[Tensor], mode: int, sample_coeff: float, alpha_diff: float,
+              denom: float, out: Optional[Tensor] = None) -> Tensor:
+    """prev = sample_coeff*sample - (alpha_diff*eps_hat)/denom; eps[0] is the newest output."""
+    need = {0: 1, 1: 2, 2: 2, 3: 3, 4: 4}[mode]
+    if len(eps) < need:
+        raise ValueError(f"mode {mode} needs {need} model outputs")
+    eps = list(eps[:need])
+    _dense(sample, "sample")
+    for e in eps:
+        if e.shape != sample.shape or e.dtype != sample.dtype or not e.is_contiguous():
+            raise ValueError("model outputs must match the sample in shape, dtype and be contiguous")
+    out = torch.empty_like(sample) if out is None else out
+    torch.ops.ldiff.plms_step(sample, eps, mode, float(sample_coeff), float(alpha_diff), float(denom), out)
+    return out
+
+
+def decode_tail_gray(img: Tensor, *, want_rgb: bool = True, gray_out: Optional[Tensor] = None,
+                     want_gray: bool = True, rgb_out: Optional[Tensor] = None):
+    """[B,3,H,W] decoder output -> (uint8 RGB [B,H,W,3] | None, uint8 gray [B,H,W] | None).
+
+    ``gray_out`` may be a [B,H,W] view whose planes are dense (e.g. slot i of a
+    [B,n+1,H,W] pixel-vector tensor), so the per-step concat costs nothing.
+    """
+    if img.dim() != 4 or img.shape[1] != 3:
+        raise ValueError("img must be [B,3,H,W]")
+    _dense(img, "img")
+    B, _, H, W = img.shape
+    rgb = rgb_out
+    if rgb is None and want_rgb:
+        rgb = torch.empty((B, H, W, 3), dtype=torch.uint8, device=img.device)
+    gray = gray_out
+    if gray is None and want_gray:
+        gray = torch.empty((B, H, W), dtype=torch.uint8, device=img.device)
+    if gray is not None:
+        if gray.shape != (B, H, W) or gray.dtype != torch.uint8 or (H * W and gray.stride()[1:] != (W, 1)):
+            raise ValueError("gray_out must be uint8 [B,H,W] with dense planes")
+    if rgb is None and gray is None:
+        raise ValueError("nothing to compute")
+    torch.ops.ldiff.decode_tail_gray(img, rgb, gray)
+    return rgb, gray
+
+
+def bilinear_lift(src: Tensor, size, *, out: Optional[Tensor] = None, out_channel: int = 0,
+                  gray: bool = False, out_dtype=None) -> Tensor:
+    """F.interpolate(src, size, mode='bilinear', align_corners=False) [+ weighted
+    gray], written into channels of ``out`` ([B,Ctot,H,W]) starting at ``out_channel``."""
+    if src.dim() != 4:
+        raise ValueError("src must be [B,C,h,w]")
+    if src.stride(3) != 1 or src.stride(2) != src.shape[3]:
+        raise ValueError("src planes must be dense")
+    B, C = src.shape[:2]
+    H, W = size
+    if out is None:
+        out = torch.empty((B, 1 if gray else C, H, W), dtype=out_dtype or src.dtype, device=src.device)
+    _dense(out, "out")
+    if out.shape[0] != B or out.shape[2:] != (H, W):
+        raise ValueError("out must be [B,Ctot,H,W]")
+    torch.ops.ldiff.bilinear_lift(src, out, out_channel, gray)
+    return out
+
+
+def head_logits(feat: Tensor, weight: Tensor, bias: Optional[Tensor] = None) -> Tensor:
+    """1x1 conv Cin->K (conductor.py:127): feat [B,Cin,h,w] -> fp32 logits [B,K,h,w]."""
+    _dense(feat, "feat"); _dense(weight, "weight")
+    if weight.dtype != feat.dtype:
+        raise ValueError("weight dtype must match feat")
+    B, Cin, h, w = feat.shape
+    K = weight.shape[0]
+    if weight.shape[1] != Cin:
+        raise ValueError("weight must be [K,Cin]")
+    bias = None if bias is None else bias.float().contiguous()
+    logits = torch.empty((B, K, h, w), dtype=torch.float32, device=feat.device)
+    torch.ops.ldiff.head_logits(feat, weight.reshape(K, Cin), bias, logits)
+    return logits
+
+
+def lift_argmax(logits: Tensor, size) -> Tensor:
+    """argmax(softmax(F.interpolate(logits, size)), 1) as uint8 [B,H,W]
+    (conductor.py:135 + segmentor.py:536) without materialising the lift."""
+    _dense(logits, "logits")
+    if logits.dtype != torch.float32:
+        raise TypeError("logits must be fp32")
+    mask = torch.empty((logits.shape[0], size[0], size[1]), dtype=torch.uint8, device=logits.device)
+    torch.ops.ldiff.lift_argmax(logits, mask)
+    return mask
+
+
+def head_argmax(feat: Tensor, weight: Tensor, bias: Optional[Tensor], size, return_logits: bool = False):
+    logits = head_logits(feat, weight, bias)
+    mask = lift_argmax(logits, size)
+    return (mask, logits) if return_logits else mask
+
+
+def cell_classify(inst_feats: Tensor, weight: Tensor, bias: Optional[Tensor], inst_ids: Tensor,
+                  lut_size: int, *, lut: Optional[Tensor] = None, return_logits: bool = False):
+    """conductor.py:218-221 -> class LUT (uint8 [lut_size], lut[0] = background)."""
+    _dense(inst_feats, "inst_feats"); _dense(weight, "weight")
+    if inst_ids.dtype != torch.int32:
+        inst_ids = inst_ids.to(torch.int32)
+    if lut is None:
+        lut = torch.zeros(lut_size, dtype=torch.uint8, device=inst_feats.device)
+    N, K = inst_feats.shape[0], weight.shape[0]
+    lo = torch.empty((N, K), dtype=torch.float32, device=inst_feats.device) if return_logits else None
+    bias = None if bias is None else bias.float().contiguous()
+    torch.ops.ldiff.cell_classify(inst_feats, weight, bias, inst_ids.contiguous(), lut, lo,
+                                  status_word(inst_feats.device))
+    return (lut, lo) if return_logits else lut
+
+
+def lut_paint(inst: Tensor, lut: Tensor, out: Optional[Tensor] = None) -> Tensor:
+    """mask[b,y,x] = lut[b][inst[b,y,x]] (conductor.py:224-231 + segmentor.py:536)."""
+    if inst.dtype != torch.int32:
+        raise TypeError("instance map must be int32")
+    if inst.dim() == 2:
+        inst = inst.unsqueeze(0)
+    _dense(inst, "inst"); _dense(lut, "lut")
+    if lut.dim() == 2 and lut.shape[0] != inst.shape[0]:
+        raise ValueError("per-image LUTs must be [B,lut_size]")
+    mask = torch.empty(inst.shape, dtype=torch.uint8, device=inst.device) if out is None else out
+    torch.ops.ldiff.lut_paint(inst, lut, mask, status_word(inst.device))
+    return mask
+
+
+def argmax_channels(x: Tensor) -> Tensor:
+    """torch.argmax(x, dim=1) (first maximum) as uint8, for [B,K,...] inputs."""
+    _dense(x, "x")
+    if x.shape[1] > 255:
+        raise ValueError("at most 255 classes")
+    out = torch.empty((x.shape[0],) + tuple(x.shape[2:]), dtype=torch.uint8, device=x.device)
+    torch.ops.ldiff.argmax_channels(x, out)
+    return out
+
+
+def labels_to_u8(x: Tensor) -> Tensor:
+    if x.dtype == torch.uint8:
+        return x.contiguous()
+    if x.dtype != torch.int64:
+        x = x.to(torch.int64)
+    x = x.contiguous()
+    out = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    torch.ops.ldiff.labels_to_u8(x, out)
+    return out
+
+
+def confusion_hist(pred: Tensor, gt: Tensor, num_classes: int, *, out: Optional[Tensor] = None,
+                   gt_lut: Optional[Tensor] = None) -> Tensor:
+    """Accumulates C[(K+1),K] (int64) += histogram of (gt, pred) pairs; uint8 inputs."""
+    if pred.dtype != torch.uint8 or gt.dtype != torch.uint8:
+        raise TypeError("pred and gt must be uint8 label maps")
+    if pred.numel() != gt.numel():
+        raise ValueError("pred and gt must have the same number of pixels")
+    _dense(pred, "pred"); _dense(gt, "gt")
+    K = int(num_classes)
+    if out is None:
+        out = torch.zeros((K + 1, K), dtype=torch.int64, device=pred.device)
+    elif out.shape != (K + 1, K) or out.dtype != torch.int64 or not out.is_contiguous():
+        raise ValueError("out must be a contiguous int64 [(K+1),K] tensor")
+    if gt_lut is not None and (gt_lut.dtype != torch.uint8 or gt_lut.numel() != 256):
+        raise ValueError("gt_lut must be 256 uint8 entries")
+    torch.ops.ldiff.confusion_hist(pred, gt, gt_lut, out, K, status_word(pred.device))
+    return out

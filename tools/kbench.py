@@ -1,0 +1,98 @@
+"""Per-kernel micro-benchmark at the BASELINE config-2 shapes (dev tool, not the bench contract).
+
+CUDA-event timing over many back-to-back launches on rotating buffers larger than L2."""
+import json
+import sys
+import os
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from ldiffusion_b200 import ops, LaplacePLMSScheduler
+
+PEAK = 6546.2
+
+
+def timeit(fn, nbuf, iters=50, warm=5):
+    for i in range(warm):
+        fn(i % nbuf)
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for i in range(iters):
+        fn(i % nbuf)
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / iters * 1e3     # us
+
+
+def main():
+    dev = "cuda"
+    res = {}
+    for dt, s in ((torch.float32, 4), (torch.bfloat16, 2)):
+        tag = "f32" if s == 4 else "bf16"
+        B = 8
+        nb = 6
+        imgs = [torch.empty(B, 3, 1024, 1024, device=dev, dtype=dt).uniform_(-1.2, 1.2) for _ in range(nb)]
+        planes = torch.empty(B, 6, 1024, 1024, dtype=torch.uint8, device=dev)
+        rgb = torch.empty(B, 1024, 1024, 3, dtype=torch.uint8, device=dev)
+        us = timeit(lambda i: ops.decode_tail_gray(imgs[i], want_rgb=False, gray_out=planes[:, i % 5]), nb)
+        byt = B * 1024 * 1024 * (3 * s + 1)
+        res[f"decode_tail_gray_{tag}"] = (us, byt / us / 1e3, byt / us / 1e3 / PEAK)
+        us = timeit(lambda i: ops.decode_tail_gray(imgs[i], rgb_out=rgb, gray_out=planes[:, i % 5]), nb)
+        byt = B * 1024 * 1024 * (3 * s + 4)
+        res[f"decode_tail_gray_rgb_{tag}"] = (us, byt / us / 1e3, byt / us / 1e3 / PEAK)
+        # bilinear up 64->1024
+        src = torch.randn(B, 3, 64, 64, device=dev).to(dt)
+        outs = [torch.empty(B, 3, 1024, 1024, device=dev, dtype=dt) for _ in range(4)]
+        us = timeit(lambda i: ops.bilinear_lift(src, (1024, 1024), out=outs[i]), 4)
+        byt = B * 3 * 1024 * 1024 * s
+        res[f"lift_up_{tag}"] = (us, byt / us / 1e3, byt / us / 1e3 / PEAK)
+        fc = torch.empty(B, 5, 64, 64, device=dev, dtype=dt)
+        us = timeit(lambda i: ops.bilinear_lift(imgs[i], (64, 64), out=fc, out_channel=i % 5, gray=True), nb)
+        res[f"lift_down_gray_{tag}"] = (us, 0, 0)
+        # sampler at config shape and at a scaled-up shape (roofline probe)
+        for name, shape in (("cfg", (8, 4, 128, 128)), ("big", (1024, 4, 128, 128))):
+            x = [torch.randn(shape, device=dev).to(dt) for _ in range(3 if name == "big" else 2)]
+            e = [torch.randn(shape, device=dev).to(dt) for _ in range(4)]
+            o = torch.empty_like(x[0])
+            n = x[0].numel()
+            us = timeit(lambda i: ops.laplace_qsample(x[i % len(x)], 0.9, seed=1, offset=i, out=o), len(x))
+            res[f"laplace_{name}_{tag}"] = (us, 2 * n * s / us / 1e3, 2 * n * s / us / 1e3 / PEAK)
+            us = timeit(lambda i: ops.plms_step(x[i % len(x)], e, 4, 1.01, 0.02, 0.9, out=o), len(x))
+            res[f"plms4_{name}_{tag}"] = (us, 6 * n * s / us / 1e3, 6 * n * s / us / 1e3 / PEAK)
+    # head
+    feat = torch.randn(8, 256, 32, 32, device=dev).bfloat16()
+    w = (torch.randn(11, 256, device=dev) / 16).bfloat16()
+    us = timeit(lambda i: ops.head_logits(feat, w, None), 1)
+    res["head_logits_bf16"] = (us, 0, 0)
+    logits = ops.head_logits(feat, w, None)
+    us = timeit(lambda i: ops.lift_argmax(logits, (1024, 1024)), 1)
+    res["lift_argmax"] = (us, 8 * 1024 * 1024 / us / 1e3, 8 * 1024 * 1024 / us / 1e3 / PEAK)
+    # paint + confusion
+    inst = torch.randint(0, 800, (8, 1024, 1024), device=dev, dtype=torch.int32)
+    lut = torch.randint(0, 11, (800,), device=dev, dtype=torch.uint8)
+    us = timeit(lambda i: ops.lut_paint(inst, lut), 1)
+    res["lut_paint"] = (us, 8 * 1024 * 1024 * 5 / us / 1e3, 8 * 1024 * 1024 * 5 / us / 1e3 / PEAK)
+    import numpy as np
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+    from test_gpu_head_metrics import _blob_labels
+    for nimg in (8, 64):
+        gt = torch.from_numpy(_blob_labels((nimg, 1024, 1024), 11, 1)).to(dev)
+        pr = torch.from_numpy(_blob_labels((nimg, 1024, 1024), 11, 2, 0)).to(dev)
+        C = torch.zeros(12, 11, dtype=torch.int64, device=dev)
+        us = timeit(lambda i: ops.confusion_hist(pr.view(-1), gt.view(-1), 11, out=C), 1)
+        byt = 2 * nimg * 1024 * 1024
+        res[f"confusion_blobs_{nimg}"] = (us, byt / us / 1e3, byt / us / 1e3 / PEAK)
+    rnd_p = torch.randint(0, 11, (8 * 1024 * 1024,), device=dev, dtype=torch.uint8)
+    rnd_g = torch.randint(0, 11, (8 * 1024 * 1024,), device=dev, dtype=torch.uint8)
+    C = torch.zeros(12, 11, dtype=torch.int64, device=dev)
+    us = timeit(lambda i: ops.confusion_hist(rnd_p, rnd_g, 11, out=C), 1)
+    res["confusion_random_8"] = (us, 2 * 8 * 1024 * 1024 / us / 1e3, 2 * 8 * 1024 * 1024 / us / 1e3 / PEAK)
+    for k, (us, gbs, fr) in res.items():
+        print(f"{k:32s} {us:10.2f} us  {gbs:9.1f} GB/s  {fr:6.3f} of measured peak")
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(res, open("gpurun_out/kbench.json", "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
