@@ -182,7 +182,7 @@ def evaluate(image_dir, label_dir, num_classes, save_dir="./eval_results", devic
     if len(image_files) != len(label_files):
         raise ValueError(f"The number of images: {len(image_files)}, The number of labels: "
                          f"{len(label_files)}, they must be equal.")
-    device = torch.device(device or ("cuda", torch.cuda.current_device()))
+    device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
     K = int(num_classes)
     mats = torch.zeros((len(image_files), K + 1, K), dtype=torch.int64, device=device)
     for i, (img_path, lbl_path) in enumerate(zip(image_files, label_files)):

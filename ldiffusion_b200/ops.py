@@ -70,10 +70,13 @@ def check_status(device):
 
 
 # ---------------------------------------------------------------------------
-# custom ops (out-variants: the wrapper below allocates)
+# raw out-variant entry points: one ctypes call each.  They are registered as
+# torch.library custom ops (torch.ops.ldiff.*) for callers that want a
+# dispatcher-visible op; the functional wrappers below call them directly,
+# because the dispatcher round trip costs ~25 us per call on the host and the
+# latent-sized kernels run for 2-3 us.
 # ---------------------------------------------------------------------------
 
-@torch.library.custom_op("ldiff::laplace_qsample", mutates_args=("out", "noise_out"))
 def _laplace_qsample(x: Tensor, out: Tensor, noise: Optional[Tensor], u: Optional[Tensor],
                      noise_out: Optional[Tensor], b: float, seed: int, offset: int) -> None:
     _cuda(x, out, noise, u, noise_out)
@@ -81,7 +84,6 @@ def _laplace_qsample(x: Tensor, out: Tensor, noise: Optional[Tensor], u: Optiona
                                             b, seed, offset, x.numel(), _dt(x), _stream(x)))
 
 
-@torch.library.custom_op("ldiff::plms_step", mutates_args=("out",))
 def _plms_step(sample: Tensor, eps: Sequence[Tensor], mode: int, sample_coeff: float,
                alpha_diff: float, denom: float, out: Tensor) -> None:
     _cuda(sample, out, *eps)
@@ -91,7 +93,6 @@ def _plms_step(sample: Tensor, eps: Sequence[Tensor], mode: int, sample_coeff: f
                                       _stream(sample)))
 
 
-@torch.library.custom_op("ldiff::decode_tail_gray", mutates_args=("rgb", "gray"))
 def _decode_tail_gray(img: Tensor, rgb: Optional[Tensor], gray: Optional[Tensor]) -> None:
     _cuda(img, rgb, gray)
     B, _, H, W = img.shape
@@ -100,7 +101,6 @@ def _decode_tail_gray(img: Tensor, rgb: Optional[Tensor], gray: Optional[Tensor]
                                              _dt(img), _stream(img)))
 
 
-@torch.library.custom_op("ldiff::bilinear_lift", mutates_args=("dst",))
 def _bilinear_lift(src: Tensor, dst: Tensor, dst_channel: int, gray: bool) -> None:
     _cuda(src, dst)
     B, C, h, w = src.shape
@@ -110,7 +110,6 @@ def _bilinear_lift(src: Tensor, dst: Tensor, dst_channel: int, gray: bool) -> No
                                           1 if gray else 0, _stream(src)))
 
 
-@torch.library.custom_op("ldiff::head_logits", mutates_args=("logits",))
 def _head_logits(feat: Tensor, weight: Tensor, bias: Optional[Tensor], logits: Tensor) -> None:
     _cuda(feat, weight, bias, logits)
     B, Cin = feat.shape[:2]
@@ -119,7 +118,6 @@ def _head_logits(feat: Tensor, weight: Tensor, bias: Optional[Tensor], logits: T
                                         weight.shape[0], hw, _dt(feat), _stream(feat)))
 
 
-@torch.library.custom_op("ldiff::lift_argmax", mutates_args=("mask",))
 def _lift_argmax(logits: Tensor, mask: Tensor) -> None:
     _cuda(logits, mask)
     B, K, h, w = logits.shape
@@ -127,7 +125,6 @@ def _lift_argmax(logits: Tensor, mask: Tensor) -> None:
     check(_cabi.lib().ldiff_lift_argmax(_ptr(logits), _ptr(mask), B, K, h, w, H, W, _stream(logits)))
 
 
-@torch.library.custom_op("ldiff::cell_classify", mutates_args=("lut", "logits_out", "status"))
 def _cell_classify(feats: Tensor, weight: Tensor, bias: Optional[Tensor], inst_ids: Tensor,
                    lut: Tensor, logits_out: Optional[Tensor], status: Tensor) -> None:
     _cuda(feats, weight, bias, inst_ids, lut, logits_out, status)
@@ -137,7 +134,6 @@ def _cell_classify(feats: Tensor, weight: Tensor, bias: Optional[Tensor], inst_i
                                           weight.shape[0], _dt(feats), _ptr(status), _stream(feats)))
 
 
-@torch.library.custom_op("ldiff::lut_paint", mutates_args=("mask", "status"))
 def _lut_paint(inst: Tensor, lut: Tensor, mask: Tensor, status: Tensor) -> None:
     _cuda(inst, lut, mask, status)
     B = inst.shape[0]
@@ -147,7 +143,6 @@ def _lut_paint(inst: Tensor, lut: Tensor, mask: Tensor, status: Tensor) -> None:
                                       lut_stride, _ptr(status), _stream(inst)))
 
 
-@torch.library.custom_op("ldiff::argmax_channels", mutates_args=("out",))
 def _argmax_channels(x: Tensor, out: Tensor) -> None:
     _cuda(x, out)
     B, K = x.shape[:2]
@@ -155,7 +150,6 @@ def _argmax_channels(x: Tensor, out: Tensor) -> None:
                                             _stream(x)))
 
 
-@torch.library.custom_op("ldiff::confusion_hist", mutates_args=("C", "status"))
 def _confusion_hist(pred: Tensor, gt: Tensor, gt_lut: Optional[Tensor], C: Tensor, K: int,
                     status: Tensor) -> None:
     _cuda(pred, gt, gt_lut, C, status)
@@ -163,10 +157,22 @@ def _confusion_hist(pred: Tensor, gt: Tensor, gt_lut: Optional[Tensor], C: Tenso
                                            K, _ptr(status), _stream(pred)))
 
 
-@torch.library.custom_op("ldiff::labels_to_u8", mutates_args=("out",))
 def _labels_to_u8(x: Tensor, out: Tensor) -> None:
     _cuda(x, out)
     check(_cabi.lib().ldiff_labels_to_u8(_ptr(x), _ptr(out), x.numel(), _stream(x)))
+
+
+torch.library.custom_op("ldiff::laplace_qsample", mutates_args=("out", "noise_out"))(_laplace_qsample)
+torch.library.custom_op("ldiff::plms_step", mutates_args=("out",))(_plms_step)
+torch.library.custom_op("ldiff::decode_tail_gray", mutates_args=("rgb", "gray"))(_decode_tail_gray)
+torch.library.custom_op("ldiff::bilinear_lift", mutates_args=("dst",))(_bilinear_lift)
+torch.library.custom_op("ldiff::head_logits", mutates_args=("logits",))(_head_logits)
+torch.library.custom_op("ldiff::lift_argmax", mutates_args=("mask",))(_lift_argmax)
+torch.library.custom_op("ldiff::cell_classify", mutates_args=("lut", "logits_out", "status"))(_cell_classify)
+torch.library.custom_op("ldiff::lut_paint", mutates_args=("mask", "status"))(_lut_paint)
+torch.library.custom_op("ldiff::argmax_channels", mutates_args=("out",))(_argmax_channels)
+torch.library.custom_op("ldiff::confusion_hist", mutates_args=("C", "status"))(_confusion_hist)
+torch.library.custom_op("ldiff::labels_to_u8", mutates_args=("out",))(_labels_to_u8)
 
 
 # ---------------------------------------------------------------------------
@@ -190,7 +196,7 @@ def laplace_qsample(x: Tensor, b: float, *, noise: Optional[Tensor] = None, u: O
             raise ValueError("injected tensor must match x in shape, dtype and be contiguous")
     out = torch.empty_like(x) if out is None else out
     nz = torch.empty_like(x) if return_noise else None
-    torch.ops.ldiff.laplace_qsample(x, out, noise, u, nz, float(b), int(seed), int(offset))
+    _laplace_qsample(x, out, noise, u, nz, float(b), int(seed), int(offset))
     return (out, nz) if return_noise else out
 
 
@@ -206,7 +212,7 @@ def plms_step(sample: Tensor, eps: Sequence[Tensor], mode: int, sample_coeff: fl
         if e.shape != sample.shape or e.dtype != sample.dtype or not e.is_contiguous():
             raise ValueError("model outputs must match the sample in shape, dtype and be contiguous")
     out = torch.empty_like(sample) if out is None else out
-    torch.ops.ldiff.plms_step(sample, eps, mode, float(sample_coeff), float(alpha_diff), float(denom), out)
+    _plms_step(sample, eps, mode, float(sample_coeff), float(alpha_diff), float(denom), out)
     return out
 
 
@@ -232,7 +238,7 @@ def decode_tail_gray(img: Tensor, *, want_rgb: bool = True, gray_out: Optional[T
             raise ValueError("gray_out must be uint8 [B,H,W] with dense planes")
     if rgb is None and gray is None:
         raise ValueError("nothing to compute")
-    torch.ops.ldiff.decode_tail_gray(img, rgb, gray)
+    _decode_tail_gray(img, rgb, gray)
     return rgb, gray
 
 
@@ -251,7 +257,7 @@ def bilinear_lift(src: Tensor, size, *, out: Optional[Tensor] = None, out_channe
     _dense(out, "out")
     if out.shape[0] != B or out.shape[2:] != (H, W):
         raise ValueError("out must be [B,Ctot,H,W]")
-    torch.ops.ldiff.bilinear_lift(src, out, out_channel, gray)
+    _bilinear_lift(src, out, out_channel, gray)
     return out
 
 
@@ -266,7 +272,7 @@ def head_logits(feat: Tensor, weight: Tensor, bias: Optional[Tensor] = None) -> 
         raise ValueError("weight must be [K,Cin]")
     bias = None if bias is None else bias.float().contiguous()
     logits = torch.empty((B, K, h, w), dtype=torch.float32, device=feat.device)
-    torch.ops.ldiff.head_logits(feat, weight.reshape(K, Cin), bias, logits)
+    _head_logits(feat, weight.reshape(K, Cin), bias, logits)
     return logits
 
 
@@ -277,7 +283,7 @@ def lift_argmax(logits: Tensor, size) -> Tensor:
     if logits.dtype != torch.float32:
         raise TypeError("logits must be fp32")
     mask = torch.empty((logits.shape[0], size[0], size[1]), dtype=torch.uint8, device=logits.device)
-    torch.ops.ldiff.lift_argmax(logits, mask)
+    _lift_argmax(logits, mask)
     return mask
 
 
@@ -298,7 +304,7 @@ def cell_classify(inst_feats: Tensor, weight: Tensor, bias: Optional[Tensor], in
     N, K = inst_feats.shape[0], weight.shape[0]
     lo = torch.empty((N, K), dtype=torch.float32, device=inst_feats.device) if return_logits else None
     bias = None if bias is None else bias.float().contiguous()
-    torch.ops.ldiff.cell_classify(inst_feats, weight, bias, inst_ids.contiguous(), lut, lo,
+    _cell_classify(inst_feats, weight, bias, inst_ids.contiguous(), lut, lo,
                                   status_word(inst_feats.device))
     return (lut, lo) if return_logits else lut
 
@@ -313,7 +319,7 @@ def lut_paint(inst: Tensor, lut: Tensor, out: Optional[Tensor] = None) -> Tensor
     if lut.dim() == 2 and lut.shape[0] != inst.shape[0]:
         raise ValueError("per-image LUTs must be [B,lut_size]")
     mask = torch.empty(inst.shape, dtype=torch.uint8, device=inst.device) if out is None else out
-    torch.ops.ldiff.lut_paint(inst, lut, mask, status_word(inst.device))
+    _lut_paint(inst, lut, mask, status_word(inst.device))
     return mask
 
 
@@ -323,7 +329,7 @@ def argmax_channels(x: Tensor) -> Tensor:
     if x.shape[1] > 255:
         raise ValueError("at most 255 classes")
     out = torch.empty((x.shape[0],) + tuple(x.shape[2:]), dtype=torch.uint8, device=x.device)
-    torch.ops.ldiff.argmax_channels(x, out)
+    _argmax_channels(x, out)
     return out
 
 
@@ -334,7 +340,7 @@ def labels_to_u8(x: Tensor) -> Tensor:
         x = x.to(torch.int64)
     x = x.contiguous()
     out = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
-    torch.ops.ldiff.labels_to_u8(x, out)
+    _labels_to_u8(x, out)
     return out
 
 
@@ -353,5 +359,5 @@ def confusion_hist(pred: Tensor, gt: Tensor, num_classes: int, *, out: Optional[
         raise ValueError("out must be a contiguous int64 [(K+1),K] tensor")
     if gt_lut is not None and (gt_lut.dtype != torch.uint8 or gt_lut.numel() != 256):
         raise ValueError("gt_lut must be 256 uint8 entries")
-    torch.ops.ldiff.confusion_hist(pred, gt, gt_lut, out, K, status_word(pred.device))
+    _confusion_hist(pred, gt, gt_lut, out, K, status_word(pred.device))
     return out

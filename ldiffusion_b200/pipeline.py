@@ -1,0 +1,162 @@
+"""One pass of the whole hot path over a batch of patches.
+
+``HotPath`` owns every intermediate buffer (so a pass allocates nothing and can
+be captured into a CUDA graph) and strings the stages together the way the
+reference's loops do, with the SD-v1.5 UNet / VAE calls replaced by the tensors
+they would have produced (``eps[i]``, ``decoded[i]``): those are cuDNN library
+calls outside the scope of this package and are timed separately.
+
+Stages per batch (reference lines in brackets):
+
+1. for each of the n sampling steps i (``set_timesteps(n-1)``,
+   pixel_latent_vector.py:74-83):
+   * Laplace forward noising of the clean latents at t_i    [ldiffusion.py:233-237]
+   * PLMS reverse update with eps_i                          [segmentor.py:102-104]
+   * decode tail of decoded_i -> gray plane i of the pixel
+     vectors (+ uint8 RGB on the last step)                  [pixel_latent_vector.py:80-93]
+   * bilinear 64x64 + weighted gray -> channel i of the
+     training-path feature tensor                            [ldiffusion.py:240-247]
+2. label bilinear down + uint8; last decode 64x64 -> HxW     [ldiffusion.py:224-226,251]
+3. tissue head: 1x1 conv -> lift -> argmax(softmax) mask     [conductor.py:127,135; segmentor.py:536]
+4. cell head: instance classifier -> LUT -> painted mask     [conductor.py:218-231]
+5. confusion matrices of both masks vs gt                    [utils.py:55-104; evaluate.py:11-45]
+"""
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+
+from . import ops
+from .scheduler import LaplacePLMSScheduler
+
+
+@dataclass
+class HotPathInputs:
+    """Everything one pass consumes (device tensors)."""
+    latents: torch.Tensor            # [B,4,H/8,W/8] VAE-encoded clean latents (storage dtype)
+    eps: List[torch.Tensor]          # n x [B,4,H/8,W/8] UNet outputs
+    decoded: List[torch.Tensor]      # n x [B,3,H,W] VAE decoder outputs
+    head_feat: torch.Tensor          # [B,256,h,w] tissue decoder features
+    inst_map: torch.Tensor           # int32 [B,H,W] Cellpose instance ids
+    inst_feats: torch.Tensor         # [B,N,256] pooled instance features
+    gt: torch.Tensor                 # uint8 [B,H,W] ground-truth classes
+
+    def tensors(self):
+        return [self.latents, *self.eps, *self.decoded, self.head_feat, self.inst_map, self.inst_feats, self.gt]
+
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in self.tensors())
+
+
+class HotPath:
+    def __init__(self, batch: int, height: int, width: int, num_classes: int, num_steps: int = 5,
+                 dtype=torch.bfloat16, device="cuda", head_hw=(32, 32), feat_size=(64, 64),
+                 n_instances: int = 800, head_channels: int = 256, seed: int = 1234):
+        dev = torch.device(device)
+        self.B, self.H, self.W, self.K, self.n = batch, height, width, num_classes, num_steps
+        self.dtype, self.device = dtype, dev
+        self.feat_size, self.head_hw, self.n_inst = feat_size, head_hw, n_instances
+        self.seed = seed
+        self.scheduler = LaplacePLMSScheduler()
+        lat = (batch, 4, height // 8, width // 8)
+        self.lat_elems = batch * 4 * (height // 8) * (width // 8)
+        e = lambda *s, dt=dtype: torch.empty(s, dtype=dt, device=dev)          # noqa: E731
+        self.noisy = [e(*lat) for _ in range(num_steps)]
+        self.lat = [e(*lat) for _ in range(num_steps)]
+        self.planes = e(batch, num_steps + 1, height, width, dt=torch.uint8)
+        self.rgb = e(batch, height, width, 3, dt=torch.uint8)
+        self.featcat = e(batch, num_steps, *feat_size)
+        self.label_small = e(batch, 1, *feat_size, dt=torch.uint8)
+        self.rgb_small = e(batch, 3, *feat_size)
+        self.rgb_up = e(batch, 3, height, width)
+        self.logits = e(batch, num_classes, *head_hw, dt=torch.float32)
+        self.mask_tissue = e(batch, height, width, dt=torch.uint8)
+        self.lut = torch.zeros((batch, n_instances + 1), dtype=torch.uint8, device=dev)
+        self.mask_cell = e(batch, height, width, dt=torch.uint8)
+        self.C = torch.zeros((2, num_classes + 1, num_classes), dtype=torch.int64, device=dev)
+        self.inst_ids = torch.arange(1, n_instances + 1, dtype=torch.int32, device=dev)
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        self.head_w = (torch.randn(num_classes, head_channels, generator=g) / 16).to(dev, dtype)
+        self.head_b = torch.zeros(num_classes, device=dev)
+        self.cell_w = (torch.randn(num_classes, head_channels, generator=g) / 16).to(dev, dtype)
+        self.cell_b = torch.zeros(num_classes, device=dev)
+        self.status = ops.status_word(dev)
+
+    # number of ldiff kernels one pass launches
+    def launches_per_pass(self) -> int:
+        return 4 * self.n + 3 + 2 + (self.B + 1) + 2
+
+    def run(self, inp: HotPathInputs):
+        """Enqueue one pass on the current stream; returns nothing (results live in
+        the preallocated buffers).  Graph-capturable: no allocation, no sync."""
+        n, sch = self.n, self.scheduler
+        sch.set_timesteps(n - 1)
+        ts = sch._host_timesteps
+        x = inp.latents
+        blocks = (self.lat_elems + 3) // 4
+        self.C.zero_()
+        for i in range(n):
+            t = ts[i]
+            ops.laplace_qsample(inp.latents, sch.laplace_scale(t), seed=self.seed, offset=i * blocks,
+                                out=self.noisy[i])
+            x = sch.step(inp.eps[i], t, x, out=self.lat[i]).prev_sample
+            last = i == n - 1
+            ops.decode_tail_gray(inp.decoded[i], want_rgb=False, rgb_out=self.rgb if last else None,
+                                 gray_out=self.planes[:, i])
+            ops.bilinear_lift(inp.decoded[i], self.feat_size, out=self.featcat, out_channel=i, gray=True)
+        self.planes[:, n].copy_(inp.gt)                                    # label slot of the pixel vectors
+        ops.bilinear_lift(inp.gt.unsqueeze(1), self.feat_size, out=self.label_small)
+        ops.bilinear_lift(inp.decoded[n - 1], self.feat_size, out=self.rgb_small)
+        ops.bilinear_lift(self.rgb_small, (self.H, self.W), out=self.rgb_up)
+        # tissue head
+        ops._head_logits(inp.head_feat, self.head_w, self.head_b, self.logits)
+        ops._lift_argmax(self.logits, self.mask_tissue)
+        # cell head
+        for b in range(self.B):
+            ops._cell_classify(inp.inst_feats[b], self.cell_w, self.cell_b, self.inst_ids, self.lut[b], None,
+                               self.status)
+        ops.lut_paint(inp.inst_map, self.lut, out=self.mask_cell)
+        # metrics
+        ops.confusion_hist(self.mask_tissue.view(-1), inp.gt.view(-1), self.K, out=self.C[0])
+        ops.confusion_hist(self.mask_cell.view(-1), inp.gt.view(-1), self.K, out=self.C[1])
+
+    def results(self):
+        return {"latents": self.lat[-1], "noisy": self.noisy, "pixel_planes": self.planes, "rgb": self.rgb,
+                "featcat": self.featcat, "label_small": self.label_small, "rgb_up": self.rgb_up,
+                "logits": self.logits, "mask_tissue": self.mask_tissue, "mask_cell": self.mask_cell,
+                "confusion": self.C}
+
+
+def synth_inputs(batch, height, width, num_classes, num_steps=5, dtype=torch.bfloat16, device="cpu",
+                 head_hw=(32, 32), n_instances=800, seed=1234, pin=False) -> HotPathInputs:
+    """Seeded synthetic PUMA-shaped inputs: latents 5.5*N(0,1) (raw SD VAE-mean
+    scale), eps N(0,1), decoded U(-1.2,1.2), features N(0,1), ~n_instances square cells per patch,
+    gt 70% background + blobs of classes 1..K-1 + 0.1% 'other' (255) pixels."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    lat = (batch, 4, height // 8, width // 8)
+
+    def fin(t):
+        if pin and t.device.type == "cpu":
+            t = t.pin_memory()
+        return t.to(device) if str(device) != "cpu" else t
+
+    latents = fin((torch.randn(lat, generator=g) * 5.5).to(dtype))
+    eps = [fin(torch.randn(lat, generator=g).to(dtype)) for _ in range(num_steps)]
+    decoded = [fin(torch.empty(batch, 3, height, width).uniform_(-1.2, 1.2, generator=g).to(dtype))
+               for _ in range(num_steps)]
+    head_feat = fin(torch.randn(batch, 256, *head_hw, generator=g).to(dtype))
+    inst_feats = fin(torch.randn(batch, n_instances, 256, generator=g).to(dtype))
+    inst = torch.zeros(batch, height, width, dtype=torch.int32)
+    gt = torch.zeros(batch, height, width, dtype=torch.uint8)
+    side = max(4, int((0.3 * height * width / max(n_instances, 1)) ** 0.5))
+    ys = torch.randint(0, max(1, height - side), (batch, n_instances), generator=g)
+    xs = torch.randint(0, max(1, width - side), (batch, n_instances), generator=g)
+    cls = torch.randint(1, num_classes, (batch, n_instances), generator=g)
+    for b in range(batch):
+        for i in range(n_instances):
+            y, x = int(ys[b, i]), int(xs[b, i])
+            inst[b, y:y + side, x:x + side] = i + 1
+            gt[b, y:y + side, x:x + side] = int(cls[b, i])
+    other = torch.rand(batch, height, width, generator=g) < 0.001
+    gt[other] = 255
+    return HotPathInputs(latents, eps, decoded, head_feat, fin(inst), inst_feats, fin(gt))

@@ -1,0 +1,195 @@
+"""CPU: scheduler known answers, Philox known answers, and the spec tier of the
+oracle against golden outputs of the third-party code the reference calls."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import bilinear as obil
+from oracle import decode_tail as odt
+from oracle import head as ohead
+from oracle import laplace as olap
+from oracle._fp import fma32
+from oracle.scheduler import PNDMOracle, sample_loop
+
+Z = np.load(os.path.join(os.path.dirname(__file__), "golden", "chain_ops.npz"))
+
+
+# --- a-2: SURVEY.md 8(a-2) known-answer constants (parity otherwise unpinned) ---
+@pytest.mark.parametrize("n,head,length", [(1, [1], 1), (4, [751, 501, 501, 251, 1], 5),
+                                           (5, [801, 601, 601, 401, 201, 1], 6),
+                                           (10, [901, 801, 801, 701], 11), (50, [981, 961, 961, 941], 51)])
+def test_timesteps_known_answers(n, head, length):
+    s = PNDMOracle(); s.set_timesteps(n)
+    assert s.timesteps.tolist()[:len(head)] == head and len(s.timesteps) == length
+    assert s.timesteps.dtype == torch.int64 and int(s.timesteps[-1]) == 1
+
+
+@pytest.mark.parametrize("t,abar,b", [(0, 0.999149978, 0.0291551333), (1, 0.998296022, 0.0412792638),
+                                      (201, 0.752143085, 0.497852296), (401, 0.422881305, 0.759683311),
+                                      (601, 0.159816325, 0.916615307), (801, 0.0365464948, 0.981556714),
+                                      (981, 0.0057754959, 0.997108042)])
+def test_alpha_bar_and_laplace_scale_known_answers(t, abar, b):
+    s = PNDMOracle()
+    assert float(s.alphas_cumprod[t]) == pytest.approx(abar, rel=2e-7)
+    assert float(olap.laplace_scale(t, s)) == pytest.approx(b, rel=2e-7)
+    assert float(s.final_alpha_cumprod) == float(s.alphas_cumprod[0])
+
+
+def test_single_step_coefficients_known_answer():
+    """N=1: t=1 -> prev_t=-999 -> final alpha: prev = 1.0004276 x - 0.0121417809 eps."""
+    s = PNDMOracle(); s.set_timesteps(1)
+    assert float(s.step(torch.zeros(1), 1, torch.ones(1))) == pytest.approx(1.0004276, rel=1e-7)
+    s.set_timesteps(1)
+    assert float(s.step(torch.ones(1), 1, torch.zeros(1))) == pytest.approx(-0.0121417809, rel=1e-6)
+
+
+def test_plms_state_machine_quirks():
+    """Second timestep duplicated; call 1 averages with the stored eps, restarts from
+    the stashed sample and does not append to the history."""
+    s = PNDMOracle(); s.set_timesteps(4)
+    g = torch.Generator().manual_seed(0)
+    x0 = torch.randn(8, generator=g)
+    eps = [torch.randn(8, generator=g) for _ in range(5)]
+    x1 = s.step(eps[0], 751, x0)
+    assert len(s.ets) == 1 and s.cur_sample is x0
+    x2 = s.step(eps[1], 501, x1)
+    assert len(s.ets) == 1 and s.cur_sample is None           # eps[1] not stored
+    a_t, a_p = s.alphas_cumprod[751], s.alphas_cumprod[501]
+    eh = (eps[1] + eps[0]) / 2
+    want = (a_p / a_t) ** 0.5 * x0 - (a_p - a_t) * eh / (a_t * (1 - a_p) ** 0.5 + (a_t * (1 - a_t) * a_p) ** 0.5)
+    assert torch.equal(x2, want)
+    s.step(eps[2], 501, x2); assert len(s.ets) == 2
+    s.step(eps[3], 251, x2); assert len(s.ets) == 3
+    s.step(eps[4], 1, x2); assert len(s.ets) == 4
+    outs = sample_loop(x0, eps, 4)
+    assert len(outs) == 5 and torch.equal(outs[1], x2)
+
+
+def test_set_timesteps_resets_state():
+    s = PNDMOracle(); s.set_timesteps(4)
+    s.step(torch.zeros(2), 751, torch.ones(2))
+    s.set_timesteps(4)
+    assert s.ets == [] and s.counter == 0 and s.cur_sample is None
+    with pytest.raises(ValueError):
+        PNDMOracle().step(torch.zeros(1), 1, torch.zeros(1))
+
+
+# --- a-1 ---
+def test_philox_known_answers():
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for c, k, o in kat:
+        r = olap.philox4x32_10(np.array([c], np.uint32), np.array(k, np.uint32))[0]
+        assert tuple(int(x) for x in r) == o
+
+
+def test_philox_uniform_properties():
+    u = olap.philox_uniform_pm1(1 << 18, 99, 3)
+    assert u.dtype == np.float32 and np.abs(u).max() < 1 and np.abs(u).min() >= 2.0 ** -23
+    assert abs(float(u.mean())) < 5e-3 and abs(float(np.abs(u).mean()) - 0.5) < 5e-3
+    assert np.array_equal(olap.philox_uniform_pm1(100, 99, 3)[4:], olap.philox_uniform_pm1(96, 99, 4))
+
+
+def test_laplace_transform_matches_torch_distributions_golden():
+    got = olap.laplace_from_uniform_chain(torch.from_numpy(Z["u"]), torch.tensor(Z["b"]))
+    assert np.array_equal(got.numpy(), Z["noise"])
+    x = torch.ones(4096)
+    assert torch.equal(olap.qsample_injected(x, got), x + torch.from_numpy(Z["noise"]))
+
+
+def test_qsample_chain_statistics():
+    g = torch.Generator().manual_seed(0)
+    noisy, noise = olap.qsample_chain(torch.zeros(1 << 18), 601, generator=g)
+    b = float(olap.laplace_scale(601))
+    assert abs(float(noise.abs().mean()) / b - 1) < 1e-2 and torch.equal(noisy, noise)
+
+
+# --- exact fp32 fma emulation ---
+def test_fma32_is_correctly_rounded():
+    from fractions import Fraction
+    rng = np.random.default_rng(0)
+    n = 1500
+    a = rng.standard_normal(n).astype(np.float32)
+    b = rng.standard_normal(n).astype(np.float32)
+    c = np.where(np.arange(n) % 2 == 0, (-a * b * (1 + rng.standard_normal(n) * 1e-7)).astype(np.float32),
+                 (rng.standard_normal(n) * 2.0 ** rng.integers(-30, 30, n)).astype(np.float32))
+    r = fma32(a, b, c)
+    for i in range(n):
+        ex = Fraction(float(a[i])) * Fraction(float(b[i])) + Fraction(float(c[i]))
+        f = np.float32(float(ex))
+        cands = [np.nextafter(f, np.float32(-np.inf)), f, np.nextafter(f, np.float32(np.inf))]
+        d = [abs(Fraction(float(v)) - ex) for v in cands]
+        best = [v for v, dd in zip(cands, d) if dd == min(d)]
+        if len(best) > 1:
+            best = [v for v in best if (np.float32(v).view(np.uint32) & 1) == 0]
+        assert best[0] == r[i]
+
+
+# --- a-4 ---
+def test_bilinear_spec_matches_aten_golden():
+    assert np.array_equal(obil.lift_spec(Z["x_up"], (128, 128)), Z["up"])          # up: bit-exact
+    assert np.array_equal(obil.lift_spec(Z["x_odd"], (31, 40)), Z["odd"])          # odd sizes: bit-exact
+    dn = obil.lift_spec(Z["x_dn"], (8, 8))
+    assert np.allclose(dn, Z["dn"], rtol=1e-5, atol=1e-6)                          # down: <= 2 ulp
+    assert np.allclose(obil.gray_weighted_spec(dn), Z["gray"], rtol=1e-5, atol=1e-6)
+    assert np.array_equal(obil.gray_weighted_spec(Z["dn"]), Z["gray"])              # gray itself: bit-exact
+    assert np.array_equal(obil.label_down_spec(Z["lab"], (8, 8)), Z["lab_dn"])
+
+
+def test_bilinear_chain_live_vs_spec():
+    g = torch.Generator().manual_seed(3)
+    for shape, size in [((1, 2, 7, 5), (15, 22)), ((1, 1, 32, 32), (1024, 1024)), ((2, 3, 64, 64), (64, 64))]:
+        x = torch.randn(shape, generator=g)
+        assert np.array_equal(obil.lift_chain(x, size).numpy(), obil.lift_spec(x.numpy(), size))
+
+
+# --- a-5 ---
+def test_head_decision_spec_matches_torch_golden():
+    assert np.array_equal(ohead.lift_argmax_spec(Z["logits"], (256, 256)), Z["mask"])
+
+
+def test_softmax_argmax_spec_ties():
+    x = np.zeros((1, 5, 3), np.float32)
+    assert ohead.softmax_argmax_spec(x).tolist() == [[0, 0, 0]]
+    x[0, 3, 1] = 1e-3
+    assert ohead.softmax_argmax_spec(x).tolist() == [[0, 3, 0]]
+    y = np.array([[[0.1], [np.nextafter(np.float32(0.1), np.float32(1))], [0.0]]], np.float32)
+    got = ohead.softmax_argmax_spec(y)[0, 0]
+    p = torch.softmax(torch.from_numpy(y), 1)
+    assert got in (0, 1) and (got == 1 or p[0, 0, 0] == p[0, 1, 0])
+
+
+def test_cell_paint_lut_equals_reference_loop():
+    rng = np.random.default_rng(0)
+    inst = np.zeros((48, 48), np.int32)
+    for i in range(1, 9):
+        y, x = rng.integers(0, 40), rng.integers(0, 40)
+        inst[y:y + 6, x:x + 6] = i
+    ids, cls = [1, 2, 3, 5, 8], [4, 10, 1, 7, 2]
+    want = ohead.cell_paint_chain(inst, ids, cls, 11).numpy()
+    assert np.array_equal(ohead.cell_paint_spec(inst, ohead.cell_lut_spec(ids, cls, 9)), want)
+
+
+# --- a-3 ---
+def test_decode_tail_and_pil_gray_golden():
+    dec = torch.from_numpy(Z["dec"])
+    rgb = odt.decode_tail_chain(dec)
+    assert np.array_equal(rgb, Z["rgb"])
+    assert np.array_equal(odt.gray_spec(rgb)[0], Z["pil_gray"])
+    assert np.array_equal(odt.gray_chain(rgb)[0], Z["pil_gray"])
+    assert np.array_equal(odt.decode_tail_chain(dec.bfloat16()), Z["rgb_bf16"])
+
+
+def test_pixel_vectors_layout():
+    g = torch.Generator().manual_seed(1)
+    steps = [torch.empty(1, 3, 6, 5).uniform_(-1.2, 1.2, generator=g) for _ in range(3)]
+    lab = np.arange(30, dtype=np.uint8).reshape(6, 5)
+    v = odt.pixel_vectors_chain(steps, lab)
+    d = odt.pixel_vectors_loop(steps, lab)
+    assert v.shape == (6, 5, 4)
+    for (i, j), vec in d.items():
+        assert v[i, j].tolist() == [int(a) for a in vec]

@@ -12,17 +12,30 @@ from ldiffusion_b200 import ops, LaplacePLMSScheduler
 PEAK = 6546.2
 
 
-def timeit(fn, nbuf, iters=50, warm=5):
+def timeit(fn, nbuf, iters=40, warm=3):
+    """GPU time per launch: `iters` launches captured into one CUDA graph (no host
+    launch gaps), replayed 5 times, CUDA events around the replays."""
     for i in range(warm):
         fn(i % nbuf)
     torch.cuda.synchronize()
+    st = torch.cuda.Stream()
+    st.wait_stream(torch.cuda.current_stream())
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(st):
+        with torch.cuda.graph(g, stream=st):
+            for i in range(iters):
+                fn(i % nbuf)
+    torch.cuda.synchronize()
+    g.replay()
+    torch.cuda.synchronize()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
     s.record()
-    for i in range(iters):
-        fn(i % nbuf)
+    for _ in range(reps):
+        g.replay()
     e.record()
     torch.cuda.synchronize()
-    return s.elapsed_time(e) / iters * 1e3     # us
+    return s.elapsed_time(e) / (iters * reps) * 1e3     # us
 
 
 def main():
