@@ -54,9 +54,11 @@ def label_down_chain(label_u8, size=(64, 64)):
 #   t     = fma(w0, a, fl(w1 * b))                 horizontal, per source row
 #   v     = fma(h0, t_top, fl(h1 * t_bottom))      vertical
 # This reproduces F.interpolate bit for bit on the up-sampling shapes of the
-# path (32->1024 logits, 64->1024 RGB, odd sizes).  ATen's down-sampling goes
-# through a differently-contracted loop (4-term sum); there the spec agrees
-# with it to <= 2 ulp and features are compared within 1e-3 relative.
+# path (32->1024 logits, 64->1024 RGB, and e.g. 37x53 -> 101x77).  ATen has no
+# single arithmetic: which contraction its compiler chose depends on the loop
+# specialisation a shape lands in (its 16x down-sampling uses a 4-term sum, a
+# 13x9 -> 31x40 lift a mirrored FMA); there the spec agrees with it to <= 2 ulp
+# and features are compared within the 1e-3 relative contract.
 
 def _f32(x):
     return np.asarray(x, dtype=np.float32)
