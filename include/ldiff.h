@@ -139,6 +139,11 @@ int ldiff_argmax_channels(const void* x, uint8_t* out, int B, int K, int64_t hw,
  * pred >= K sets LDIFF_STATUS_PRED_RANGE (the reference's one_hot raises). */
 int ldiff_confusion_hist(const uint8_t* pred, const uint8_t* gt, const uint8_t* gt_lut,
                          int64_t* C, int64_t n, int K, int* status, void* stream);
+/* batched form for per-image metrics (evaluate.py:60-102 averages per-image scores):
+ * image i = pixels [i*n_per_image, (i+1)*n_per_image), matrix i at C + i*(K+1)*K. */
+int ldiff_confusion_hist_batched(const uint8_t* pred, const uint8_t* gt, const uint8_t* gt_lut,
+                                 int64_t* C, int64_t n_per_image, int n_images, int K, int* status,
+                                 void* stream);
 /* int64 labels -> uint8 (values outside [0,254] become 255 = "other") */
 int ldiff_labels_to_u8(const int64_t* in, uint8_t* out, int64_t n, void* stream);
 

@@ -39,6 +39,8 @@ SIGNATURES = {
     "ldiff_argmax_channels": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_void_p]),
     "ldiff_confusion_hist": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
                                      c_void_p, c_void_p]),
+    "ldiff_confusion_hist_batched": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int,
+                                             c_void_p, c_void_p]),
     "ldiff_labels_to_u8": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
 }
 

@@ -15,8 +15,8 @@
 //  * lift_separable_kernel — up-sampling: a CTA owns a band of output rows of
 //    one image; the few source rows it needs are staged into shared memory with
 //    1-D bulk TMA copies (cp.async.bulk + mbarrier), the horizontal pass is done
-//    ONCE per source row into shared memory, and every output row is then one
-//    mul + one fma per pixel with 128-bit stores: HBM-write-bound.
+//    once per source row into REGISTERS, and every output row is then one mul +
+//    one fma per pixel with 128-bit stores: HBM-write-bound.
 #include "common.cuh"
 
 namespace ldiff {
@@ -155,18 +155,21 @@ template <> struct OutVec<uint8_t> {
 };
 
 // grid: (bands, channel groups, B).  NC = channels handled by one CTA (3 in gray
-// mode, else 1).  Shared memory: [NC][max_rows][w] TS raw rows (TMA destination),
-// then [NC][max_rows][W] fp32 horizontally-lifted rows.
+// mode, else 1).  Shared memory: [NC][max_rows][w] TS raw source rows (the bulk-TMA
+// destination) + the band's vertical taps.  A thread owns V adjacent output
+// columns (one 16-byte store) and walks down its rows keeping the horizontally
+// lifted values of the two current source rows in REGISTERS; they are refreshed
+// from the staged raw rows only when the source row pair changes (every H/h output
+// rows), so the steady state per output element is one FMUL + one FFMA + the store.
 template <typename TS, typename TD, int NC, bool GRAY>
 __global__ void __launch_bounds__(256)
 lift_separable_kernel(const TS* __restrict__ src, int64_t sbs, int64_t scs, TD* __restrict__ dst,
                       int Ctot, int dch, Axis ay, Axis ax, int band, int max_rows) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar;
+  __shared__ int4 s_tap[32];                           // {r0, r1, bits(l0), bits(l1)} per band row
   const int w = ax.in, W = ax.out, H = ay.out;
   TS* raw = reinterpret_cast<TS*>(smem);
-  const size_t raw_bytes = ((size_t)NC * max_rows * w * sizeof(TS) + 127) & ~(size_t)127;
-  float* lifted = reinterpret_cast<float*>(smem + raw_bytes);
 
   const int b = blockIdx.z;
   const int c0 = blockIdx.y * NC;
@@ -176,6 +179,10 @@ lift_separable_kernel(const TS* __restrict__ src, int64_t sbs, int64_t scs, TD* 
   const int yhi = make_tap(ay, Y1 - 1).i1;
   const int nrows = yhi - ylo + 1;                      // <= max_rows by construction
 
+  if (threadIdx.x < Y1 - Y0) {
+    const Tap t = make_tap(ay, Y0 + threadIdx.x);
+    s_tap[threadIdx.x] = make_int4(t.i0 - ylo, t.i1 - ylo, __float_as_int(t.l0), __float_as_int(t.l1));
+  }
   if (threadIdx.x == 0) mbar_init(&bar, 1);
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -189,48 +196,83 @@ lift_separable_kernel(const TS* __restrict__ src, int64_t sbs, int64_t scs, TD* 
   }
   mbar_wait(&bar, 0);
 
-  // horizontal pass: lifted[c][r][X]
-  for (int i = threadIdx.x; i < NC * nrows * W; i += blockDim.x) {
-    const int X = i % W;
-    const int cr = i / W;                               // c * nrows + r
-    const int c = cr / nrows, r = cr - c * nrows;
-    const Tap tx = make_tap(ax, X);
-    const TS* row = raw + ((size_t)c * max_rows + r) * w;
-    lifted[((size_t)c * max_rows + r) * W + X] = lerp_h(tx.l0, to_f32(row[tx.i0]), tx.l1, to_f32(row[tx.i1]));
-  }
-  __syncthreads();
-
   constexpr int V = OutVec<TD>::N;
-  const int vec_per_row = W / V;
+  const int groups = W / V;                             // 16-byte vectors per output row
+  const int nthr = blockDim.x;
+  // groups < nthr: the block splits the band into nsub row sub-bands
+  const int nsub = groups >= nthr ? 1 : nthr / groups;
+  const int sub = groups >= nthr ? 0 : (int)threadIdx.x / groups;
+  const int xg0 = groups >= nthr ? (int)threadIdx.x : (int)threadIdx.x - sub * groups;
+  const int xstep = groups >= nthr ? nthr : groups;
+  if (sub >= nsub) return;
+  const int rows_total = Y1 - Y0;
+  const int rows_per_sub = (rows_total + nsub - 1) / nsub;
+  const int ya = sub * rows_per_sub, yb = min(ya + rows_per_sub, rows_total);
   const int64_t HW = (int64_t)H * W;
-  for (int i = threadIdx.x; i < (Y1 - Y0) * vec_per_row; i += blockDim.x) {
-    const int y = Y0 + i / vec_per_row;
-    const int X = (i % vec_per_row) * V;
-    const Tap ty = make_tap(ay, y);
-    const int r0 = ty.i0 - ylo, r1 = ty.i1 - ylo;
-    float out[V];
-    if (GRAY) {
-      float ch[3][V];
+
+  for (int xg = xg0; xg < groups; xg += xstep) {
+    const int X = xg * V;
+    float T0[NC][V], T1[NC][V];
+    int xi0[V];                                         // horizontal taps of this thread's columns
+    float xl1[V];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        float t[V], u[V];
-        load_row<V>(lifted + ((size_t)c * max_rows + r0) * W + X, t);
-        load_row<V>(lifted + ((size_t)c * max_rows + r1) * W + X, u);
+    for (int k = 0; k < V; ++k) {
+      const Tap tx = make_tap(ax, X + k);
+      xi0[k] = tx.i0; xl1[k] = tx.l1;
+    }
+    auto fill = [&](float (&T)[NC][V], int r) {
 #pragma unroll
-        for (int k = 0; k < V; ++k) ch[c][k] = lerp_h(ty.l0, t[k], ty.l1, u[k]);
+      for (int k = 0; k < V; ++k) {
+        const int i1 = (ax.in == ax.out) ? xi0[k] : min(xi0[k] + 1, w - 1);   // as make_tap
+        const float l0 = __fsub_rn(1.f, xl1[k]);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const TS* row = raw + ((size_t)c * max_rows + r) * w;
+          T[c][k] = lerp_h(l0, to_f32(row[xi0[k]]), xl1[k], to_f32(row[i1]));
+        }
       }
+    };
+    int cur0 = -1, cur1 = -1;
+    for (int yy = ya; yy < yb; ++yy) {
+      const int4 tp = s_tap[yy];
+      const float l0 = __int_as_float(tp.z), l1 = __int_as_float(tp.w);
+      if (tp.x != cur0 || tp.y != cur1) {                // block-uniform per sub-band
+        if (tp.x == cur1) {
 #pragma unroll
-      for (int k = 0; k < V; ++k) out[k] = gray3(ch[0][k], ch[1][k], ch[2][k]);
-      OutVec<TD>::store(dst + ((int64_t)b * Ctot + dch) * HW + (int64_t)y * W + X, out);
-    } else {
+          for (int c = 0; c < NC; ++c)
 #pragma unroll
-      for (int c = 0; c < NC; ++c) {
-        float t[V], u[V];
-        load_row<V>(lifted + ((size_t)c * max_rows + r0) * W + X, t);
-        load_row<V>(lifted + ((size_t)c * max_rows + r1) * W + X, u);
+            for (int k = 0; k < V; ++k) T0[c][k] = T1[c][k];
+        } else {
+          fill(T0, tp.x);
+        }
+        if (tp.y == tp.x) {
 #pragma unroll
-        for (int k = 0; k < V; ++k) out[k] = lerp_h(ty.l0, t[k], ty.l1, u[k]);
-        OutVec<TD>::store(dst + ((int64_t)b * Ctot + dch + c0 + c) * HW + (int64_t)y * W + X, out);
+          for (int c = 0; c < NC; ++c)
+#pragma unroll
+            for (int k = 0; k < V; ++k) T1[c][k] = T0[c][k];
+        } else {
+          fill(T1, tp.y);
+        }
+        cur0 = tp.x; cur1 = tp.y;
+      }
+      const int64_t row_off = (int64_t)(Y0 + yy) * W + X;
+      float out[V];
+      if (GRAY) {
+        float ch[3][V];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+          for (int k = 0; k < V; ++k) ch[c][k] = lerp_h(l0, T0[c % NC][k], l1, T1[c % NC][k]);
+#pragma unroll
+        for (int k = 0; k < V; ++k) out[k] = gray3(ch[0][k], ch[1][k], ch[2][k]);
+        OutVec<TD>::store(dst + ((int64_t)b * Ctot + dch) * HW + row_off, out);
+      } else {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+#pragma unroll
+          for (int k = 0; k < V; ++k) out[k] = lerp_h(l0, T0[c][k], l1, T1[c][k]);
+          OutVec<TD>::store(dst + ((int64_t)b * Ctot + dch + c0 + c) * HW + row_off, out);
+        }
       }
     }
   }
@@ -246,14 +288,16 @@ static int launch_lift(const void* src, int C, int h, int w, int64_t sbs, int64_
   // rows of source a band can touch: ceil(band * scale) + 2
   const int max_rows = (int)((double)band * h / H) + 3;
   const int NCg = gray ? 3 : 1;
-  const size_t raw_bytes = ((size_t)NCg * max_rows * w * sizeof(TS) + 127) & ~(size_t)127;
-  const size_t smem = raw_bytes + (size_t)NCg * max_rows * W * sizeof(float);
+  const size_t smem = ((size_t)NCg * max_rows * w * sizeof(TS) + 127) & ~(size_t)127;
   const bool separable = H >= h && W >= w && (W % V == 0) && ((w * sizeof(TS)) % 16 == 0) &&
                          aligned16(src) && aligned16(dst) && ((sbs * sizeof(TS)) % 16 == 0) &&
                          ((scs * sizeof(TS)) % 16 == 0) && (((int64_t)H * W * sizeof(TD)) % 16 == 0) &&
                          smem <= 160 * 1024 && (int64_t)max_rows * w * sizeof(TS) < (1 << 20);
   if (separable) {
     dim3 grid((H + band - 1) / band, gray ? 1 : C, B);
+    // one thread per 16-byte output vector of a row when the row has < 256 of them
+    const int groups = W / V;
+    const int threads = groups >= 256 ? 256 : (groups >= 128 ? 128 : (groups >= 64 ? 64 : 32));
     if (gray) {
       auto k = lift_separable_kernel<TS, TD, 3, true>;
       if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);

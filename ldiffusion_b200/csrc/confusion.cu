@@ -1,18 +1,28 @@
 // a-6 confusion matrix C[(K+1),K] from uint8 prediction / ground-truth maps (sm_100a).
 //
-// One pass, 2 bytes per pixel: each thread streams 16 pixels per iteration with
-// two 128-bit loads, merges equal neighbours into runs in registers (label maps
-// are spatially coherent, so most 4-pixel words extend the current run with two
-// compares), and flushes a run with ONE shared-memory atomic into a histogram
-// that is replicated per lane (hist[bin][lane], bank == lane: a warp-wide flush
-// never bank-conflicts and never contends inside the warp).  At the end the
-// block folds the replicas and issues one 64-bit global atomic per non-empty
-// bin into the caller's int64 matrix (which may be the NCCL all-reduce buffer).
+// One pass, 2 bytes per pixel.  The budget at the HBM roofline is ~11 issued
+// instructions per pixel, so the per-pixel work is SWAR on the loaded words:
+//  * 16 pixels per thread per iteration (two 128-bit streaming loads);
+//  * per 32-bit word (4 pixels): branch-free bytewise "gt >= K -> K" clamp and
+//    "pred >= K" check, then ONE multiply-add gives the four bin indices
+//    gt*K + pred packed in bytes (bins fit a byte for K <= 15);
+//  * one fire-and-forget shared-memory atomic per pixel into a histogram
+//    replicated per lane (hist[bin][lane]: bank == lane, so a warp-wide update
+//    never bank-conflicts and never hits the same address twice);
+//  * at the end the block folds the 32 replicas and issues one 64-bit global
+//    atomic per non-empty bin into the caller's int64 matrix (which may be the
+//    buffer handed to ncclAllReduce).
+// Larger K (16..128) takes the same kernel with per-pixel integer bin math.
 #include "common.cuh"
 
 namespace ldiff {
 
-template <int R>
+// bytes of w that are >= k (k <= 128) get 0x80, others 0
+__device__ __forceinline__ uint32_t bytes_ge(uint32_t w, uint32_t k) {
+  return (((w & 0x7f7f7f7fu) + (0x80u - k) * 0x01010101u) | w) & 0x80808080u;
+}
+
+template <int R, bool SMALLK, bool HAS_LUT>
 __global__ void __launch_bounds__(512)
 confusion_hist_kernel(const uint8_t* __restrict__ pred, const uint8_t* __restrict__ gt,
                       const uint8_t* __restrict__ gt_lut, unsigned long long* __restrict__ C,
@@ -21,54 +31,64 @@ confusion_hist_kernel(const uint8_t* __restrict__ pred, const uint8_t* __restric
   __shared__ uint8_t lut[256];
   const int nbins = (K + 1) * K;
   for (int i = threadIdx.x; i < nbins * R; i += blockDim.x) hist[i] = 0;
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = gt_lut ? gt_lut[i] : (uint8_t)i;
+  if (HAS_LUT)
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = gt_lut[i];
   __syncthreads();
 
-  const int rep = threadIdx.x & (R - 1);
-  int bad = 0;
-  uint32_t run_p = 0, run_g = 0, run_cnt = 0;
+  // grid.y = image (batched form: one matrix per image)
+  pred += (int64_t)blockIdx.y * n;
+  gt += (int64_t)blockIdx.y * n;
+  C += (int64_t)blockIdx.y * nbins;
 
-  auto flush = [&]() {
-    if (run_cnt) {
-      const int row = min((int)lut[run_g], K);
-      if ((int)run_p < K) atomicAdd(&hist[(row * K + (int)run_p) * R + rep], run_cnt);
-      else bad = 1;
-    }
+  uint32_t* my = hist + (threadIdx.x & (R - 1));     // this lane's replica column
+  uint32_t bad = 0;
+  const uint32_t k4 = (uint32_t)K * 0x01010101u;
+
+  auto pixel = [&](uint32_t p, uint32_t g) {         // generic path
+    if (HAS_LUT) g = lut[g];
+    g = min(g, (uint32_t)K);
+    if (p >= (uint32_t)K) { bad = 1; p = 0; }
+    atomicAdd(my + (g * K + p) * R, 1u);
   };
   auto word = [&](uint32_t pw, uint32_t gw) {
-    if (pw == run_p * 0x01010101u && gw == run_g * 0x01010101u) {
-      run_cnt += 4;
-      return;
-    }
+    if (SMALLK) {
+      if (HAS_LUT)
+        gw = (uint32_t)lut[gw & 0xff] | ((uint32_t)lut[(gw >> 8) & 0xff] << 8) |
+             ((uint32_t)lut[(gw >> 16) & 0xff] << 16) | ((uint32_t)lut[gw >> 24] << 24);
+      const uint32_t gm = (bytes_ge(gw, K) >> 7) * 0xffu;          // 0xff where gt >= K
+      const uint32_t gc = (gw & ~gm) | (k4 & gm);
+      const uint32_t po = bytes_ge(pw, K);
+      bad |= po;
+      const uint32_t pc = pw & ~((po >> 7) * 0xffu);
+      const uint32_t bins = gc * (uint32_t)K + pc;                  // four byte-sized bin indices
+      atomicAdd(my + (bins & 0xffu) * R, 1u);
+      atomicAdd(my + ((bins >> 8) & 0xffu) * R, 1u);
+      atomicAdd(my + ((bins >> 16) & 0xffu) * R, 1u);
+      atomicAdd(my + (bins >> 24) * R, 1u);
+    } else {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const uint32_t p = (pw >> (8 * k)) & 0xffu, g = (gw >> (8 * k)) & 0xffu;
-      if (p == run_p && g == run_g) {
-        ++run_cnt;
-      } else {
-        flush();
-        run_p = p; run_g = g; run_cnt = 1;
-      }
+      for (int k = 0; k < 4; ++k) pixel((pw >> (8 * k)) & 0xffu, (gw >> (8 * k)) & 0xffu);
     }
   };
 
-  const int64_t nvec = n >> 4;
+  // [0,head) scalar until both streams are 16-byte aligned (all of it if they are
+  // aligned differently), then 16-pixel vectors, then the scalar tail
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  const uint4* pv = reinterpret_cast<const uint4*>(pred);
-  const uint4* gv = reinterpret_cast<const uint4*>(gt);
-  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t mp = (uint32_t)(reinterpret_cast<uintptr_t>(pred) & 15u);
+  const uint32_t mg = (uint32_t)(reinterpret_cast<uintptr_t>(gt) & 15u);
+  int64_t head = (mp == mg) ? (int64_t)((16u - mp) & 15u) : n;
+  if (head > n) head = n;
+  const int64_t nvec = (n - head) >> 4;
+  for (int64_t i = gtid; i < head; i += stride) pixel(pred[i], gt[i]);
+  const uint4* pv = reinterpret_cast<const uint4*>(pred + head);
+  const uint4* gv = reinterpret_cast<const uint4*>(gt + head);
+  for (int64_t v = gtid; v < nvec; v += stride) {
     const uint4 a = __ldcs(pv + v);
     const uint4 b = __ldcs(gv + v);
     word(a.x, b.x); word(a.y, b.y); word(a.z, b.z); word(a.w, b.w);
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {          // n % 16 trailing pixels
-    for (int64_t i = nvec << 4; i < n; ++i) {
-      const uint32_t p = pred[i], g = gt[i];
-      if (p == run_p && g == run_g) ++run_cnt;
-      else { flush(); run_p = p; run_g = g; run_cnt = 1; }
-    }
-  }
-  flush();
+  for (int64_t i = head + (nvec << 4) + gtid; i < n; i += stride) pixel(pred[i], gt[i]);
   if (bad) atomicOr(status, LDIFF_STATUS_PRED_RANGE);
   __syncthreads();
 
@@ -101,40 +121,66 @@ labels_to_u8_kernel(const int64_t* __restrict__ in, uint8_t* __restrict__ out, i
 
 using namespace ldiff;
 
-extern "C" int ldiff_confusion_hist(const uint8_t* pred, const uint8_t* gt, const uint8_t* gt_lut,
-                                    int64_t* C, int64_t n, int K, int* status, void* stream) {
-  if (!pred || !gt || !C || !status || n < 0 || K < 1) return LDIFF_EINVAL;
-  if (K > 128) return LDIFF_EUNSUPPORTED;
-  if (n == 0) return LDIFF_OK;
-  if (!aligned16(pred) || !aligned16(gt)) return LDIFF_EALIGN;
-  cudaStream_t st = (cudaStream_t)stream;
+static int launch_confusion(const uint8_t* pred, const uint8_t* gt, const uint8_t* gt_lut, int64_t* C,
+                            int64_t n_per_image, int n_images, int K, int* status, cudaStream_t st) {
   const int threads = 512;
   const int nbins = (K + 1) * K;
   int R = 32;
   while (R > 1 && (size_t)nbins * R * 4 > 64 * 1024) R >>= 1;
   const size_t smem = (size_t)nbins * R * 4;
-  const int grid = grid_for((n >> 4) > 0 ? (n >> 4) : 1, threads, 4);
+  // blocks per image: up to 4 resident blocks per SM over the batch, each thread >= 1 vector
+  const int64_t nvec = (n_per_image >> 4) > 0 ? (n_per_image >> 4) : 1;
+  int64_t bx = (nvec + threads - 1) / threads;
+  const int64_t cap = ((int64_t)sm_count() * 4 + n_images - 1) / n_images;
+  if (bx > cap) bx = cap > 0 ? cap : 1;
+  const dim3 grid((unsigned)bx, (unsigned)n_images);
   unsigned long long* Cu = reinterpret_cast<unsigned long long*>(C);
-#define CH(RR)                                                                                      \
+  const bool smallk = K <= 15;
+#define CH3(RR, SK, LUT)                                                                            \
   do {                                                                                              \
-    static bool attr_set = false;                                                                   \
-    if (!attr_set && smem > 48 * 1024) {                                                            \
-      cudaFuncSetAttribute(confusion_hist_kernel<RR>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                           72 * 1024);                                                              \
-      attr_set = true;                                                                              \
-    }                                                                                               \
-    confusion_hist_kernel<RR><<<grid, threads, smem, st>>>(pred, gt, gt_lut, Cu, n, K, status);     \
+    if (smem > 48 * 1024)                                                                           \
+      cudaFuncSetAttribute(confusion_hist_kernel<RR, SK, LUT>,                                      \
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);                 \
+    confusion_hist_kernel<RR, SK, LUT><<<grid, threads, smem, st>>>(pred, gt, gt_lut, Cu,           \
+                                                                    n_per_image, K, status);        \
   } while (0)
-  switch (R) {
-    case 32: CH(32); break;
-    case 16: CH(16); break;
-    case 8: CH(8); break;
-    case 4: CH(4); break;
-    case 2: CH(2); break;
-    default: CH(1); break;
+#define CH(RR, SK)                                \
+  do {                                            \
+    if (gt_lut) CH3(RR, SK, true);                \
+    else CH3(RR, SK, false);                      \
+  } while (0)
+  if (smallk) {
+    CH(32, true);                                  // K <= 15 -> nbins <= 240 -> R == 32 always
+  } else {
+    switch (R) {
+      case 32: CH(32, false); break;
+      case 16: CH(16, false); break;
+      case 8: CH(8, false); break;
+      case 4: CH(4, false); break;
+      case 2: CH(2, false); break;
+      default: CH(1, false); break;
+    }
   }
 #undef CH
+#undef CH3
   return check_launch();
+}
+
+extern "C" int ldiff_confusion_hist(const uint8_t* pred, const uint8_t* gt, const uint8_t* gt_lut,
+                                    int64_t* C, int64_t n, int K, int* status, void* stream) {
+  if (!pred || !gt || !C || !status || n < 0 || K < 1) return LDIFF_EINVAL;
+  if (K > 128) return LDIFF_EUNSUPPORTED;
+  if (n == 0) return LDIFF_OK;
+  return launch_confusion(pred, gt, gt_lut, C, n, 1, K, status, (cudaStream_t)stream);
+}
+
+extern "C" int ldiff_confusion_hist_batched(const uint8_t* pred, const uint8_t* gt,
+                                            const uint8_t* gt_lut, int64_t* C, int64_t n_per_image,
+                                            int n_images, int K, int* status, void* stream) {
+  if (!pred || !gt || !C || !status || n_per_image < 0 || n_images < 0 || K < 1) return LDIFF_EINVAL;
+  if (K > 128 || n_images > 65535) return LDIFF_EUNSUPPORTED;
+  if (n_per_image == 0 || n_images == 0) return LDIFF_OK;
+  return launch_confusion(pred, gt, gt_lut, C, n_per_image, n_images, K, status, (cudaStream_t)stream);
 }
 
 extern "C" int ldiff_labels_to_u8(const int64_t* in, uint8_t* out, int64_t n, void* stream) {

@@ -14,53 +14,103 @@
 
 namespace ldiff {
 
-template <typename T> __device__ __forceinline__ float round_storage(float x);
-template <> __device__ __forceinline__ float round_storage<float>(float x) { return x; }
-template <> __device__ __forceinline__ float round_storage<__nv_bfloat16>(float x) {
-  return __bfloat162float(__float2bfloat16_rn(x));
+// The kernel is issue-bound before it is HBM-bound unless the per-pixel
+// instruction count stays near 15, so the chain is strength-reduced without
+// changing a single rounding:
+//  * x/2 is exact, so fl(x/2 + 0.5) == fma(x, 0.5, 0.5), and the clamp to [0,1]
+//    is the FFMA's .SAT modifier (NaN -> 0, as numpy's uint8 cast gives);
+//  * rint(v) for v in [0,255] == low mantissa bits of fl(v + 1.5*2^23)
+//    (round-half-even in hardware, no F2I conversion);
+//  * the 16.16 luma weights sum to exactly 2^16, so the 0x4B400000 exponent
+//    pattern of those magic floats cancels mod 2^32: the luma is three IMADs on
+//    the RAW float bits and its result byte is picked out with PRMT;
+//  * bf16 images: the reference's bf16 VAE rounds x/2+0.5 to bf16 (x/2 is exact
+//    there too): one packed fma.relu.bf16x2 + min.bf16x2 per TWO pixels, straight
+//    on the loaded words; t then has 8 significant bits, t*255 is exact in fp32
+//    and the multiply folds into the magic add as one FFMA.
+template <typename T> struct Quant;
+
+template <> struct Quant<float> {
+  // returns the float bits 0x4B400000 | q
+  __device__ static __forceinline__ uint32_t bits(float x) {
+    const float t = __saturatef(__fmaf_rn(x, 0.5f, 0.5f));
+    return __float_as_uint(__fadd_rn(__fmul_rn(t, 255.f), 12582912.f));
+  }
+};
+
+template <> struct Quant<__nv_bfloat16> {
+  // two packed bf16 pixels -> two magic-float bit patterns.  fma.rn.relu.bf16x2 rounds
+  // x/2+0.5 to bf16 once; the reference rounds to fp32 first, which is exact here (x has 8
+  // significant bits) or cannot change the bf16 result (|x| < 2^-16).  NaN inputs are
+  // unspecified (numpy's uint8 cast of NaN is platform-defined too).
+  __device__ static __forceinline__ void packed2(uint32_t x2, uint32_t& q0, uint32_t& q1) {
+    uint32_t t;
+    asm("{ .reg .b32 f;\n"
+        "  fma.rn.relu.bf16x2 f, %1, %2, %2;\n"
+        "  min.bf16x2 %0, f, %3;\n}"
+        : "=r"(t) : "r"(x2), "r"(0x3f003f00u), "r"(0x3f803f80u));
+    q0 = __float_as_uint(__fmaf_rn(__uint_as_float(t << 16), 255.f, 12582912.f));
+    q1 = __float_as_uint(__fmaf_rn(__uint_as_float(t & 0xffff0000u), 255.f, 12582912.f));
+  }
+  __device__ static __forceinline__ uint32_t bits(float x) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);            // x is a bf16 value: exact
+    uint32_t a, b;
+    packed2((uint32_t)*reinterpret_cast<const uint16_t*>(&h), a, b);
+    return a;
+  }
+};
+
+// 16 consecutive pixels of one plane -> 16 magic-float bit patterns
+__device__ __forceinline__ void quant16(const float* p, uint32_t (&q)[16]) {
+  float v[16];
+  Vec8<float>::load(p, reinterpret_cast<float(&)[8]>(v[0]));
+  Vec8<float>::load(p + 8, reinterpret_cast<float(&)[8]>(v[8]));
+#pragma unroll
+  for (int i = 0; i < 16; ++i) q[i] = Quant<float>::bits(v[i]);
+}
+__device__ __forceinline__ void quant16(const __nv_bfloat16* p, uint32_t (&q)[16]) {
+  const uint4 a = __ldcs(reinterpret_cast<const uint4*>(p));
+  const uint4 b = __ldcs(reinterpret_cast<const uint4*>(p) + 1);
+  const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) Quant<__nv_bfloat16>::packed2(w[i], q[2 * i], q[2 * i + 1]);
 }
 
-template <typename T>
-__device__ __forceinline__ uint32_t quantise(float x) {
-  float t = round_storage<T>(__fmul_rn(x, 0.5f));
-  t = round_storage<T>(__fadd_rn(t, 0.5f));
-  t = fminf(fmaxf(t, 0.f), 1.f);
-  return (uint32_t)__float2int_rn(__fmul_rn(t, 255.f));
+// (19595 R + 38470 G + 7471 B + 0x8000): result byte 2 is the PIL "L" value
+__device__ __forceinline__ uint32_t luma_sum(uint32_t rb, uint32_t gb, uint32_t bb) {
+  return 19595u * rb + 38470u * gb + 7471u * bb + 0x8000u;
 }
 
-__device__ __forceinline__ uint32_t luma(uint32_t r, uint32_t g, uint32_t b) {
-  return (19595u * r + 38470u * g + 7471u * b + 0x8000u) >> 16;
+// byte `B` of four registers -> one packed word
+template <int B>
+__device__ __forceinline__ uint32_t pack4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  const uint32_t lo = __byte_perm(a, b, 0x0040 + B * 0x11);
+  const uint32_t hi = __byte_perm(c, d, 0x0040 + B * 0x11);
+  return __byte_perm(lo, hi, 0x5410);
 }
 
 template <typename T, bool RGB, bool GRAY>
 __global__ void __launch_bounds__(256)
 decode_tail_vec16_kernel(const T* __restrict__ img, uint8_t* __restrict__ rgb,
-                         uint8_t* __restrict__ gray, int64_t hw, int64_t groups_per_img,
-                         int64_t total_groups, int64_t gray_batch_stride) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t gidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gidx < total_groups;
-       gidx += stride) {
-    const int64_t b = gidx / groups_per_img;
-    const int64_t p = (gidx - b * groups_per_img) << 4;
+                         uint8_t* __restrict__ gray, int64_t hw, int groups_per_img,
+                         int64_t gray_batch_stride) {
+  // grid = (blocks over one image, B): no division in the loop
+  const int64_t b = blockIdx.y;
+  const int stride = gridDim.x * blockDim.x;
+  for (int gidx = blockIdx.x * blockDim.x + threadIdx.x; gidx < groups_per_img; gidx += stride) {
+    const int64_t p = (int64_t)gidx << 4;
     const T* base = img + b * 3 * hw + p;
-    uint32_t q[3][16];
+    uint32_t q[3][16];                                 // float bits 0x4B400000 | value
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      float v[16];
-      Vec8<T>::load(base + c * hw, reinterpret_cast<float(&)[8]>(v[0]));
-      Vec8<T>::load(base + c * hw + 8, reinterpret_cast<float(&)[8]>(v[8]));
-#pragma unroll
-      for (int i = 0; i < 16; ++i) q[c][i] = quantise<T>(v[i]);
-    }
+    for (int c = 0; c < 3; ++c) quant16(base + c * hw, q[c]);
     if (GRAY) {
       uint32_t w[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        w[j] = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          w[j] |= luma(q[0][4 * j + k], q[1][4 * j + k], q[2][4 * j + k]) << (8 * k);
-      }
+      for (int j = 0; j < 4; ++j)
+        w[j] = pack4<2>(luma_sum(q[0][4 * j], q[1][4 * j], q[2][4 * j]),
+                        luma_sum(q[0][4 * j + 1], q[1][4 * j + 1], q[2][4 * j + 1]),
+                        luma_sum(q[0][4 * j + 2], q[1][4 * j + 2], q[2][4 * j + 2]),
+                        luma_sum(q[0][4 * j + 3], q[1][4 * j + 3], q[2][4 * j + 3]));
       __stcs(reinterpret_cast<uint4*>(gray + b * gray_batch_stride + p),
              make_uint4(w[0], w[1], w[2], w[3]));
     }
@@ -68,12 +118,9 @@ decode_tail_vec16_kernel(const T* __restrict__ img, uint8_t* __restrict__ rgb,
       uint32_t w[12];
 #pragma unroll
       for (int j = 0; j < 12; ++j) {
-        w[j] = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int byte = 4 * j + k;
-          w[j] |= q[byte % 3][byte / 3] << (8 * k);
-        }
+        // output bytes 4j .. 4j+3: byte k belongs to pixel k/3, channel k%3
+        w[j] = pack4<0>(q[(4 * j) % 3][(4 * j) / 3], q[(4 * j + 1) % 3][(4 * j + 1) / 3],
+                        q[(4 * j + 2) % 3][(4 * j + 2) / 3], q[(4 * j + 3) % 3][(4 * j + 3) / 3]);
       }
       uint4* o = reinterpret_cast<uint4*>(rgb + (b * hw + p) * 3);
       __stcs(o, make_uint4(w[0], w[1], w[2], w[3]));
@@ -93,10 +140,10 @@ decode_tail_scalar_kernel(const T* __restrict__ img, uint8_t* __restrict__ rgb,
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
     const int64_t b = i / hw, p = i - b * hw;
     const T* base = img + b * 3 * hw + p;
-    const uint32_t r = quantise<T>(to_f32(base[0]));
-    const uint32_t g = quantise<T>(to_f32(base[hw]));
-    const uint32_t bl = quantise<T>(to_f32(base[2 * hw]));
-    if (gray) gray[b * gray_batch_stride + p] = (uint8_t)luma(r, g, bl);
+    const uint32_t r = Quant<T>::bits(to_f32(base[0]));
+    const uint32_t g = Quant<T>::bits(to_f32(base[hw]));
+    const uint32_t bl = Quant<T>::bits(to_f32(base[2 * hw]));
+    if (gray) gray[b * gray_batch_stride + p] = (uint8_t)(luma_sum(r, g, bl) >> 16);
     if (rgb) {
       uint8_t* o = rgb + i * 3;
       o[0] = (uint8_t)r; o[1] = (uint8_t)g; o[2] = (uint8_t)bl;
@@ -112,15 +159,23 @@ static int launch_decode_tail(const void* img, uint8_t* rgb, uint8_t* gray, int 
   const bool vec_ok = (hw % 16 == 0) && aligned16(img) && aligned16(rgb) && aligned16(gray) &&
                       (gray_batch_stride % 16 == 0);
   if (vec_ok) {
-    const int64_t gpi = hw >> 4, total = gpi * B;
-    const int grid = grid_for(total, threads, 8);
+    if ((hw >> 4) > 0x7fffffff / 2 || B > 65535) return LDIFF_EUNSUPPORTED;
+    const int gpi = (int)(hw >> 4);
+    // blocks per image: cover it, but no more than ~8 resident blocks per SM over the batch
+    // (balanced: every thread runs the same number of iterations, so the grid is one even wave)
+    const int need = (gpi + threads - 1) / threads;
+    int cap = (sm_count() * 8) / B;
+    if (cap < 1) cap = 1;
+    const int iters = (need + cap - 1) / cap;
+    const int bx = (need + iters - 1) / iters;
+    const dim3 grid(bx, B);
     const T* p = (const T*)img;
     if (rgb && gray)
-      decode_tail_vec16_kernel<T, true, true><<<grid, threads, 0, st>>>(p, rgb, gray, hw, gpi, total, gray_batch_stride);
+      decode_tail_vec16_kernel<T, true, true><<<grid, threads, 0, st>>>(p, rgb, gray, hw, gpi, gray_batch_stride);
     else if (gray)
-      decode_tail_vec16_kernel<T, false, true><<<grid, threads, 0, st>>>(p, rgb, gray, hw, gpi, total, gray_batch_stride);
+      decode_tail_vec16_kernel<T, false, true><<<grid, threads, 0, st>>>(p, rgb, gray, hw, gpi, gray_batch_stride);
     else
-      decode_tail_vec16_kernel<T, true, false><<<grid, threads, 0, st>>>(p, rgb, gray, hw, gpi, total, gray_batch_stride);
+      decode_tail_vec16_kernel<T, true, false><<<grid, threads, 0, st>>>(p, rgb, gray, hw, gpi, gray_batch_stride);
   } else {
     const int64_t total = hw * B;
     decode_tail_scalar_kernel<T><<<grid_for(total, threads, 8), threads, 0, st>>>(

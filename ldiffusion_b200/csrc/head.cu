@@ -12,6 +12,8 @@
 // probabilities, which needs a top-2 gap below ~2e-7; pixels whose gap is
 // <= kTieGap re-evaluate the pinned softmax (exp in fp64 rounded to fp32,
 // sequential fp32 sum, fp32 division, first maximum).
+#include <utility>
+
 #include "common.cuh"
 
 namespace ldiff {
@@ -56,56 +58,129 @@ __device__ __noinline__ int softmax_argmax_exact(const float (&v)[KT], int K, in
   return best;
 }
 
-// ----------------------------------------------------------------------------
-// logits fp32 [B,K,h,w] -> mask uint8 [B,H,W]; K <= KT.  One thread per output
-// column, a band of output rows per block-y.
-template <int KT>
-__global__ void __launch_bounds__(256)
-lift_argmax_kernel(const float* __restrict__ logits, uint8_t* __restrict__ mask, int K, AxisH ay,
-                   AxisH ax, int band) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  if (x >= ax.out) return;
-  const int b = blockIdx.z;
-  const int Y0 = blockIdx.y * band, Y1 = min(Y0 + band, ay.out);
-  const TapH tx = tap(ax, x);
-  const int64_t plane = (int64_t)ay.in * ax.in;
-  const float* lb = logits + (int64_t)b * K * plane;
-  uint8_t* out = mask + (int64_t)b * ay.out * ax.out + x;
+// Cold path: one pixel resolved from scratch with the pinned softmax.  Kept out of
+// line and fed scalars only so that it costs the hot loops no registers.
+__device__ __noinline__ int exact_pixel(const float* __restrict__ lb, int K, int plane, int in_w,
+                                        int yi0, int yi1, float yl0, float yl1, int xi0, int xi1,
+                                        float xl0, float xl1) {
+  auto value = [&](int k) {
+    const float* r0 = lb + k * plane + yi0 * in_w;
+    const float* r1 = lb + k * plane + yi1 * in_w;
+    return lerp2(yl0, lerp2(xl0, __ldg(r0 + xi0), xl1, __ldg(r0 + xi1)), yl1,
+                 lerp2(xl0, __ldg(r1 + xi0), xl1, __ldg(r1 + xi1)));
+  };
+  float m = value(0);
+  for (int k = 1; k < K; ++k) m = fmaxf(m, value(k));
+  float s = 0.f;
+  for (int k = 0; k < K; ++k) s = __fadd_rn(s, (float)exp((double)__fsub_rn(value(k), m)));
+  float pb = -1.f;
+  int idx = 0;
+  for (int k = 0; k < K; ++k) {
+    const float pk = __fdiv_rn((float)exp((double)__fsub_rn(value(k), m)), s);
+    if (pk > pb) { pb = pk; idx = k; }
+  }
+  return idx;
+}
 
-  float T[KT], U[KT];
-  int cy0 = -1, cy1 = -1;
-  for (int y = Y0; y < Y1; ++y) {
-    const TapH ty = tap(ay, y);
-    if (ty.i0 != cy0 || ty.i1 != cy1) {
-      cy0 = ty.i0; cy1 = ty.i1;
+// ----------------------------------------------------------------------------
+// logits fp32 [B,K,h,w] -> mask uint8 [B,H,W], K known at compile time.
+// A thread owns COLS adjacent output columns and walks a band of output rows.
+// Per (column, class) it keeps the horizontally lifted logits of the two source
+// rows in registers (T, U), reloaded only when the source row pair changes, so a
+// pixel costs per class: FMUL+FFMA (vertical lerp), FMNMX (running max), then
+// FSETP + one predicated IADD that accumulates "16+k" for every class within
+// kTieGap of the max: count == 1 gives the argmax directly; anything else only
+// sets a bit, and those (rare) pixels are re-resolved after the row loop by the
+// out-of-line pinned softmax.  The kernel is issue-bound (ALU), not HBM-bound: it
+// reads 0.36 MB of logits and writes 1 byte per pixel.
+constexpr int kBand = 32;
+
+// acc += (v >= thr) ? C : 0 as exactly FSETP + one predicated integer add
+template <int C>
+__device__ __forceinline__ void tie_add(int& acc, float v, float thr) {
+  asm("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %1, %2;\n\t@p add.s32 %0, %0, %3;\n\t}"
+      : "+r"(acc) : "f"(v), "f"(thr), "n"(C));
+}
+template <int K, int... Is>
+__device__ __forceinline__ int tie_acc(const float (&v)[K], float thr, std::integer_sequence<int, Is...>) {
+  int acc = 0;
+  (tie_add<16 + Is>(acc, v[Is], thr), ...);
+  return acc;
+}
+
+template <int K, int COLS>
+__global__ void __launch_bounds__(256)
+lift_argmax_kernel(const float* __restrict__ logits, uint8_t* __restrict__ mask, AxisH ay, AxisH ax) {
+  __shared__ int s_i0[kBand], s_i1[kBand];
+  __shared__ float s_l0[kBand], s_l1[kBand];
+  const int Y0 = blockIdx.y * kBand, Y1 = min(Y0 + kBand, ay.out);
+  if (threadIdx.x < Y1 - Y0) {
+    const TapH t = tap(ay, Y0 + threadIdx.x);
+    s_i0[threadIdx.x] = t.i0; s_i1[threadIdx.x] = t.i1;
+    s_l0[threadIdx.x] = t.l0; s_l1[threadIdx.x] = t.l1;
+  }
+  __syncthreads();
+  const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * COLS;
+  if (x0 >= ax.out) return;
+  const int b = blockIdx.z;
+  const int plane = ay.in * ax.in;
+  const float* lb = logits + (int64_t)b * K * plane;
+  uint8_t* out = mask + ((int64_t)b * ay.out + Y0) * ax.out + x0;
+
+  TapH tx[COLS];
 #pragma unroll
-      for (int k = 0; k < KT; ++k) {
-        if (k < K) {
-          const float* r0 = lb + k * plane + (int64_t)cy0 * ax.in;
-          const float* r1 = lb + k * plane + (int64_t)cy1 * ax.in;
-          T[k] = lerp2(tx.l0, __ldg(r0 + tx.i0), tx.l1, __ldg(r0 + tx.i1));
-          U[k] = lerp2(tx.l0, __ldg(r1 + tx.i0), tx.l1, __ldg(r1 + tx.i1));
+  for (int c = 0; c < COLS; ++c) tx[c] = tap(ax, min(x0 + c, ax.out - 1));
+
+  float T[COLS][K], U[COLS][K];
+  uint32_t amb[COLS];
+#pragma unroll
+  for (int c = 0; c < COLS; ++c) amb[c] = 0;
+  int cy0 = -1, cy1 = -1;
+  for (int r = 0; r < Y1 - Y0; ++r) {
+    const int i0 = s_i0[r], i1 = s_i1[r];
+    const float l0 = s_l0[r], l1 = s_l1[r];
+    if (i0 != cy0 || i1 != cy1) {                      // warp-uniform
+      cy0 = i0; cy1 = i1;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const float* r0 = lb + k * plane + i0 * ax.in;
+        const float* r1 = lb + k * plane + i1 * ax.in;
+#pragma unroll
+        for (int c = 0; c < COLS; ++c) {
+          T[c][k] = lerp2(tx[c].l0, __ldg(r0 + tx[c].i0), tx[c].l1, __ldg(r0 + tx[c].i1));
+          U[c][k] = lerp2(tx[c].l0, __ldg(r1 + tx[c].i0), tx[c].l1, __ldg(r1 + tx[c].i1));
         }
       }
     }
-    float best = lerp2(ty.l0, T[0], ty.l1, U[0]);
-    float second = -INFINITY;
-    int idx = 0;
+    uint32_t packed = 0;
 #pragma unroll
-    for (int k = 1; k < KT; ++k) {
-      if (k < K) {
-        const float v = lerp2(ty.l0, T[k], ty.l1, U[k]);
-        if (v > best) { second = best; best = v; idx = k; }
-        else second = fmaxf(second, v);
+    for (int c = 0; c < COLS; ++c) {
+      float v[K];
+      float m = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        v[k] = lerp2(l0, T[c][k], l1, U[c][k]);
+        m = fmaxf(m, v[k]);
       }
+      const float thr = __fsub_rn(m, kTieGap);
+      const int acc = tie_acc(v, thr, std::make_integer_sequence<int, K>{});
+      if ((acc >> 4) != 1) amb[c] |= 1u << r;          // rare: tie or near-tie
+      packed |= (uint32_t)(acc & 15) << (8 * c);
     }
-    if (__fsub_rn(best, second) <= kTieGap) {          // rare: pinned softmax decides
-      float v[KT];
+    if (COLS == 1) out[0] = (uint8_t)packed;
+    else if (COLS == 2) *reinterpret_cast<uint16_t*>(out) = (uint16_t)packed;
+    else *reinterpret_cast<uint32_t*>(out) = packed;
+    out += ax.out;
+  }
 #pragma unroll
-      for (int k = 0; k < KT; ++k) v[k] = (k < K) ? lerp2(ty.l0, T[k], ty.l1, U[k]) : 0.f;
-      idx = softmax_argmax_exact<KT>(v, K, 0);
+  for (int c = 0; c < COLS; ++c) {
+    uint32_t bits = amb[c];
+    while (bits) {
+      const int r = __ffs(bits) - 1;
+      bits &= bits - 1;
+      mask[((int64_t)b * ay.out + Y0 + r) * ax.out + x0 + c] = (uint8_t)exact_pixel(
+          lb, K, plane, ax.in, s_i0[r], s_i1[r], s_l0[r], s_l1[r], tx[c].i0, tx[c].i1, tx[c].l0, tx[c].l1);
     }
-    out[(int64_t)y * ax.out] = (uint8_t)idx;
   }
 }
 
@@ -135,15 +210,8 @@ lift_argmax_generic_kernel(const float* __restrict__ logits, uint8_t* __restrict
       if (v > best) { second = best; best = v; idx = k; }
       else second = fmaxf(second, v);
     }
-    if (__fsub_rn(best, second) <= kTieGap) {
-      float s = 0.f;
-      for (int k = 0; k < K; ++k) s = __fadd_rn(s, (float)exp((double)__fsub_rn(value(k), best)));
-      float pb = -1.f;
-      for (int k = 0; k < K; ++k) {
-        const float pk = __fdiv_rn((float)exp((double)__fsub_rn(value(k), best)), s);
-        if (pk > pb) { pb = pk; idx = k; }
-      }
-    }
+    if (__fsub_rn(best, second) <= kTieGap)
+      idx = exact_pixel(lb, K, (int)plane, ax.in, ty.i0, ty.i1, ty.l0, ty.l1, tx.i0, tx.i1, tx.l0, tx.l1);
     mask[i] = (uint8_t)idx;
   }
 }
@@ -291,11 +359,14 @@ extern "C" int ldiff_lift_argmax(const float* logits, uint8_t* mask, int B, int 
   if (B == 0) return LDIFF_OK;
   cudaStream_t st = (cudaStream_t)stream;
   AxisH ay{(float)h / (float)H, h, H}, ax{(float)w / (float)W, w, W};
-  if (K <= 16) {
-    const int band = 32;
-    dim3 grid((W + 255) / 256, (H + band - 1) / band, B);
-    if (K <= 8) lift_argmax_kernel<8><<<grid, 256, 0, st>>>(logits, mask, K, ay, ax, band);
-    else lift_argmax_kernel<16><<<grid, 256, 0, st>>>(logits, mask, K, ay, ax, band);
+  constexpr int COLS = 2;
+  if (K <= 15 && (W % COLS) == 0) {
+    dim3 grid((W / COLS + 255) / 256, (H + kBand - 1) / kBand, B);
+    switch (K) {
+#define LA(KK) case KK: lift_argmax_kernel<KK, COLS><<<grid, 256, 0, st>>>(logits, mask, ay, ax); break;
+      LA(1) LA(2) LA(3) LA(4) LA(5) LA(6) LA(7) LA(8) LA(9) LA(10) LA(11) LA(12) LA(13) LA(14) LA(15)
+#undef LA
+    }
   } else {
     const int64_t total = (int64_t)H * W * B;
     lift_argmax_generic_kernel<<<grid_for(total, 256, 8), 256, 0, st>>>(logits, mask, K, ay, ax, B);

@@ -1,11 +1,206 @@
-// tcgen05 / TMEM contraction for the classifier head (bf16 in, fp32 accumulate).
+// a-5 classifier-head contraction on the 5th-gen tensor cores (sm_100a):
+//   logits[b, k, p] = bias[k] + sum_c W[k, c] * feat[b, c, p]      (conductor.py:127)
+// bf16 operands, fp32 accumulation in TMEM.
+//
+// GEMM view per CTA: D[128 pixels, 16 classes] = A[128, Cin] * B[16, Cin]^T with
+// one tcgen05.mma (M=128, N=16, K=16) per 16 channels, issued by a single thread.
+//
+//  * The feature map is NCHW: pixels are contiguous, channels strided, i.e. the
+//    A operand arrives "M-major".  Instead of an MN-major descriptor the tile is
+//    transposed on its way into shared memory: each thread gathers 8 consecutive
+//    channels of one pixel (coalesced 2-byte loads across the warp) and writes
+//    one 16-byte chunk of the canonical K-major SWIZZLE_128B layout (row = pixel,
+//    128 bytes = 64 channels per row, chunk index XOR (row & 7)).  W is K-major
+//    already and is copied with 16-byte loads into the same layout.
+//  * The whole K extent fits in shared memory (Cin/64 blocks of 16 KB + 2 KB), so
+//    there is no pipeline: fill, fence.proxy.async, one elected thread issues
+//    Cin/16 MMAs and a tcgen05.commit onto an mbarrier, four warps read the
+//    accumulator back with tcgen05.ld (lane = pixel, 16 columns = classes), add
+//    the bias and store coalesced fp32 logits.
+//
+// The problem is tiny (8 x 1024 pixels x 256 x 11: 46 MFLOP, 4 MB): the tensor
+// core is there to take the math off the critical path, the kernel is bound by
+// the latency of one pass over its 64 KB tile.
 #include "common.cuh"
 
 namespace ldiff {
 
-int launch_head_logits_tc(const void*, const void*, const float*, float*, int, int, int, int,
-                          cudaStream_t) {
-  return LDIFF_EUNSUPPORTED;   // placeholder until the tensor-core kernel lands
+namespace tc {
+
+constexpr int kTileM = 128;     // pixels per CTA  (UMMA M)
+constexpr int kTileN = 16;      // padded classes  (UMMA N)
+constexpr int kBlockK = 64;     // channels per 128-byte swizzle row
+constexpr int kUmmaK = 16;      // channels per tcgen05.mma (bf16)
+constexpr int kThreads = 256;
+constexpr uint32_t kTmemCols = 32;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (sm_100 format):
+//   [0,14) start address >> 4, [16,30) LBO >> 4 (unused for swizzled K-major),
+//   [32,46) SBO >> 4 = 1024 B between 8-row groups, [46,48) version = 1,
+//   [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3ffffu) >> 4);
+  d |= (uint64_t)(1024u >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// instruction descriptor, kind::f16: D=f32 (bit 4), A=B=bf16 (bits 7, 10), both
+// K-major (bits 15, 16 = 0), N>>3 at [17,23), M>>4 at [24,29)
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTileN >> 3) << 17) |
+                            ((uint32_t)(kTileM >> 4) << 24);
+
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "TC_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra TC_DONE;\n\t"
+      "bra TC_WAIT;\n\t"
+      "TC_DONE:\n\t}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+
+// grid = (hw / 128, B); dynamic smem = 1024 (alignment slack) + nkb * (16 KB + 2 KB)
+__global__ void __launch_bounds__(kThreads, 1)
+head_logits_tc_kernel(const __nv_bfloat16* __restrict__ feat, const __nv_bfloat16* __restrict__ weight,
+                      const float* __restrict__ bias, float* __restrict__ logits, int Cin, int K, int hw) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t mma_bar;
+  __shared__ uint32_t tmem_base_slot;
+
+  // SWIZZLE_128B atoms must be 1024-byte aligned
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int nkb = Cin / kBlockK;
+  uint8_t* sA = smem;                                   // [nkb][128 rows][128 B]
+  uint8_t* sB = smem + (size_t)nkb * kTileM * 128;      // [nkb][ 16 rows][128 B]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int p0 = blockIdx.x * kTileM;
+
+  if (warp == 0) {                                      // TMEM allocation (one warp, .sync.aligned)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&tmem_base_slot)), "n"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x == 32) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mma_bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+
+  // ---- A: transpose [c][p] -> K-major rows.  item = (row r, 16-byte chunk j of the full K extent)
+  const __nv_bfloat16* fb = feat + (int64_t)b * Cin * hw + p0;
+  const int chunks_per_row = Cin / 8;
+  for (int item = threadIdx.x; item < kTileM * chunks_per_row; item += kThreads) {
+    const int r = item % kTileM;                         // consecutive threads -> consecutive pixels
+    const int j = item / kTileM;                         // channels 8j .. 8j+7
+    const __nv_bfloat16* src = fb + (int64_t)(8 * j) * hw + r;
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint16_t lo = __ldg(reinterpret_cast<const uint16_t*>(src + (int64_t)(2 * q) * hw));
+      const uint16_t hi = __ldg(reinterpret_cast<const uint16_t*>(src + (int64_t)(2 * q + 1) * hw));
+      w[q] = (uint32_t)lo | ((uint32_t)hi << 16);
+    }
+    const int kb = j >> 3, ch = j & 7;
+    uint8_t* dst = sA + ((size_t)kb * kTileM + r) * 128 + ((ch ^ (r & 7)) << 4);
+    *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  // ---- B: weights [K][Cin] (K-major), rows >= K are zero
+  for (int item = threadIdx.x; item < kTileN * chunks_per_row; item += kThreads) {
+    const int n = item / chunks_per_row, j = item - n * chunks_per_row;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (n < K) v = __ldg(reinterpret_cast<const uint4*>(weight + (int64_t)n * Cin) + j);
+    const int kb = j >> 3, ch = j & 7;
+    *reinterpret_cast<uint4*>(sB + ((size_t)kb * kTileN + n) * 128 + ((ch ^ (n & 7)) << 4)) = v;
+  }
+  // generic-proxy writes -> visible to the async proxy (tensor core) before the MMAs
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = tmem_base_slot;
+
+  // ---- MMA issue: one thread
+  if (threadIdx.x == 0) {
+    uint32_t acc = 0;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const uint32_t a0 = smem_u32(sA + (size_t)kb * kTileM * 128);
+      const uint32_t b0 = smem_u32(sB + (size_t)kb * kTileN * 128);
+#pragma unroll
+      for (int k = 0; k < kBlockK / kUmmaK; ++k) {        // advance 32 bytes inside the swizzle atom
+        mma_bf16(tmem_d, make_desc(a0 + k * kUmmaK * 2), make_desc(b0 + k * kUmmaK * 2), acc);
+        acc = 1;
+      }
+    }
+    // arrives on the mbarrier when every MMA above has completed
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                     smem_u32(&mma_bar)) : "memory");
+  }
+
+  // ---- epilogue: warps 0..3, warp w owns TMEM lanes 32w..32w+31 (= pixels)
+  if (warp < 4) {
+    mbar_wait(smem_u32(&mma_bar), 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t v[16];
+    const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    const int p = p0 + warp * 32 + lane;
+    float* out = logits + (int64_t)b * K * hw + p;
+#pragma unroll
+    for (int k = 0; k < kTileN; ++k)
+      if (k < K) out[(int64_t)k * hw] = __uint_as_float(v[k]) + (bias ? __ldg(bias + k) : 0.f);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(kTmemCols)
+                 : "memory");
+  }
+}
+
+}  // namespace tc
+
+int launch_head_logits_tc(const void* feat, const void* weight, const float* bias, float* logits,
+                          int B, int Cin, int K, int hw, cudaStream_t st) {
+  using namespace tc;
+  if (K > kTileN || (hw % kTileM) != 0 || (Cin % kBlockK) != 0 || B > 65535) return LDIFF_EUNSUPPORTED;
+  if (!aligned16(weight) || (reinterpret_cast<uintptr_t>(feat) & 1)) return LDIFF_EUNSUPPORTED;
+  const int nkb = Cin / kBlockK;
+  const size_t smem = 1024 + (size_t)nkb * (kTileM + kTileN) * 128;
+  if (smem > 200 * 1024) return LDIFF_EUNSUPPORTED;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(head_logits_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set = true;
+  }
+  dim3 grid(hw / kTileM, B);
+  head_logits_tc_kernel<<<grid, kThreads, smem, st>>>((const __nv_bfloat16*)feat,
+                                                       (const __nv_bfloat16*)weight, bias, logits, Cin, K, hw);
+  return check_launch();
 }
 
 }  // namespace ldiff

@@ -165,12 +165,8 @@ def summarize_images(per_image_C):
 
 
 def per_image_confusion(preds: torch.Tensor, gts: torch.Tensor, num_classes: int) -> torch.Tensor:
-    """uint8 [N,H,W] x2 -> int64 [N,(K+1),K] (one launch per image, no syncs)."""
-    K = int(num_classes)
-    out = torch.zeros((preds.shape[0], K + 1, K), dtype=torch.int64, device=preds.device)
-    for i in range(preds.shape[0]):
-        ops.confusion_hist(preds[i].reshape(-1), gts[i].reshape(-1), K, out=out[i])
-    return out
+    """uint8 [N,H,W] x2 -> int64 [N,(K+1),K] in one launch, no syncs."""
+    return ops.confusion_hist_batched(preds, gts, int(num_classes))
 
 
 def evaluate(image_dir, label_dir, num_classes, save_dir="./eval_results", device=None):

@@ -157,6 +157,14 @@ def _confusion_hist(pred: Tensor, gt: Tensor, gt_lut: Optional[Tensor], C: Tenso
                                            K, _ptr(status), _stream(pred)))
 
 
+def _confusion_hist_batched(pred: Tensor, gt: Tensor, gt_lut: Optional[Tensor], C: Tensor, K: int,
+                            status: Tensor) -> None:
+    _cuda(pred, gt, gt_lut, C, status)
+    n_images = pred.shape[0]
+    check(_cabi.lib().ldiff_confusion_hist_batched(_ptr(pred), _ptr(gt), _ptr(gt_lut), _ptr(C),
+                                                   pred[0].numel(), n_images, K, _ptr(status), _stream(pred)))
+
+
 def _labels_to_u8(x: Tensor, out: Tensor) -> None:
     _cuda(x, out)
     check(_cabi.lib().ldiff_labels_to_u8(_ptr(x), _ptr(out), x.numel(), _stream(x)))
@@ -172,6 +180,7 @@ torch.library.custom_op("ldiff::cell_classify", mutates_args=("lut", "logits_out
 torch.library.custom_op("ldiff::lut_paint", mutates_args=("mask", "status"))(_lut_paint)
 torch.library.custom_op("ldiff::argmax_channels", mutates_args=("out",))(_argmax_channels)
 torch.library.custom_op("ldiff::confusion_hist", mutates_args=("C", "status"))(_confusion_hist)
+torch.library.custom_op("ldiff::confusion_hist_batched", mutates_args=("C", "status"))(_confusion_hist_batched)
 torch.library.custom_op("ldiff::labels_to_u8", mutates_args=("out",))(_labels_to_u8)
 
 
@@ -360,4 +369,21 @@ def confusion_hist(pred: Tensor, gt: Tensor, num_classes: int, *, out: Optional[
     if gt_lut is not None and (gt_lut.dtype != torch.uint8 or gt_lut.numel() != 256):
         raise ValueError("gt_lut must be 256 uint8 entries")
     _confusion_hist(pred, gt, gt_lut, out, K, status_word(pred.device))
+    return out
+
+
+def confusion_hist_batched(pred: Tensor, gt: Tensor, num_classes: int, *, out: Optional[Tensor] = None,
+                           gt_lut: Optional[Tensor] = None) -> Tensor:
+    """Per-image matrices in ONE launch: uint8 [N,...] x2 -> int64 [N,(K+1),K] (accumulates)."""
+    if pred.dtype != torch.uint8 or gt.dtype != torch.uint8:
+        raise TypeError("pred and gt must be uint8 label maps")
+    if pred.shape != gt.shape or pred.dim() < 2:
+        raise ValueError("pred and gt must be [N,...] of the same shape")
+    _dense(pred, "pred"); _dense(gt, "gt")
+    K, N = int(num_classes), pred.shape[0]
+    if out is None:
+        out = torch.zeros((N, K + 1, K), dtype=torch.int64, device=pred.device)
+    elif out.shape != (N, K + 1, K) or out.dtype != torch.int64 or not out.is_contiguous():
+        raise ValueError("out must be a contiguous int64 [N,(K+1),K] tensor")
+    _confusion_hist_batched(pred, gt, gt_lut, out, K, status_word(pred.device))
     return out

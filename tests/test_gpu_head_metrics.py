@@ -155,6 +155,29 @@ def test_confusion_random_labels_and_accumulate():
     assert np.array_equal(C.cpu().numpy(), want)
 
 
+def test_confusion_batched_per_image():
+    """One launch, one matrix per image (evaluate.py averages per-image scores)."""
+    K = 11
+    gt = _blob_labels((5, 256, 320), K, 31)
+    pred = _blob_labels((5, 256, 320), K, 32, other_frac=0)
+    got = _ops().confusion_hist_batched(torch.from_numpy(pred).cuda(), torch.from_numpy(gt).cuda(), K).cpu().numpy()
+    for i in range(5):
+        assert np.array_equal(got[i], omet.confusion_matrix(pred[i], gt[i], K))
+    odd = _ops().confusion_hist_batched(torch.from_numpy(pred[:, :37, :53].copy()).cuda(),
+                                        torch.from_numpy(gt[:, :37, :53].copy()).cuda(), K).cpu().numpy()
+    for i in range(5):
+        assert np.array_equal(odd[i], omet.confusion_matrix(pred[i, :37, :53], gt[i, :37, :53], K))
+
+
+@pytest.mark.parametrize("K", [16, 40, 128])
+def test_confusion_large_k(K):
+    rng = np.random.default_rng(K)
+    pred = rng.integers(0, K, (1, 200, 200)).astype(np.uint8)
+    gt = rng.integers(0, min(K + 3, 256), (1, 200, 200)).astype(np.uint8)
+    got = _ops().confusion_hist(torch.from_numpy(pred).cuda().reshape(-1), torch.from_numpy(gt).cuda().reshape(-1), K)
+    assert np.array_equal(got.cpu().numpy(), omet.confusion_matrix(pred, gt, K))
+
+
 def test_confusion_gt_lut_fusion():
     """dataset.py:20-32 gray-level -> class LUT applied inside the histogram pass."""
     K = 11
