@@ -305,6 +305,7 @@ def head_argmax(feat: Tensor, weight: Tensor, bias: Optional[Tensor], size, retu
 def cell_classify(inst_feats: Tensor, weight: Tensor, bias: Optional[Tensor], inst_ids: Tensor,
                   lut_size: int, *, lut: Optional[Tensor] = None, return_logits: bool = False):
     """conductor.py:218-221 -> class LUT (uint8 [lut_size], lut[0] = background)."""
+    _cuda(inst_feats, weight, inst_ids)
     _dense(inst_feats, "inst_feats"); _dense(weight, "weight")
     if inst_ids.dtype != torch.int32:
         inst_ids = inst_ids.to(torch.int32)
@@ -322,6 +323,7 @@ def lut_paint(inst: Tensor, lut: Tensor, out: Optional[Tensor] = None) -> Tensor
     """mask[b,y,x] = lut[b][inst[b,y,x]] (conductor.py:224-231 + segmentor.py:536)."""
     if inst.dtype != torch.int32:
         raise TypeError("instance map must be int32")
+    _cuda(inst, lut)
     if inst.dim() == 2:
         inst = inst.unsqueeze(0)
     _dense(inst, "inst"); _dense(lut, "lut")
@@ -358,6 +360,7 @@ def confusion_hist(pred: Tensor, gt: Tensor, num_classes: int, *, out: Optional[
     """Accumulates C[(K+1),K] (int64) += histogram of (gt, pred) pairs; uint8 inputs."""
     if pred.dtype != torch.uint8 or gt.dtype != torch.uint8:
         raise TypeError("pred and gt must be uint8 label maps")
+    _cuda(pred, gt)
     if pred.numel() != gt.numel():
         raise ValueError("pred and gt must have the same number of pixels")
     _dense(pred, "pred"); _dense(gt, "gt")
@@ -377,6 +380,7 @@ def confusion_hist_batched(pred: Tensor, gt: Tensor, num_classes: int, *, out: O
     """Per-image matrices in ONE launch: uint8 [N,...] x2 -> int64 [N,(K+1),K] (accumulates)."""
     if pred.dtype != torch.uint8 or gt.dtype != torch.uint8:
         raise TypeError("pred and gt must be uint8 label maps")
+    _cuda(pred, gt)
     if pred.shape != gt.shape or pred.dim() < 2:
         raise ValueError("pred and gt must be [N,...] of the same shape")
     _dense(pred, "pred"); _dense(gt, "gt")

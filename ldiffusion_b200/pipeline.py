@@ -120,6 +120,78 @@ class HotPath:
         ops.confusion_hist(self.mask_tissue.view(-1), inp.gt.view(-1), self.K, out=self.C[0])
         ops.confusion_hist(self.mask_cell.view(-1), inp.gt.view(-1), self.K, out=self.C[1])
 
+    # ------------------------------------------------------------------
+    # host-facing API: pinned host batches in, pinned host results out
+    # ------------------------------------------------------------------
+    RESULT_KEYS = ("latents", "pixel_planes", "rgb", "featcat", "label_small", "rgb_up", "mask_tissue",
+                   "mask_cell", "confusion")
+
+    def _host_state(self, like: "HotPathInputs"):
+        st = getattr(self, "_hs", None)
+        if st is None:
+            dev = self.device
+
+            def mirror(f):
+                return [torch.empty_like(t, device=dev) for t in f] if isinstance(f, list) \
+                    else torch.empty_like(f, device=dev)
+
+            st = {
+                "in": [HotPathInputs(*[mirror(f) for f in (like.latents, like.eps, like.decoded, like.head_feat,
+                                                           like.inst_map, like.inst_feats, like.gt)])
+                       for _ in range(2)],
+                "s_in": torch.cuda.Stream(dev), "s_run": torch.cuda.Stream(dev), "s_out": torch.cuda.Stream(dev),
+                "in_ready": [torch.cuda.Event() for _ in range(2)],
+                "in_free": [torch.cuda.Event() for _ in range(2)],
+                "run_done": torch.cuda.Event(), "out_done": torch.cuda.Event(),
+            }
+            self._hs = st
+        return st
+
+    def alloc_host_results(self):
+        res = self.results()
+        return {k: torch.empty(res[k].shape, dtype=res[k].dtype, pin_memory=True) for k in self.RESULT_KEYS}
+
+    def run_host(self, batches, host_out, after_run=None):
+        """Process a sequence of host-resident batches (HotPathInputs of pinned CPU
+        tensors); the results of batch i are copied into ``host_out[i % len(host_out)]``.
+
+        Three streams pipeline the work: while batch i computes, batch i+1 streams
+        host->device into the other input set and batch i-1's results stream
+        device->host, so a long run costs max(H2D, compute, D2H) per batch instead
+        of their sum (PCIe is full duplex).  ``after_run`` (optional) is called on
+        the compute stream after each pass (e.g. the confusion all-reduce)."""
+        st = self._host_state(batches[0])
+        s_in, s_run, s_out = st["s_in"], st["s_run"], st["s_out"]
+        cur = torch.cuda.current_stream(self.device)
+        for s in (s_in, s_run, s_out):
+            s.wait_stream(cur)
+        res = self.results()
+        for i, hb in enumerate(batches):
+            slot = i & 1
+            with torch.cuda.stream(s_in):
+                if i >= 2:
+                    s_in.wait_event(st["in_free"][slot])          # pass i-2 has consumed this set
+                for src, dst in zip(hb.tensors(), st["in"][slot].tensors()):
+                    dst.copy_(src, non_blocking=True)
+                st["in_ready"][slot].record(s_in)
+            with torch.cuda.stream(s_run):
+                s_run.wait_event(st["in_ready"][slot])
+                if i >= 1:
+                    s_run.wait_event(st["out_done"])              # results of pass i-1 are out of the buffers
+                self.run(st["in"][slot])
+                if after_run is not None:
+                    after_run()
+                st["in_free"][slot].record(s_run)
+                st["run_done"].record(s_run)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(st["run_done"])
+                ho = host_out[i % len(host_out)]
+                for k in self.RESULT_KEYS:
+                    ho[k].copy_(res[k], non_blocking=True)
+                st["out_done"].record(s_out)
+        for s in (s_in, s_run, s_out):
+            cur.wait_stream(s)
+
     def results(self):
         return {"latents": self.lat[-1], "noisy": self.noisy, "pixel_planes": self.planes, "rgb": self.rgb,
                 "featcat": self.featcat, "label_small": self.label_small, "rgb_up": self.rgb_up,

@@ -1,0 +1,141 @@
+"""CPU: host-side logic of the product (scheduler state machine + scalar folding,
+metric drop-ins' argument handling, tile sharding + collectives over gloo, world size 2)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from oracle import metrics as omet
+from oracle.scheduler import PNDMOracle
+
+
+def _emulate_kernel(sample, eps, mode, sc, dA, den):
+    """What ldiff_plms_step computes, restated with torch-CPU fp32 ops in the kernel's
+    order (mul/add/div each rounded once) — lets the host logic be checked without a GPU."""
+    f = lambda v: torch.tensor(v, dtype=torch.float32)                       # noqa: E731
+    if mode == 0:
+        eh = eps[0]
+    elif mode == 1:
+        eh = (eps[0] + eps[1]) * f(0.5)
+    elif mode == 2:
+        eh = (f(3.0) * eps[0] - eps[1]) * f(0.5)
+    elif mode == 3:
+        eh = ((f(23.0) * eps[0] - f(16.0) * eps[1]) + f(5.0) * eps[2]) / f(12.0)
+    else:
+        eh = f(1.0 / 24.0) * (((f(55.0) * eps[0] - f(59.0) * eps[1]) + f(37.0) * eps[2]) - f(9.0) * eps[3])
+    return f(sc) * sample - (f(dA) * eh) / f(den)
+
+
+@pytest.mark.parametrize("n_set", [1, 2, 4, 5, 10, 50])
+def test_scheduler_host_logic_reproduces_oracle(monkeypatch, n_set):
+    from ldiffusion_b200 import ops
+    from ldiffusion_b200.scheduler import LaplacePLMSScheduler
+    calls = []
+
+    def fake_plms(sample, eps, mode, sc, dA, den, out=None):
+        calls.append((mode, len(eps)))
+        return _emulate_kernel(sample, list(eps), mode, sc, dA, den)
+
+    monkeypatch.setattr(ops, "plms_step", fake_plms)
+    ref, sch = PNDMOracle(), LaplacePLMSScheduler()
+    ref.set_timesteps(n_set); sch.set_timesteps(n_set)
+    assert sch.timesteps.tolist() == ref.timesteps.tolist() and sch.timesteps.dtype == torch.int64
+    assert torch.equal(sch.alphas_cumprod, ref.alphas_cumprod)
+    g = torch.Generator().manual_seed(n_set)
+    x = xr = torch.randn(64, generator=g) * 5.5
+    for t in ref.timesteps:
+        eps = torch.randn(64, generator=g)
+        xr = ref.step(eps, t, ref.scale_model_input(xr, t))
+        x = sch.step(eps, t, sch.scale_model_input(x, t)).prev_sample
+        assert torch.equal(x, xr), f"t={int(t)}"
+    want_modes = [0, 1, 2, 3] + [4] * 60
+    assert [m for m, _ in calls] == want_modes[:len(calls)]
+    assert len(sch.ets) == min(4, max(1, len(calls) - 1)) if len(calls) > 1 else len(sch.ets) == 1
+
+
+def test_scheduler_errors_and_reset():
+    from ldiffusion_b200.scheduler import LaplacePLMSScheduler
+    s = LaplacePLMSScheduler()
+    with pytest.raises(ValueError):
+        s.step(torch.zeros(1), 1, torch.zeros(1))
+    with pytest.raises(ValueError):
+        s.set_timesteps(0)
+    s.set_timesteps(4)
+    assert s.scale_model_input(5, 3) == 5 and s.init_noise_sigma == 1.0 and len(s) == 1000
+    assert s.laplace_scale(601) == pytest.approx(0.916615307, rel=2e-7)
+    assert s.plan_step(751)[0] == 0
+
+
+def test_metric_dropins_validate_arguments():
+    from ldiffusion_b200 import metrics as pmet
+    with pytest.raises(ValueError):
+        pmet._pred_labels_u8(torch.zeros(4))
+    C = omet.confusion_matrix(np.array([[0, 1, 1]]), np.array([[0, 1, 2]]), 2)
+    assert pmet.pa_from_confusion(C)[1] == [1.0, 1.0]
+    d, a = pmet.dice_from_confusion(C)
+    assert d.dtype == torch.float32 and d.shape == (2,) and a.shape == ()
+
+
+def test_evaluate_count_mismatch(tmp_path):
+    from PIL import Image
+    from ldiffusion_b200 import metrics as pmet
+    (tmp_path / "p").mkdir(); (tmp_path / "g").mkdir()
+    Image.fromarray(np.zeros((4, 4), np.uint8)).save(tmp_path / "p" / "a.png")
+    with pytest.raises(ValueError, match="must be equal"):
+        pmet.evaluate(str(tmp_path / "p"), str(tmp_path / "g"), 3, str(tmp_path / "o"), device="cpu")
+
+
+def test_shard_tiles():
+    from ldiffusion_b200.dist import shard_tiles
+    for n, w in [(64, 1), (64, 2), (64, 8), (10, 4), (3, 8)]:
+        shards = [shard_tiles(n, r, w) for r in range(w)]
+        assert sorted(sum(shards, [])) == list(range(n))
+        assert max(map(len, shards)) - min(map(len, shards)) <= 1
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _worker(rank, world, port, n_tiles, K, q):
+    import torch.distributed as dist
+    from ldiffusion_b200 import dist as ld
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(0)                         # same data on every rank
+    preds = rng.integers(0, K, (n_tiles, 24, 24)).astype(np.uint8)
+    gts = rng.integers(0, K + 1, (n_tiles, 24, 24)).astype(np.uint8)
+    mine = ld.shard_tiles(n_tiles)
+    local = torch.from_numpy(np.stack([omet.confusion_matrix(preds[i], gts[i], K) for i in mine])
+                             if mine else np.zeros((0, K + 1, K), np.int64))
+    total = ld.allreduce_confusion(local.sum(0).clone())
+    tiles = ld.gather_tile_confusions(local, n_tiles)
+    q.put((rank, total.numpy(), tiles.numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_tiles", [7, 8])
+def test_confusion_collectives_world_size_2(n_tiles):
+    K, world = 5, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_tiles, K, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(0)
+    preds = rng.integers(0, K, (n_tiles, 24, 24)).astype(np.uint8)
+    gts = rng.integers(0, K + 1, (n_tiles, 24, 24)).astype(np.uint8)
+    per_tile = np.stack([omet.confusion_matrix(preds[i], gts[i], K) for i in range(n_tiles)])
+    for _, total, tiles in got:
+        assert np.array_equal(total, per_tile.sum(0))          # == single-process matrix, bit for bit
+        assert np.array_equal(tiles, per_tile)                  # global tile order restored
