@@ -115,11 +115,13 @@ int ldiff_head_logits(const void* feat, const void* weight, const float* bias, f
 int ldiff_lift_argmax(const float* logits, uint8_t* mask, int B, int K, int h, int w, int H, int W,
                       void* stream);
 /* cell form, replaces conductor.py:218-221: per-instance Linear(Cin,K) ->
- * softmax[:,1:] -> top-1 (+1); writes lut[inst_ids[i]] = class.
- * inst_feats [N,Cin] row-major fp32/bf16; inst_ids int32 [N]; lut uint8. */
+ * softmax[:,1:] -> top-1 (+1); writes lut[b*lut_stride + inst_ids[i]] = class.
+ * inst_feats [B,n_per_image,Cin] row-major fp32/bf16 (Cin % 8 == 0); inst_ids int32
+ * [n_per_image] (shared by the images of the batch); lut uint8 [B,lut_size]. */
 int ldiff_cell_classify(const void* inst_feats, const void* weight, const float* bias,
-                        const int32_t* inst_ids, uint8_t* lut, int lut_size, float* logits_out,
-                        int N, int Cin, int K, int dtype, int* status, void* stream);
+                        const int32_t* inst_ids, uint8_t* lut, int lut_size, int64_t lut_stride,
+                        float* logits_out, int n_per_image, int B, int Cin, int K, int dtype,
+                        int* status, void* stream);
 /* replaces the painting loop conductor.py:224-231 (+ segmentor.py:536):
  * mask[b,p] = lut[b*lut_stride + inst[b,p]]; ids outside [0,lut_size) -> 0 and
  * LDIFF_STATUS_INST_RANGE. */
@@ -144,6 +146,10 @@ int ldiff_confusion_hist(const uint8_t* pred, const uint8_t* gt, const uint8_t* 
 int ldiff_confusion_hist_batched(const uint8_t* pred, const uint8_t* gt, const uint8_t* gt_lut,
                                  int64_t* C, int64_t n_per_image, int n_images, int K, int* status,
                                  void* stream);
+/* B planes of n bytes -> a strided slot (the label plane of the pixel vectors,
+ * pixel_latent_vector.py:92); n and dst_stride multiples of 16 */
+int ldiff_copy_planes_u8(const uint8_t* src, uint8_t* dst, int64_t n, int B, int64_t dst_stride,
+                         void* stream);
 /* int64 labels -> uint8 (values outside [0,254] become 255 = "other") */
 int ldiff_labels_to_u8(const int64_t* in, uint8_t* out, int64_t n, void* stream);
 

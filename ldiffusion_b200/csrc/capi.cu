@@ -18,7 +18,32 @@ int sm_count() {
   return cached;
 }
 
+// dst plane b (dst + b*dst_stride) = src plane b (src + b*n), n bytes each, 16 bytes per thread
+__global__ void __launch_bounds__(256)
+copy_planes_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int64_t n, int64_t dst_stride) {
+  const uint4* s = reinterpret_cast<const uint4*>(src + (int64_t)blockIdx.y * n);
+  uint4* d = reinterpret_cast<uint4*>(dst + (int64_t)blockIdx.y * dst_stride);
+  const int64_t nvec = n >> 4;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x)
+    __stcs(d + v, __ldcs(s + v));
+}
+
 }  // namespace ldiff
+
+// label plane of the pixel vectors (pixel_latent_vector.py:92): B planes of n bytes into a strided slot
+extern "C" int ldiff_copy_planes_u8(const uint8_t* src, uint8_t* dst, int64_t n, int B, int64_t dst_stride,
+                                    void* stream) {
+  if (!src || !dst || n < 0 || B < 0 || dst_stride < n) return LDIFF_EINVAL;
+  if (n == 0 || B == 0) return LDIFF_OK;
+  if (!ldiff::aligned16(src) || !ldiff::aligned16(dst) || (n % 16) || (dst_stride % 16)) return LDIFF_EALIGN;
+  if (B > 65535) return LDIFF_EUNSUPPORTED;
+  int64_t bx = ((n >> 4) + 255) / 256;
+  const int64_t cap = ((int64_t)ldiff::sm_count() * 8 + B - 1) / B;
+  if (bx > cap) bx = cap;
+  ldiff::copy_planes_kernel<<<dim3((unsigned)bx, (unsigned)B), 256, 0, (cudaStream_t)stream>>>(src, dst, n,
+                                                                                             dst_stride);
+  return ldiff::check_launch();
+}
 
 extern "C" int ldiff_abi_version(void) { return LDIFF_ABI_VERSION; }
 

@@ -257,39 +257,93 @@ head_logits_simt_kernel(const T* __restrict__ feat, const T* __restrict__ weight
 }
 
 // ----------------------------------------------------------------------------
-// cell form: one warp per instance
+// cell form (conductor.py:218-221) for a whole batch in one launch.  A warp keeps
+// its slice of the classifier weights in registers (lane l owns channels
+// 8l .. 8l+7 of every class), then walks instances: one 16-byte feature load,
+// 8*K FMAs, a butterfly reduction, and lane 0 decides: softmax(...)[:, 1:] ->
+// top-1 -> +1 is the first argmax over k >= 1 unless two logits are within
+// kTieGap, in which case the pinned softmax (softmax_argmax_exact) decides.
+// Cin <= 256 (8 channels per lane); larger heads loop over channel slabs.
+template <typename T> struct Feat8;
+template <> struct Feat8<float> {
+  __device__ static void load(const float* p, float (&v)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+};
+template <> struct Feat8<__nv_bfloat16> {
+  __device__ static void load(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+};
+
 template <typename T, int KT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 cell_classify_kernel(const T* __restrict__ feats, const T* __restrict__ weight,
                      const float* __restrict__ bias, const int32_t* __restrict__ ids,
-                     uint8_t* __restrict__ lut, int lut_size, float* __restrict__ logits_out, int N,
-                     int Cin, int K, int* __restrict__ status) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= N) return;
-  float acc[KT];
+                     uint8_t* __restrict__ lut, int lut_size, int64_t lut_stride,
+                     float* __restrict__ logits_out, int n_per_image, int n_total, int Cin, int K,
+                     int* __restrict__ status) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int nslab = (Cin + 255) / 256;                   // 256 channels per pass over the lanes
+  for (int inst0 = warp; inst0 < n_total; inst0 += nwarps) {
+    float acc[KT];
 #pragma unroll
-  for (int k = 0; k < KT; ++k) acc[k] = 0.f;
-  for (int c = lane; c < Cin; c += 32) {
-    const float v = to_f32(feats[(int64_t)warp * Cin + c]);
+    for (int k = 0; k < KT; ++k) acc[k] = 0.f;
+    for (int slab = 0; slab < nslab; ++slab) {
+      const int c = slab * 256 + lane * 8;
+      if (c < Cin) {                                      // Cin % 8 == 0 (checked on the host)
+        float f[8];
+        Feat8<T>::load(feats + (int64_t)inst0 * Cin + c, f);
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+          if (k < K) {
+            float w[8];
+            Feat8<T>::load(weight + (int64_t)k * Cin + c, w);   // L1-resident after the first instance
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[k] = fmaf(w[j], f[j], acc[k]);
+          }
+        }
+      }
+    }
 #pragma unroll
     for (int k = 0; k < KT; ++k)
-      if (k < K) acc[k] = fmaf(to_f32(__ldg(weight + (int64_t)k * Cin + c)), v, acc[k]);
-  }
+      if (k < K) {
 #pragma unroll
-  for (int k = 0; k < KT; ++k)
+        for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+      }
+    if (lane == 0) {
+      float v[KT];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
-  if (lane == 0) {
-    float v[KT];
+      for (int k = 0; k < KT; ++k) v[k] = (k < K) ? acc[k] + (bias ? bias[k] : 0.f) : -INFINITY;
+      if (logits_out)
+        for (int k = 0; k < K; ++k) logits_out[(int64_t)inst0 * K + k] = v[k];
+      int cls = 0;
+      if (K > 1) {
+        float best = v[1], second = -INFINITY;
+        cls = 1;
 #pragma unroll
-    for (int k = 0; k < KT; ++k) v[k] = (k < K) ? acc[k] + (bias ? bias[k] : 0.f) : 0.f;
-    if (logits_out)
-      for (int k = 0; k < K; ++k) logits_out[(int64_t)warp * K + k] = v[k];
-    // softmax(...)[:, 1:] -> top-1 -> +1  (conductor.py:219-221)
-    const int cls = (K > 1) ? softmax_argmax_exact<KT>(v, K, 1) : 0;
-    const int id = ids[warp];
-    if (id >= 0 && id < lut_size) lut[id] = (uint8_t)cls;
-    else atomicOr(status, LDIFF_STATUS_INST_RANGE);
+        for (int k = 2; k < KT; ++k)
+          if (k < K) {
+            if (v[k] > best) { second = best; best = v[k]; cls = k; }
+            else second = fmaxf(second, v[k]);
+          }
+        if (__fsub_rn(best, second) <= kTieGap) cls = softmax_argmax_exact<KT>(v, K, 1);
+      }
+      const int img = inst0 / n_per_image;
+      const int id = ids[inst0 - img * n_per_image];
+      if (id >= 0 && id < lut_size) lut[(int64_t)img * lut_stride + id] = (uint8_t)cls;
+      else atomicOr(status, LDIFF_STATUS_INST_RANGE);
+    }
   }
 }
 
@@ -399,18 +453,23 @@ extern "C" int ldiff_head_logits(const void* feat, const void* weight, const flo
 
 extern "C" int ldiff_cell_classify(const void* inst_feats, const void* weight, const float* bias,
                                    const int32_t* inst_ids, uint8_t* lut, int lut_size,
-                                   float* logits_out, int N, int Cin, int K, int dtype, int* status,
-                                   void* stream) {
-  if (!inst_feats || !weight || !inst_ids || !lut || !status || N < 0 || Cin < 1 || K < 1 ||
-      lut_size < 1)
+                                   int64_t lut_stride, float* logits_out, int n_per_image, int B,
+                                   int Cin, int K, int dtype, int* status, void* stream) {
+  if (!inst_feats || !weight || !inst_ids || !lut || !status || n_per_image < 0 || B < 0 || Cin < 1 ||
+      K < 1 || lut_size < 1)
     return LDIFF_EINVAL;
-  if (K > 32) return LDIFF_EUNSUPPORTED;
-  if (N == 0) return LDIFF_OK;
+  if (K > 32 || (Cin % 8) != 0) return LDIFF_EUNSUPPORTED;
+  if (n_per_image == 0 || B == 0) return LDIFF_OK;
+  if (!aligned16(inst_feats) || !aligned16(weight)) return LDIFF_EALIGN;
   cudaStream_t st = (cudaStream_t)stream;
-  const int grid = (N * 32 + 255) / 256;
-#define CC(T, KT)                                                                                 \
-  cell_classify_kernel<T, KT><<<grid, 256, 0, st>>>((const T*)inst_feats, (const T*)weight, bias, \
-                                                    inst_ids, lut, lut_size, logits_out, N, Cin, K, status)
+  const int n_total = n_per_image * B;
+  int grid = (n_total + 3) / 4;                          // 4 warps per block, >= 1 instance per warp
+  const int cap = sm_count() * 8;
+  if (grid > cap) grid = cap;
+#define CC(T, KT)                                                                                   \
+  cell_classify_kernel<T, KT><<<grid, 128, 0, st>>>((const T*)inst_feats, (const T*)weight, bias,   \
+                                                    inst_ids, lut, lut_size, lut_stride, logits_out, \
+                                                    n_per_image, n_total, Cin, K, status)
   if (dtype == LDIFF_F32) { if (K <= 16) CC(float, 16); else CC(float, 32); }
   else if (dtype == LDIFF_BF16) { if (K <= 16) CC(__nv_bfloat16, 16); else CC(__nv_bfloat16, 32); }
   else return LDIFF_EUNSUPPORTED;

@@ -43,8 +43,8 @@ class PixelVectorBuilder:
 
     def set_label(self, label: torch.Tensor):
         """label: integer class map [B,H,W] (or [B,1,H,W]) -> last slot."""
-        lab = label.reshape(self.planes.shape[0], *self.planes.shape[2:])
-        self.planes[:, self.n].copy_(lab.to(torch.uint8))
+        lab = label.reshape(self.planes.shape[0], *self.planes.shape[2:]).to(torch.uint8).contiguous()
+        ops.copy_planes_u8(lab, self.planes[:, self.n])
 
     @property
     def vectors(self) -> torch.Tensor:

@@ -127,11 +127,20 @@ def _lift_argmax(logits: Tensor, mask: Tensor) -> None:
 
 def _cell_classify(feats: Tensor, weight: Tensor, bias: Optional[Tensor], inst_ids: Tensor,
                    lut: Tensor, logits_out: Optional[Tensor], status: Tensor) -> None:
+    """feats [B,N,Cin] (or [N,Cin]); lut [B,lut_size] (or [lut_size])."""
     _cuda(feats, weight, bias, inst_ids, lut, logits_out, status)
-    N, Cin = feats.shape
+    B = feats.shape[0] if feats.dim() == 3 else 1
+    N, Cin = feats.shape[-2], feats.shape[-1]
+    lut_stride = lut.stride(0) if lut.dim() == 2 else 0
     check(_cabi.lib().ldiff_cell_classify(_ptr(feats), _ptr(weight), _ptr(bias), _ptr(inst_ids),
-                                          _ptr(lut), lut.numel(), _ptr(logits_out), N, Cin,
+                                          _ptr(lut), lut.shape[-1], lut_stride, _ptr(logits_out), N, B, Cin,
                                           weight.shape[0], _dt(feats), _ptr(status), _stream(feats)))
+
+
+def _copy_planes_u8(src: Tensor, dst: Tensor) -> None:
+    _cuda(src, dst)
+    check(_cabi.lib().ldiff_copy_planes_u8(_ptr(src), _ptr(dst), src[0].numel(), src.shape[0], dst.stride(0),
+                                           _stream(src)))
 
 
 def _lut_paint(inst: Tensor, lut: Tensor, mask: Tensor, status: Tensor) -> None:
@@ -177,6 +186,7 @@ torch.library.custom_op("ldiff::bilinear_lift", mutates_args=("dst",))(_bilinear
 torch.library.custom_op("ldiff::head_logits", mutates_args=("logits",))(_head_logits)
 torch.library.custom_op("ldiff::lift_argmax", mutates_args=("mask",))(_lift_argmax)
 torch.library.custom_op("ldiff::cell_classify", mutates_args=("lut", "logits_out", "status"))(_cell_classify)
+torch.library.custom_op("ldiff::copy_planes_u8", mutates_args=("dst",))(_copy_planes_u8)
 torch.library.custom_op("ldiff::lut_paint", mutates_args=("mask", "status"))(_lut_paint)
 torch.library.custom_op("ldiff::argmax_channels", mutates_args=("out",))(_argmax_channels)
 torch.library.custom_op("ldiff::confusion_hist", mutates_args=("C", "status"))(_confusion_hist)
@@ -304,19 +314,38 @@ def head_argmax(feat: Tensor, weight: Tensor, bias: Optional[Tensor], size, retu
 
 def cell_classify(inst_feats: Tensor, weight: Tensor, bias: Optional[Tensor], inst_ids: Tensor,
                   lut_size: int, *, lut: Optional[Tensor] = None, return_logits: bool = False):
-    """conductor.py:218-221 -> class LUT (uint8 [lut_size], lut[0] = background)."""
+    """conductor.py:218-221 -> class LUT.  inst_feats [N,Cin] -> uint8 [lut_size], or a batch
+    [B,N,Cin] -> [B,lut_size] in one launch (``inst_ids`` [N] shared); lut[..., 0] = background."""
     _cuda(inst_feats, weight, inst_ids)
     _dense(inst_feats, "inst_feats"); _dense(weight, "weight")
+    if inst_feats.shape[-1] % 8:
+        raise ValueError("feature width must be a multiple of 8")
     if inst_ids.dtype != torch.int32:
         inst_ids = inst_ids.to(torch.int32)
+    batched = inst_feats.dim() == 3
     if lut is None:
-        lut = torch.zeros(lut_size, dtype=torch.uint8, device=inst_feats.device)
-    N, K = inst_feats.shape[0], weight.shape[0]
-    lo = torch.empty((N, K), dtype=torch.float32, device=inst_feats.device) if return_logits else None
+        shape = (inst_feats.shape[0], lut_size) if batched else (lut_size,)
+        lut = torch.zeros(shape, dtype=torch.uint8, device=inst_feats.device)
+    K = weight.shape[0]
+    lo = torch.empty(tuple(inst_feats.shape[:-1]) + (K,), dtype=torch.float32,
+                     device=inst_feats.device) if return_logits else None
     bias = None if bias is None else bias.float().contiguous()
-    _cell_classify(inst_feats, weight, bias, inst_ids.contiguous(), lut, lo,
-                                  status_word(inst_feats.device))
+    _cell_classify(inst_feats, weight, bias, inst_ids.contiguous(), lut, lo, status_word(inst_feats.device))
     return (lut, lo) if return_logits else lut
+
+
+def copy_planes_u8(src: Tensor, dst: Tensor) -> Tensor:
+    """dst[b] = src[b] for uint8 [B,H,W] planes, dst possibly a strided slot (dense planes)."""
+    _cuda(src, dst)
+    if src.dtype != torch.uint8 or dst.dtype != torch.uint8 or src.shape != dst.shape:
+        raise ValueError("uint8 tensors of the same shape expected")
+    _dense(src, "src")
+    n = src[0].numel()
+    if n % 16 or dst.stride(0) % 16 or dst[0].stride() != src[0].stride():
+        dst.copy_(src)                                   # odd sizes: plain strided copy
+        return dst
+    _copy_planes_u8(src, dst)
+    return dst
 
 
 def lut_paint(inst: Tensor, lut: Tensor, out: Optional[Tensor] = None) -> Tensor:

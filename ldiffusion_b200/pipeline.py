@@ -84,7 +84,7 @@ class HotPath:
 
     # number of ldiff kernels one pass launches
     def launches_per_pass(self) -> int:
-        return 4 * self.n + 3 + 2 + (self.B + 1) + 2
+        return 4 * self.n + 1 + 3 + 2 + 2 + 2
 
     def run(self, inp: HotPathInputs):
         """Enqueue one pass on the current stream; returns nothing (results live in
@@ -104,7 +104,7 @@ class HotPath:
             ops.decode_tail_gray(inp.decoded[i], want_rgb=False, rgb_out=self.rgb if last else None,
                                  gray_out=self.planes[:, i])
             ops.bilinear_lift(inp.decoded[i], self.feat_size, out=self.featcat, out_channel=i, gray=True)
-        self.planes[:, n].copy_(inp.gt)                                    # label slot of the pixel vectors
+        ops.copy_planes_u8(inp.gt, self.planes[:, n])                      # label slot of the pixel vectors
         ops.bilinear_lift(inp.gt.unsqueeze(1), self.feat_size, out=self.label_small)
         ops.bilinear_lift(inp.decoded[n - 1], self.feat_size, out=self.rgb_small)
         ops.bilinear_lift(self.rgb_small, (self.H, self.W), out=self.rgb_up)
@@ -112,9 +112,7 @@ class HotPath:
         ops._head_logits(inp.head_feat, self.head_w, self.head_b, self.logits)
         ops._lift_argmax(self.logits, self.mask_tissue)
         # cell head
-        for b in range(self.B):
-            ops._cell_classify(inp.inst_feats[b], self.cell_w, self.cell_b, self.inst_ids, self.lut[b], None,
-                               self.status)
+        ops._cell_classify(inp.inst_feats, self.cell_w, self.cell_b, self.inst_ids, self.lut, None, self.status)
         ops.lut_paint(inp.inst_map, self.lut, out=self.mask_cell)
         # metrics
         ops.confusion_hist(self.mask_tissue.view(-1), inp.gt.view(-1), self.K, out=self.C[0])

@@ -1,0 +1,121 @@
+"""GPU parity of one whole pass of the hot path (HotPath.run) against the oracle's
+CPU pipeline, eager and as a replayed CUDA graph, plus the pipelined host API."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import bilinear as obil
+from oracle import head as ohead
+from oracle import laplace as olap
+from oracle import metrics as omet
+from oracle.pipeline import run_chain
+
+pytestmark = pytest.mark.gpu
+
+CFG = dict(batch=2, height=256, width=256, num_classes=11, num_steps=5, n_instances=40)
+
+
+def _setup(dtype, seed=7):
+    from ldiffusion_b200.pipeline import HotPath, HotPathInputs, synth_inputs
+    host = synth_inputs(CFG["batch"], CFG["height"], CFG["width"], CFG["num_classes"], CFG["num_steps"],
+                        dtype=dtype, device="cpu", head_hw=(8, 8), n_instances=CFG["n_instances"], seed=seed)
+    dev = HotPathInputs(*[([t.cuda() for t in f] if isinstance(f, list) else f.cuda())
+                          for f in (host.latents, host.eps, host.decoded, host.head_feat, host.inst_map,
+                                    host.inst_feats, host.gt)])
+    hp = HotPath(dtype=dtype, device="cuda", head_hw=(8, 8), seed=seed, **CFG)
+    return host, dev, hp
+
+
+def _check(host, hp, dtype):
+    K, n = CFG["num_classes"], CFG["num_steps"]
+    res = {k: (v.cpu() if torch.is_tensor(v) else [t.cpu() for t in v]) for k, v in hp.results().items()}
+    ref = run_chain(host, K, hp.head_w.cpu(), hp.head_b.cpu(), hp.cell_w.cpu(), hp.cell_b.cpu())
+    exact = dtype == torch.float32
+    # a-2: latents after the last step
+    if exact:
+        assert torch.equal(res["latents"], ref["lat"][-1])
+    else:
+        torch.testing.assert_close(res["latents"].float(), ref["lat"][-1], rtol=2e-2, atol=2e-2)
+    # a-1: the kernel's own Philox stream, restated on the CPU
+    blocks = (host.latents.numel() + 3) // 4
+    for i, t in enumerate(hp.scheduler._host_timesteps):
+        nz = olap.laplace_philox(host.latents.numel(), hp.scheduler.laplace_scale(t), hp.seed, i * blocks)
+        want = (host.latents.float().reshape(-1) + nz).reshape(host.latents.shape)
+        torch.testing.assert_close(res["noisy"][i].float(), want, rtol=1e-5 if exact else 1e-2,
+                                   atol=1e-6 if exact else 1e-2)
+    # a-3: integer exact (given the same decoded tensors, fp32 or bf16)
+    assert np.array_equal(res["pixel_planes"].numpy(), ref["pixel_planes"])
+    assert np.array_equal(res["rgb"].numpy(), ref["rgb"])
+    # a-4
+    if exact:
+        want = obil.feature_concat_spec([d.numpy() for d in host.decoded])
+        assert np.array_equal(res["featcat"].numpy(), want)
+        torch.testing.assert_close(res["featcat"], ref["featcat"], rtol=1e-3, atol=1e-6)
+        small = obil.lift_spec(host.decoded[-1].numpy(), (64, 64))
+        assert np.array_equal(res["rgb_up"].numpy(), obil.lift_spec(small, (CFG["height"], CFG["width"])))
+    else:
+        torch.testing.assert_close(res["featcat"].float(), ref["featcat"], rtol=2e-2, atol=2e-2)
+    assert torch.equal(res["label_small"], ref["label_small"])
+    # a-5: logits within tolerance, masks exact given the kernel's own logits
+    torch.testing.assert_close(res["logits"], ref["logits"], rtol=1e-3, atol=1e-3)
+    assert np.array_equal(res["mask_tissue"].numpy(),
+                          ohead.lift_argmax_spec(res["logits"].numpy(), (CFG["height"], CFG["width"])))
+    assert (res["mask_cell"] != ref["mask_cell"]).float().mean() < 2e-3   # only if an instance logit flips
+    # a-6: exact given the masks
+    want_c = np.stack([omet.confusion_matrix(res[m].numpy(), host.gt.numpy(), K) for m in ("mask_tissue", "mask_cell")])
+    assert np.array_equal(res["confusion"].numpy(), want_c)
+    if exact and torch.equal(res["mask_tissue"], ref["mask_tissue"]) and torch.equal(res["mask_cell"], ref["mask_cell"]):
+        assert np.array_equal(res["confusion"].numpy(), ref["confusion"])
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_pass_matches_oracle_pipeline(dtype):
+    from ldiffusion_b200 import _cabi, ops
+    host, dev, hp = _setup(dtype)
+    c0 = _cabi.launch_count()
+    hp.run(dev)
+    assert _cabi.launch_count() - c0 == hp.launches_per_pass()
+    torch.cuda.synchronize()
+    ops.check_status("cuda")
+    _check(host, hp, dtype)
+
+
+def test_graph_replay_equals_eager():
+    host, dev, hp = _setup(torch.bfloat16, seed=11)
+    hp.run(dev)
+    torch.cuda.synchronize()
+    eager = {k: (v.clone() if torch.is_tensor(v) else [t.clone() for t in v]) for k, v in hp.results().items()}
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(g, stream=s):
+            hp.run(dev)
+    for k, v in hp.results().items():                       # scribble over the outputs, then replay
+        for t in (v if isinstance(v, list) else [v]):
+            t.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    for k, v in hp.results().items():
+        for a, b in zip(v if isinstance(v, list) else [v], eager[k] if isinstance(eager[k], list) else [eager[k]]):
+            assert torch.equal(a, b), k
+
+
+def test_run_host_pipelined_matches_device_pass():
+    from ldiffusion_b200.pipeline import synth_inputs
+    host, dev, hp = _setup(torch.bfloat16, seed=13)
+    hosts = [synth_inputs(CFG["batch"], CFG["height"], CFG["width"], CFG["num_classes"], CFG["num_steps"],
+                          dtype=torch.bfloat16, device="cpu", head_hw=(8, 8), n_instances=CFG["n_instances"],
+                          seed=20 + i, pin=True) for i in range(3)]
+    outs = [hp.alloc_host_results() for _ in range(3)]
+    hp.run_host(hosts, outs)
+    torch.cuda.synchronize()
+    for hb, out in zip(hosts, outs):
+        from ldiffusion_b200.pipeline import HotPathInputs
+        d = HotPathInputs(*[([t.cuda() for t in f] if isinstance(f, list) else f.cuda())
+                            for f in (hb.latents, hb.eps, hb.decoded, hb.head_feat, hb.inst_map, hb.inst_feats, hb.gt)])
+        hp.run(d)
+        torch.cuda.synchronize()
+        res = hp.results()
+        for k in hp.RESULT_KEYS:
+            assert torch.equal(out[k], res[k].cpu()), k
