@@ -19,6 +19,8 @@ from .features import (PixelVectorBuilder, feature_concat, label_down, pixel_lat
 from .head import TissueHead, cell_mask, tissue_mask  # noqa: F401
 from .metrics import (confusion_matrix, evaluate, frequency_weighted_iou, mean_iou_and_per_class,  # noqa: F401
                       micro_dice, pixel_accuracy)
+from .ldiffusion import LDiffusionModel  # noqa: F401
 from .scheduler import LaplacePLMSScheduler  # noqa: F401
+from .segmentor import Segmentor  # noqa: F401
 
 __version__ = "0.1.0"
