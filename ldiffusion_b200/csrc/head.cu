@@ -58,7 +58,35 @@ __device__ __noinline__ int softmax_argmax_exact(const float (&v)[KT], int K, in
   return best;
 }
 
-// Cold path: one pixel resolved from scratch with the pinned softmax.  Kept out of
+// Cold path taken INSIDE the row loop: the K lifted logits of one pixel by value (the
+// struct travels through the ABI's parameter space, so the hot loop keeps its
+// register allocation), no memory traffic, ~1k instructions.
+template <int K>
+struct Vals { float v[K]; };
+
+template <int K>
+__device__ __noinline__ int exact_from_values(Vals<K> x) {
+  float m = x.v[0];
+#pragma unroll 1
+  for (int k = 1; k < K; ++k) m = fmaxf(m, x.v[k]);
+  float e[K];
+  float s = 0.f;
+#pragma unroll 1
+  for (int k = 0; k < K; ++k) {
+    e[k] = (float)exp((double)__fsub_rn(x.v[k], m));
+    s = __fadd_rn(s, e[k]);
+  }
+  int best = 0;
+  float pb = __fdiv_rn(e[0], s);
+#pragma unroll 1
+  for (int k = 1; k < K; ++k) {
+    const float p = __fdiv_rn(e[k], s);
+    if (p > pb) { pb = p; best = k; }
+  }
+  return best;
+}
+
+// Cold path of the generic kernel: one pixel resolved from scratch with the pinned softmax.  Kept out of
 // line and fed scalars only so that it costs the hot loops no registers.
 __device__ __noinline__ int exact_pixel(const float* __restrict__ lb, int K, int plane, int in_w,
                                         int yi0, int yi1, float yl0, float yl1, int xi0, int xi1,
@@ -89,11 +117,14 @@ __device__ __noinline__ int exact_pixel(const float* __restrict__ lb, int K, int
 // rows in registers (T, U), reloaded only when the source row pair changes, so a
 // pixel costs per class: FMUL+FFMA (vertical lerp), FMNMX (running max), then
 // FSETP + one predicated IADD that accumulates "16+k" for every class within
-// kTieGap of the max: count == 1 gives the argmax directly; anything else only
-// sets a bit, and those (rare) pixels are re-resolved after the row loop by the
-// out-of-line pinned softmax.  The kernel is issue-bound (ALU), not HBM-bound: it
+// kTieGap of the max: count == 1 gives the argmax directly; anything else (rare)
+// is queued per warp and resolved by the out-of-line pinned softmax AFTER the row
+// loop, when none of the loop's registers is live, with the queue spread over the
+// warp's lanes (resolving in place costs 60 registers; resolving serially in the
+// owning thread made a vertical run of 16 near-ties cost 60 us).  The kernel is issue-bound (ALU), not HBM-bound: it
 // reads 0.36 MB of logits and writes 1 byte per pixel.
 constexpr int kBand = 32;
+constexpr int kQueue = 128;
 
 // acc += (v >= thr) ? C : 0 as exactly FSETP + one predicated integer add
 template <int C>
@@ -109,11 +140,15 @@ __device__ __forceinline__ int tie_acc(const float (&v)[K], float thr, std::inte
 }
 
 template <int K, int COLS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)   // 3 CTAs/SM: the cold fp64 exp may spill, the hot loop must not
 lift_argmax_kernel(const float* __restrict__ logits, uint8_t* __restrict__ mask, AxisH ay, AxisH ax) {
   __shared__ int s_i0[kBand], s_i1[kBand];
   __shared__ float s_l0[kBand], s_l1[kBand];
+  __shared__ uint32_t s_q[8][kQueue];                    // per-warp queue of near-tie pixels (row, column)
+  __shared__ int s_qn[8];
+  const int warp_in_block = threadIdx.x >> 5;
   const int Y0 = blockIdx.y * kBand, Y1 = min(Y0 + kBand, ay.out);
+  if (threadIdx.x < 8) s_qn[threadIdx.x] = 0;
   if (threadIdx.x < Y1 - Y0) {
     const TapH t = tap(ay, Y0 + threadIdx.x);
     s_i0[threadIdx.x] = t.i0; s_i1[threadIdx.x] = t.i1;
@@ -121,7 +156,7 @@ lift_argmax_kernel(const float* __restrict__ logits, uint8_t* __restrict__ mask,
   }
   __syncthreads();
   const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * COLS;
-  if (x0 >= ax.out) return;
+  const bool active = x0 < ax.out;                       // inactive lanes still help in the epilogue
   const int b = blockIdx.z;
   const int plane = ay.in * ax.in;
   const float* lb = logits + (int64_t)b * K * plane;
@@ -132,11 +167,11 @@ lift_argmax_kernel(const float* __restrict__ logits, uint8_t* __restrict__ mask,
   for (int c = 0; c < COLS; ++c) tx[c] = tap(ax, min(x0 + c, ax.out - 1));
 
   float T[COLS][K], U[COLS][K];
-  uint32_t amb[COLS];
+  uint32_t overflow[COLS];
 #pragma unroll
-  for (int c = 0; c < COLS; ++c) amb[c] = 0;
+  for (int c = 0; c < COLS; ++c) overflow[c] = 0;
   int cy0 = -1, cy1 = -1;
-  for (int r = 0; r < Y1 - Y0; ++r) {
+  for (int r = 0; active && r < Y1 - Y0; ++r) {
     const int i0 = s_i0[r], i1 = s_i1[r];
     const float l0 = s_l0[r], l1 = s_l1[r];
     if (i0 != cy0 || i1 != cy1) {                      // warp-uniform
@@ -164,7 +199,11 @@ lift_argmax_kernel(const float* __restrict__ logits, uint8_t* __restrict__ mask,
       }
       const float thr = __fsub_rn(m, kTieGap);
       const int acc = tie_acc(v, thr, std::make_integer_sequence<int, K>{});
-      if ((acc >> 4) != 1) amb[c] |= 1u << r;          // rare: tie or near-tie
+      if ((acc >> 4) != 1) {                             // rare: tie or near-tie -> queue for the epilogue
+        const int slot = atomicAdd(&s_qn[warp_in_block], 1);
+        if (slot < kQueue) s_q[warp_in_block][slot] = ((uint32_t)r << 16) | (uint32_t)(threadIdx.x * COLS + c);
+        else overflow[c] |= 1u << r;
+      }
       packed |= (uint32_t)(acc & 15) << (8 * c);
     }
     if (COLS == 1) out[0] = (uint8_t)packed;
@@ -172,9 +211,31 @@ lift_argmax_kernel(const float* __restrict__ logits, uint8_t* __restrict__ mask,
     else *reinterpret_cast<uint32_t*>(out) = packed;
     out += ax.out;
   }
+  // ---- cold epilogue: nothing of the hot loop is live any more.  The warp's queued pixels are
+  // spread over its lanes (a vertical run of near-ties in ONE column would otherwise serialise
+  // in one thread); each lane gathers the 4K logits of its pixel with independent loads.
+  __syncwarp();
+  const int nq = min(s_qn[warp_in_block], kQueue);
+  const int xblock = blockIdx.x * blockDim.x * COLS;
+  for (int e = (int)(threadIdx.x & 31); e < nq; e += 32) {
+    const uint32_t ent = s_q[warp_in_block][e];
+    const int r = (int)(ent >> 16), x = xblock + (int)(ent & 0xffffu);
+    const TapH t = tap(ax, x);
+    const int i0 = s_i0[r], i1 = s_i1[r];
+    const float l0 = s_l0[r], l1 = s_l1[r];
+    Vals<K> vals;
 #pragma unroll
-  for (int c = 0; c < COLS; ++c) {
-    uint32_t bits = amb[c];
+    for (int k = 0; k < K; ++k) {
+      const float* r0 = lb + k * plane + i0 * ax.in;
+      const float* r1 = lb + k * plane + i1 * ax.in;
+      vals.v[k] = lerp2(l0, lerp2(t.l0, __ldg(r0 + t.i0), t.l1, __ldg(r0 + t.i1)), l1,
+                        lerp2(t.l0, __ldg(r1 + t.i0), t.l1, __ldg(r1 + t.i1)));
+    }
+    mask[((int64_t)b * ay.out + Y0 + r) * ax.out + x] = (uint8_t)exact_from_values<K>(vals);
+  }
+#pragma unroll
+  for (int c = 0; c < COLS; ++c) {                       // queue overflow (> kQueue events in a warp)
+    uint32_t bits = overflow[c];
     while (bits) {
       const int r = __ffs(bits) - 1;
       bits &= bits - 1;
@@ -413,13 +474,20 @@ extern "C" int ldiff_lift_argmax(const float* logits, uint8_t* mask, int B, int 
   if (B == 0) return LDIFF_OK;
   cudaStream_t st = (cudaStream_t)stream;
   AxisH ay{(float)h / (float)H, h, H}, ax{(float)w / (float)W, w, W};
-  constexpr int COLS = 2;
-  if (K <= 15 && (W % COLS) == 0) {
-    dim3 grid((W / COLS + 255) / 256, (H + kBand - 1) / kBand, B);
+  if (K <= 15) {
+    // two columns per thread while T/U (4K registers) fit the 80-register budget, else one
+    const int cols = (K <= 12 && (W % 2) == 0) ? 2 : 1;
+    dim3 grid((W / cols + 255) / 256, (H + kBand - 1) / kBand, B);
     switch (K) {
-#define LA(KK) case KK: lift_argmax_kernel<KK, COLS><<<grid, 256, 0, st>>>(logits, mask, ay, ax); break;
-      LA(1) LA(2) LA(3) LA(4) LA(5) LA(6) LA(7) LA(8) LA(9) LA(10) LA(11) LA(12) LA(13) LA(14) LA(15)
-#undef LA
+#define LA2(KK) case KK:                                                                      \
+      if (cols == 2) lift_argmax_kernel<KK, 2><<<grid, 256, 0, st>>>(logits, mask, ay, ax);    \
+      else lift_argmax_kernel<KK, 1><<<grid, 256, 0, st>>>(logits, mask, ay, ax);              \
+      break;
+#define LA1(KK) case KK: lift_argmax_kernel<KK, 1><<<grid, 256, 0, st>>>(logits, mask, ay, ax); break;
+      LA2(1) LA2(2) LA2(3) LA2(4) LA2(5) LA2(6) LA2(7) LA2(8) LA2(9) LA2(10) LA2(11) LA2(12)
+      LA1(13) LA1(14) LA1(15)
+#undef LA2
+#undef LA1
     }
   } else {
     const int64_t total = (int64_t)H * W * B;

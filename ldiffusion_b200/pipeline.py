@@ -86,36 +86,76 @@ class HotPath:
     def launches_per_pass(self) -> int:
         return 4 * self.n + 1 + 3 + 2 + 2 + 2
 
-    def run(self, inp: HotPathInputs):
-        """Enqueue one pass on the current stream; returns nothing (results live in
-        the preallocated buffers).  Graph-capturable: no allocation, no sync."""
+    def run(self, inp: HotPathInputs, concurrent: bool = True):
+        """Enqueue one pass; returns nothing (results live in the preallocated buffers).
+        Graph-capturable: no allocation, no sync.
+
+        The pass is five independent chains (sampler, decode tails, training-path lifts,
+        tissue head, cell head).  With ``concurrent`` they are forked onto side streams and
+        joined at the end, so inside a CUDA graph the latency-bound latent-sized launches
+        and the ALU-bound lift+argmax overlap the HBM-bound decode tails instead of
+        queueing behind them."""
+        cur = torch.cuda.current_stream(self.device)
+        n = self.n
+        self.C.zero_()
+        if concurrent:
+            side = self._side_streams()
+            for s in side:
+                s.wait_stream(cur)
+        else:
+            side = [cur] * 4
+        with torch.cuda.stream(side[0]):
+            self._chain_sampler(inp)
+        with torch.cuda.stream(side[1]):
+            self._chain_lifts(inp)
+        with torch.cuda.stream(side[2]):
+            self._chain_tissue(inp)
+        with torch.cuda.stream(side[3]):
+            self._chain_cell(inp)
+        # the bandwidth-heavy chain stays on the caller's stream
+        for i in range(n):
+            last = i == n - 1
+            ops.decode_tail_gray(inp.decoded[i], want_rgb=False, rgb_out=self.rgb if last else None,
+                                 gray_out=self.planes[:, i])
+        ops.copy_planes_u8(inp.gt, self.planes[:, n])                      # label slot of the pixel vectors
+        if concurrent:
+            for s in side:
+                cur.wait_stream(s)
+
+    def _side_streams(self):
+        st = getattr(self, "_side", None)
+        if st is None:
+            st = [torch.cuda.Stream(self.device) for _ in range(4)]
+            self._side = st
+        return st
+
+    def _chain_sampler(self, inp):
         n, sch = self.n, self.scheduler
         sch.set_timesteps(n - 1)
         ts = sch._host_timesteps
         x = inp.latents
         blocks = (self.lat_elems + 3) // 4
-        self.C.zero_()
         for i in range(n):
-            t = ts[i]
-            ops.laplace_qsample(inp.latents, sch.laplace_scale(t), seed=self.seed, offset=i * blocks,
+            ops.laplace_qsample(inp.latents, sch.laplace_scale(ts[i]), seed=self.seed, offset=i * blocks,
                                 out=self.noisy[i])
-            x = sch.step(inp.eps[i], t, x, out=self.lat[i]).prev_sample
-            last = i == n - 1
-            ops.decode_tail_gray(inp.decoded[i], want_rgb=False, rgb_out=self.rgb if last else None,
-                                 gray_out=self.planes[:, i])
+            x = sch.step(inp.eps[i], ts[i], x, out=self.lat[i]).prev_sample
+
+    def _chain_lifts(self, inp):
+        n = self.n
+        for i in range(n):
             ops.bilinear_lift(inp.decoded[i], self.feat_size, out=self.featcat, out_channel=i, gray=True)
-        ops.copy_planes_u8(inp.gt, self.planes[:, n])                      # label slot of the pixel vectors
         ops.bilinear_lift(inp.gt.unsqueeze(1), self.feat_size, out=self.label_small)
         ops.bilinear_lift(inp.decoded[n - 1], self.feat_size, out=self.rgb_small)
         ops.bilinear_lift(self.rgb_small, (self.H, self.W), out=self.rgb_up)
-        # tissue head
+
+    def _chain_tissue(self, inp):
         ops._head_logits(inp.head_feat, self.head_w, self.head_b, self.logits)
         ops._lift_argmax(self.logits, self.mask_tissue)
-        # cell head
+        ops.confusion_hist(self.mask_tissue.view(-1), inp.gt.view(-1), self.K, out=self.C[0])
+
+    def _chain_cell(self, inp):
         ops._cell_classify(inp.inst_feats, self.cell_w, self.cell_b, self.inst_ids, self.lut, None, self.status)
         ops.lut_paint(inp.inst_map, self.lut, out=self.mask_cell)
-        # metrics
-        ops.confusion_hist(self.mask_tissue.view(-1), inp.gt.view(-1), self.K, out=self.C[0])
         ops.confusion_hist(self.mask_cell.view(-1), inp.gt.view(-1), self.K, out=self.C[1])
 
     # ------------------------------------------------------------------
