@@ -12,6 +12,7 @@
 // probabilities, which needs a top-2 gap below ~2e-7; pixels whose gap is
 // <= kTieGap re-evaluate the pinned softmax (exp in fp64 rounded to fp32,
 // sequential fp32 sum, fp32 division, first maximum).
+#include <cstdlib>
 #include <utility>
 
 #include "common.cuh"
@@ -115,15 +116,16 @@ __device__ __noinline__ int exact_pixel(const float* __restrict__ lb, int K, int
 // A thread owns COLS adjacent output columns and walks a band of output rows.
 // Per (column, class) it keeps the horizontally lifted logits of the two source
 // rows in registers (T, U), reloaded only when the source row pair changes, so a
-// pixel costs per class: FMUL+FFMA (vertical lerp), FMNMX (running max), then
-// FSETP + one predicated IADD that accumulates "16+k" for every class within
-// kTieGap of the max: count == 1 gives the argmax directly; anything else (rare)
+// pixel costs per class: half an FMUL2 + half an FFMA2 (vertical lerp on the packed
+// fp32x2 pipe), a third of an FMNMX3 (running max), half an FADD2 (v - thr) and one
+// funnel shift that collects its sign bit: a single zero bit gives the argmax
+// directly; anything else (rare)
 // is queued per warp and resolved by the out-of-line pinned softmax AFTER the row
 // loop, when none of the loop's registers is live, with the queue spread over the
 // warp's lanes (resolving in place costs 60 registers; resolving serially in the
 // owning thread made a vertical run of 16 near-ties cost 60 us).  The kernel is issue-bound (ALU), not HBM-bound: it
 // reads 0.36 MB of logits and writes 1 byte per pixel.
-constexpr int kBand = 32;
+constexpr int kBand = 128;                             // longest band (output rows per source row)
 constexpr int kQueue = 128;
 
 // acc += (v >= thr) ? C : 0 as exactly FSETP + one predicated integer add
@@ -139,34 +141,52 @@ __device__ __forceinline__ int tie_acc(const float (&v)[K], float thr, std::inte
   return acc;
 }
 
-template <int K, int COLS>
-__global__ void __launch_bounds__(256, 3)   // 3 CTAs/SM: the cold fp64 exp may spill, the hot loop must not
+template <int K, int COLS, int MINB>
+__global__ void __launch_bounds__(256, MINB)   // the cold fp64 exp may spill, the hot loop must not
 lift_argmax_kernel(const float* __restrict__ logits, uint8_t* __restrict__ mask, AxisH ay, AxisH ax) {
   __shared__ int s_i0[kBand], s_i1[kBand];
   __shared__ float s_l0[kBand], s_l1[kBand];
   __shared__ uint32_t s_q[8][kQueue];                    // per-warp queue of near-tie pixels (row, column)
   __shared__ int s_qn[8];
   const int warp_in_block = threadIdx.x >> 5;
-  const int Y0 = blockIdx.y * kBand, Y1 = min(Y0 + kBand, ay.out);
+  // blockIdx.y = a source row iy; the band is every output row whose upper tap is iy, so the
+  // whole band shares one source row pair and T/U are gathered exactly once
+  const int iy = blockIdx.y;
+  auto first_row = [&](int i) {
+    if (i <= 0) return 0;
+    int y = (int)ceilf(((float)i + 0.5f) / ay.scale - 0.5f);
+    y = max(0, min(y, ay.out));
+    while (y > 0 && tap(ay, y - 1).i0 >= i) --y;
+    while (y < ay.out && tap(ay, y).i0 < i) ++y;
+    return y;
+  };
+  const int Y0 = first_row(iy);
+  const int Y1 = (iy + 1 >= ay.in) ? ay.out : first_row(iy + 1);
+  if (Y0 >= Y1) return;                                  // (block-uniform)
   if (threadIdx.x < 8) s_qn[threadIdx.x] = 0;
   if (threadIdx.x < Y1 - Y0) {
     const TapH t = tap(ay, Y0 + threadIdx.x);
     s_i0[threadIdx.x] = t.i0; s_i1[threadIdx.x] = t.i1;
     s_l0[threadIdx.x] = t.l0; s_l1[threadIdx.x] = t.l1;
   }
-  __syncthreads();
-  const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * COLS;
-  const bool active = x0 < ax.out;                       // inactive lanes still help in the epilogue
   const int b = blockIdx.z;
   const int plane = ay.in * ax.in;
   const float* lb = logits + (int64_t)b * K * plane;
+  __syncthreads();
+  const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * COLS;
+  const bool active = x0 < ax.out;                       // inactive lanes still help in the epilogue
   uint8_t* out = mask + ((int64_t)b * ay.out + Y0) * ax.out + x0;
 
   TapH tx[COLS];
 #pragma unroll
   for (int c = 0; c < COLS; ++c) tx[c] = tap(ax, min(x0 + c, ax.out - 1));
 
-  float T[COLS][K], U[COLS][K];
+  // classes in pairs for the packed fp32x2 pipe (FMUL2 / FFMA2 / FADD2: IEEE per lane, so
+  // the roundings are those of the scalar chain); an odd K is padded with a class that can
+  // never be within kTieGap of the maximum
+  constexpr int KP = (K + 1) / 2;
+  constexpr float kPad = -1e30f;
+  float2 T[COLS][KP], U[COLS][KP];
   uint32_t overflow[COLS];
 #pragma unroll
   for (int c = 0; c < COLS; ++c) overflow[c] = 0;
@@ -177,34 +197,78 @@ lift_argmax_kernel(const float* __restrict__ logits, uint8_t* __restrict__ mask,
     if (i0 != cy0 || i1 != cy1) {                      // warp-uniform
       cy0 = i0; cy1 = i1;
 #pragma unroll
-      for (int k = 0; k < K; ++k) {
-        const float* r0 = lb + k * plane + i0 * ax.in;
-        const float* r1 = lb + k * plane + i1 * ax.in;
+      for (int k = 0; k < 2 * KP; ++k) {
+        float t[COLS], u[COLS];
+#pragma unroll
+        for (int c = 0; c < COLS; ++c) { t[c] = kPad; u[c] = kPad; }
+        if (k < K) {
+          const float* r0 = lb + k * plane + i0 * ax.in;
+          const float* r1 = lb + k * plane + i1 * ax.in;
+#pragma unroll
+          for (int c = 0; c < COLS; ++c) {
+            t[c] = lerp2(tx[c].l0, __ldg(r0 + tx[c].i0), tx[c].l1, __ldg(r0 + tx[c].i1));
+            u[c] = lerp2(tx[c].l0, __ldg(r1 + tx[c].i0), tx[c].l1, __ldg(r1 + tx[c].i1));
+          }
+        }
 #pragma unroll
         for (int c = 0; c < COLS; ++c) {
-          T[c][k] = lerp2(tx[c].l0, __ldg(r0 + tx[c].i0), tx[c].l1, __ldg(r0 + tx[c].i1));
-          U[c][k] = lerp2(tx[c].l0, __ldg(r1 + tx[c].i0), tx[c].l1, __ldg(r1 + tx[c].i1));
+          if (k & 1) { T[c][k >> 1].y = t[c]; U[c][k >> 1].y = u[c]; }
+          else { T[c][k >> 1].x = t[c]; U[c][k >> 1].x = u[c]; }
         }
       }
     }
+    const float2 l0p = make_float2(l0, l0), l1p = make_float2(l1, l1);
     uint32_t packed = 0;
 #pragma unroll
     for (int c = 0; c < COLS; ++c) {
-      float v[K];
-      float m = -INFINITY;
+      float2 v[KP];
 #pragma unroll
-      for (int k = 0; k < K; ++k) {
-        v[k] = lerp2(l0, T[c][k], l1, U[c][k]);
-        m = fmaxf(m, v[k]);
+      for (int j = 0; j < KP; ++j)
+        v[j] = __ffma2_rn(l0p, T[c][j], __fmul2_rn(l1p, U[c][j]));   // == fma(l0, T, fl(l1*U)) per class
+      // running max as a tree (short dependency chains: the kernel runs at low occupancy)
+      float mp[KP];
+#pragma unroll
+      for (int j = 0; j < KP; ++j) mp[j] = fmaxf(v[j].x, v[j].y);
+      float m = mp[0];
+      if (KP == 2) m = fmaxf(mp[0], mp[1]);
+      if (KP == 3) m = fmaxf(fmaxf(mp[0], mp[1]), mp[2]);
+      if (KP == 4) m = fmaxf(fmaxf(mp[0], mp[1]), fmaxf(mp[2], mp[3]));
+      if (KP == 5) m = fmaxf(fmaxf(fmaxf(mp[0], mp[1]), mp[2]), fmaxf(mp[3], mp[4]));
+      if (KP == 6) m = fmaxf(fmaxf(fmaxf(mp[0], mp[1]), mp[2]), fmaxf(fmaxf(mp[3], mp[4]), mp[5]));
+      if (KP == 7) m = fmaxf(fmaxf(fmaxf(fmaxf(mp[0], mp[1]), mp[2]), fmaxf(fmaxf(mp[3], mp[4]), mp[5])), mp[6]);
+      if (KP == 8)
+        m = fmaxf(fmaxf(fmaxf(mp[0], mp[1]), fmaxf(mp[2], mp[3])), fmaxf(fmaxf(mp[4], mp[5]), fmaxf(mp[6], mp[7])));
+      // sign(v - thr) is set exactly when v < thr.  The sign bits are funnel-shifted into
+      // per-group accumulators (independent chains), then concatenated: bit (2*KP-1-k) == 0
+      // marks class k as being within kTieGap of the maximum
+      const float nthr = __fsub_rn(kTieGap, m);
+      const float2 nthr2 = make_float2(nthr, nthr);
+      constexpr int G = (KP + 1) / 2;                    // groups of two pairs (four classes)
+      uint32_t grp[G];
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        grp[g] = 0;
+#pragma unroll
+        for (int j = 2 * g; j < 2 * g + 2 && j < KP; ++j) {
+          const float2 d = __fadd2_rn(v[j], nthr2);
+          grp[g] = __funnelshift_l(__float_as_uint(d.x), grp[g], 1);
+          grp[g] = __funnelshift_l(__float_as_uint(d.y), grp[g], 1);
+        }
       }
-      const float thr = __fsub_rn(m, kTieGap);
-      const int acc = tie_acc(v, thr, std::make_integer_sequence<int, K>{});
-      if ((acc >> 4) != 1) {                             // rare: tie or near-tie -> queue for the epilogue
+      uint32_t below = 0;
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const int nb = (2 * g + 2 <= KP) ? 4 : 2;        // classes in this group
+        below = (below << nb) | grp[g];
+      }
+      const uint32_t cand = ~below & ((1u << (2 * KP)) - 1u);
+      const int idx = __clz(cand) - (32 - 2 * KP);       // class of the highest candidate bit
+      if (cand & (cand - 1)) {                           // rare: more than one candidate -> queue for the epilogue
         const int slot = atomicAdd(&s_qn[warp_in_block], 1);
         if (slot < kQueue) s_q[warp_in_block][slot] = ((uint32_t)r << 16) | (uint32_t)(threadIdx.x * COLS + c);
         else overflow[c] |= 1u << r;
       }
-      packed |= (uint32_t)(acc & 15) << (8 * c);
+      packed |= (uint32_t)idx << (8 * c);
     }
     if (COLS == 1) out[0] = (uint8_t)packed;
     else if (COLS == 2) *reinterpret_cast<uint16_t*>(out) = (uint16_t)packed;
@@ -474,16 +538,21 @@ extern "C" int ldiff_lift_argmax(const float* logits, uint8_t* mask, int B, int 
   if (B == 0) return LDIFF_OK;
   cudaStream_t st = (cudaStream_t)stream;
   AxisH ay{(float)h / (float)H, h, H}, ax{(float)w / (float)W, w, W};
-  if (K <= 15) {
+  if (K <= 15 && H >= 4 * h && (H + h - 1) / h + 2 <= kBand && h <= 65535) {
     // two columns per thread while T/U (4K registers) fit the 80-register budget, else one
-    const int cols = (K <= 12 && (W % 2) == 0) ? 2 : 1;
-    dim3 grid((W / cols + 255) / 256, (H + kBand - 1) / kBand, B);
+    // variant: 0 = 2 columns/thread, 2 CTAs/SM; 1 = 1 column, 3 CTAs/SM; 2 = 1 column, 4 CTAs/SM
+    static const int knob = [] { const char* e = getenv("LDIFF_ARGMAX_VARIANT"); return e ? atoi(e) : -1; }();
+    int variant = knob >= 0 ? knob : 1;                    // measured: 1 is fastest at 32x lift, K=11
+    if (K > 12 || (W % 2) != 0) variant = variant == 0 ? 1 : variant;
+    const int cols = variant == 0 ? 2 : 1;
+    dim3 grid((W / cols + 255) / 256, h, B);
     switch (K) {
-#define LA2(KK) case KK:                                                                      \
-      if (cols == 2) lift_argmax_kernel<KK, 2><<<grid, 256, 0, st>>>(logits, mask, ay, ax);    \
-      else lift_argmax_kernel<KK, 1><<<grid, 256, 0, st>>>(logits, mask, ay, ax);              \
+#define LA2(KK) case KK:                                                                               \
+      if (variant == 0) lift_argmax_kernel<KK, 2, 2><<<grid, 256, 0, st>>>(logits, mask, ay, ax);       \
+      else if (variant == 1) lift_argmax_kernel<KK, 1, 3><<<grid, 256, 0, st>>>(logits, mask, ay, ax);  \
+      else lift_argmax_kernel<KK, 1, 4><<<grid, 256, 0, st>>>(logits, mask, ay, ax);                    \
       break;
-#define LA1(KK) case KK: lift_argmax_kernel<KK, 1><<<grid, 256, 0, st>>>(logits, mask, ay, ax); break;
+#define LA1(KK) case KK: lift_argmax_kernel<KK, 1, 3><<<grid, 256, 0, st>>>(logits, mask, ay, ax); break;
       LA2(1) LA2(2) LA2(3) LA2(4) LA2(5) LA2(6) LA2(7) LA2(8) LA2(9) LA2(10) LA2(11) LA2(12)
       LA1(13) LA1(14) LA1(15)
 #undef LA2

@@ -83,3 +83,33 @@ for name, fn in STAGES.items():
         tot += us
     print(f"{name:16s} {us:8.2f} us")
 print(f"{'sum of stages':16s} {tot:8.2f} us")
+
+# ---- which chain bounds the concurrent pass?  Re-time the pass with one chain removed.
+import types
+orig = {n: getattr(HotPath, n) for n in ("_chain_sampler", "_chain_lifts", "_chain_tissue", "_chain_cell")}
+
+
+def time_pass(label):
+    with torch.cuda.stream(st):
+        hp.run(sets[0]); st.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=st):
+            for r in range(10):
+                hp.run(sets[r & 1])
+        g.replay(); st.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for _ in range(5):
+            g.replay()
+        e1.record(st); st.synchronize()
+    print(f"{label:28s} {e0.elapsed_time(e1) / 50 * 1e3:8.2f} us")
+
+
+time_pass("concurrent pass, all chains")
+for name in orig:
+    setattr(HotPath, name, lambda self, inp: None)
+    time_pass("  without " + name)
+    setattr(HotPath, name, orig[name])
+for name in orig:
+    setattr(HotPath, name, lambda self, inp: None)
+time_pass("  decode tails + label only")
