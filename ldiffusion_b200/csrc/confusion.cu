@@ -13,6 +13,8 @@
 //    atomic per non-empty bin into the caller's int64 matrix (which may be the
 //    buffer handed to ncclAllReduce).
 // Larger K (16..128) takes the same kernel with per-pixel integer bin math.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace ldiff {
@@ -128,10 +130,12 @@ static int launch_confusion(const uint8_t* pred, const uint8_t* gt, const uint8_
   int R = 32;
   while (R > 1 && (size_t)nbins * R * 4 > 64 * 1024) R >>= 1;
   const size_t smem = (size_t)nbins * R * 4;
-  // blocks per image: up to 4 resident blocks per SM over the batch, each thread >= 1 vector
+  // blocks per image: 2 blocks of 512 threads per SM over the batch (measured best: fewer global
+  // atomics per bin than 4, same streaming rate), each thread >= 1 vector
   const int64_t nvec = (n_per_image >> 4) > 0 ? (n_per_image >> 4) : 1;
   int64_t bx = (nvec + threads - 1) / threads;
-  const int64_t cap = ((int64_t)sm_count() * 4 + n_images - 1) / n_images;
+  static const int bps = [] { const char* e = getenv("LDIFF_CONF_BPS"); return e ? atoi(e) : 2; }();
+  const int64_t cap = ((int64_t)sm_count() * bps + n_images - 1) / n_images;
   if (bx > cap) bx = cap > 0 ? cap : 1;
   const dim3 grid((unsigned)bx, (unsigned)n_images);
   unsigned long long* Cu = reinterpret_cast<unsigned long long*>(C);

@@ -49,8 +49,11 @@ template <> struct Quant<__nv_bfloat16> {
         "  fma.rn.relu.bf16x2 f, %1, %2, %2;\n"
         "  min.bf16x2 %0, f, %3;\n}"
         : "=r"(t) : "r"(x2), "r"(0x3f003f00u), "r"(0x3f803f80u));
-    q0 = __float_as_uint(__fmaf_rn(__uint_as_float(t << 16), 255.f, 12582912.f));
-    q1 = __float_as_uint(__fmaf_rn(__uint_as_float(t & 0xffff0000u), 255.f, 12582912.f));
+    // both pixels in one packed fp32x2 FMA (FFMA2: IEEE per lane)
+    const float2 y = __ffma2_rn(make_float2(__uint_as_float(t << 16), __uint_as_float(t & 0xffff0000u)),
+                                make_float2(255.f, 255.f), make_float2(12582912.f, 12582912.f));
+    q0 = __float_as_uint(y.x);
+    q1 = __float_as_uint(y.y);
   }
   __device__ static __forceinline__ uint32_t bits(float x) {
     const __nv_bfloat16 h = __float2bfloat16_rn(x);            // x is a bf16 value: exact
@@ -65,6 +68,8 @@ __device__ __forceinline__ void quant16(const float* p, uint32_t (&q)[16]) {
   float v[16];
   Vec8<float>::load(p, reinterpret_cast<float(&)[8]>(v[0]));
   Vec8<float>::load(p + 8, reinterpret_cast<float(&)[8]>(v[8]));
+  // (scalar on purpose: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2,
+  //  which would round t*255 + magic once instead of twice)
 #pragma unroll
   for (int i = 0; i < 16; ++i) q[i] = Quant<float>::bits(v[i]);
 }

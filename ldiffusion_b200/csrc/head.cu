@@ -472,20 +472,37 @@ cell_classify_kernel(const T* __restrict__ feats, const T* __restrict__ weight,
   }
 }
 
-// mask[b,p] = lut[b][inst[b,p]], 16 pixels per thread
+// mask[b,p] = lut[b][inst[b,p]], 16 pixels per thread.  The image's LUT (a few hundred
+// bytes) is copied to shared memory first (SMEM_LUT) so the per-pixel lookup is an LDS;
+// ids are range-checked four at a time (max of the unsigned ids).
+template <bool SMEM_LUT>
 __global__ void __launch_bounds__(256)
 lut_paint_kernel(const int32_t* __restrict__ inst, const uint8_t* __restrict__ lut,
                  uint8_t* __restrict__ mask, int64_t n, int lut_size, int64_t lut_stride,
                  int* __restrict__ status) {
+  extern __shared__ uint8_t s_lut[];
   const int b = blockIdx.y;
   const uint8_t* l = lut + b * lut_stride;
+  if (SMEM_LUT) {
+    for (int i = threadIdx.x; i < lut_size; i += blockDim.x) s_lut[i] = l[i];
+    __syncthreads();
+    l = s_lut;
+  }
+  // (global LUT: the loads below go through L1; the table is a few hundred bytes)
   const int32_t* in = inst + b * n;
   uint8_t* out = mask + b * n;
   int bad = 0;
-  auto look = [&](int id) -> uint32_t {
-    if ((unsigned)id < (unsigned)lut_size) return __ldg(l + id);
+  auto look4 = [&](int4 q) -> uint32_t {
+    const uint32_t a = (uint32_t)q.x, bb = (uint32_t)q.y, c = (uint32_t)q.z, d = (uint32_t)q.w;
+    if (max(max(a, bb), max(c, d)) < (uint32_t)lut_size)          // common case: all four in range
+      return (uint32_t)l[a] | ((uint32_t)l[bb] << 8) | ((uint32_t)l[c] << 16) | ((uint32_t)l[d] << 24);
     bad = 1;
-    return 0u;
+    uint32_t w = 0;
+    if (a < (uint32_t)lut_size) w |= l[a];
+    if (bb < (uint32_t)lut_size) w |= (uint32_t)l[bb] << 8;
+    if (c < (uint32_t)lut_size) w |= (uint32_t)l[c] << 16;
+    if (d < (uint32_t)lut_size) w |= (uint32_t)l[d] << 24;
+    return w;
   };
   const int64_t nvec = n >> 4;
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec;
@@ -496,12 +513,15 @@ lut_paint_kernel(const int32_t* __restrict__ inst, const uint8_t* __restrict__ l
     for (int j = 0; j < 4; ++j) q[j] = __ldcs(p + j);
     uint32_t w[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      w[j] = look(q[j].x) | (look(q[j].y) << 8) | (look(q[j].z) << 16) | (look(q[j].w) << 24);
+    for (int j = 0; j < 4; ++j) w[j] = look4(q[j]);
     __stcs(reinterpret_cast<uint4*>(out) + v, make_uint4(w[0], w[1], w[2], w[3]));
   }
   const int64_t t = (nvec << 4) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < n) out[t] = (uint8_t)look(in[t]);
+  if (t < n) {
+    const uint32_t id = (uint32_t)in[t];
+    if (id < (uint32_t)lut_size) out[t] = l[id];
+    else { out[t] = 0; bad = 1; }
+  }
   if (bad) atomicOr(status, LDIFF_STATUS_INST_RANGE);
 }
 
@@ -621,9 +641,15 @@ extern "C" int ldiff_lut_paint(const int32_t* inst, const uint8_t* lut, uint8_t*
   if (n_per_image == 0 || B == 0) return LDIFF_OK;
   if (!aligned16(inst) || !aligned16(mask) || (B > 1 && (n_per_image % 16))) return LDIFF_EALIGN;
   const int64_t items = (n_per_image >> 4) > (n_per_image & 15) ? (n_per_image >> 4) : (n_per_image & 15);
-  dim3 grid(grid_for(items, 256, 8), B);
-  lut_paint_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(inst, lut, mask, n_per_image, lut_size,
-                                                           lut_stride, status);
+  dim3 grid(grid_for(items, 256, 8), B);                 // one 16-pixel vector per thread at 1024x1024
+  // (measured: the L1-cached global LUT beats a per-block shared-memory copy at 800 entries: 9.4 vs 10.5 us)
+  static const bool smem_lut = getenv("LDIFF_PAINT_SMEM_LUT") != nullptr;
+  if (smem_lut && lut_size <= 32 * 1024)
+    lut_paint_kernel<true><<<grid, 256, (size_t)lut_size, (cudaStream_t)stream>>>(
+        inst, lut, mask, n_per_image, lut_size, lut_stride, status);
+  else
+    lut_paint_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(inst, lut, mask, n_per_image, lut_size,
+                                                                    lut_stride, status);
   return check_launch();
 }
 
