@@ -42,12 +42,13 @@ def test_qsample_injected_uniform(shape):
 
 @pytest.mark.parametrize("n", [1, 3, 8, 1000, 65536 + 5])
 def test_qsample_philox_stream_matches_restatement(n):
-    """The kernel's own counter-based stream is reproducible on the CPU."""
+    """The kernel's own counter-based stream is reproducible on the CPU.  Philox mode uses a
+    short log1p (hardware log2 / 5-term series, <= 6e-6 relative; contract 1e-3)."""
     seed, offset, b = 0x1234ABCD5678, 77, 0.75
     x = torch.zeros(n)
     got, nz = _ops().laplace_qsample(x.cuda(), b, seed=seed, offset=offset, return_noise=True)
     want = olap.laplace_philox(n, b, seed, offset)
-    torch.testing.assert_close(nz.cpu(), want, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(nz.cpu(), want, rtol=2e-5, atol=1e-7)
     assert torch.equal(got, nz)                      # x == 0 -> out == noise
 
 
