@@ -29,19 +29,35 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
+    """Compile every .cu for sm_100a (one nvcc per file, in parallel) and link the shared library."""
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-           "--shared", "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
+    from concurrent.futures import ThreadPoolExecutor
+    obj_dir = os.path.join(HERE, "_build")
+    os.makedirs(obj_dir, exist_ok=True)
+    common = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
     if verbose:
-        cmd += ["-Xptxas", "-v"]
-    cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
+        common += ["-Xptxas", "-v"]
+
+    def compile_one(src):
+        obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
+        res = subprocess.run(common + ["-c", os.path.join(CSRC, src), "-o", obj], capture_output=True, text=True)
+        return src, obj, res
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as ex:
+        results = list(ex.map(compile_one, SOURCES))
+    log = "".join(r.stdout + r.stderr for _, _, r in results)
+    if any(r.returncode for _, _, r in results):
+        sys.stderr.write(log)
         raise RuntimeError("nvcc failed building libldiff_sm100.so")
+    link = subprocess.run([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "--shared",
+                           *[o for _, o, _ in results], "-o", LIB], capture_output=True, text=True)
+    if link.returncode != 0:
+        sys.stderr.write(link.stdout + link.stderr)
+        raise RuntimeError("linking libldiff_sm100.so failed")
     if verbose:
-        sys.stderr.write(res.stdout + res.stderr)
+        sys.stderr.write(log)
     return LIB
 
 
