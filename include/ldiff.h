@@ -91,6 +91,14 @@ int ldiff_plms_step(const void* sample, const void* e0, const void* e1, const vo
 int ldiff_decode_tail_gray(const void* img, uint8_t* rgb_hwc, uint8_t* gray, int B, int H, int W,
                            int64_t gray_batch_stride, int dtype, void* stream);
 
+/* same pass with the segmentor's model input fused in (replaces the PIL ->
+ * transforms.ToTensor -> Normalize hand-off at segmentor.py:107-108,533-534):
+ * model_input fp32 [B,3,H,W] = ((q / 255) - mean[c]) / std[c] on the quantised image q.
+ * host_mean3 / host_std3 are HOST pointers to three floats.  rgb_hwc and gray optional. */
+int ldiff_decode_tail_model_input(const void* img, uint8_t* rgb_hwc, uint8_t* gray, float* model_input,
+                                  const float* host_mean3, const float* host_std3, int B, int H, int W,
+                                  int64_t gray_batch_stride, int dtype, void* stream);
+
 /* ---- a-4  bilinear lift + gray + concat ----------------------------------
  * replaces F.interpolate(mode='bilinear', align_corners=False) (+ weighted gray
  * + torch.cat) at ldiffusion.py:224-226, :240-251 (same primitive at

@@ -26,6 +26,8 @@ SIGNATURES = {
                                 c_float, c_float, c_void_p, c_int64, c_int, c_void_p]),
     "ldiff_decode_tail_gray": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64,
                                        c_int, c_void_p]),
+    "ldiff_decode_tail_model_input": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                              c_int, c_int, c_int64, c_int, c_void_p]),
     "ldiff_bilinear_lift": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int64, c_int64, c_void_p,
                                     c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "ldiff_head_logits": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,

@@ -94,11 +94,25 @@ __device__ __forceinline__ uint32_t pack4(uint32_t a, uint32_t b, uint32_t c, ui
   return __byte_perm(lo, hi, 0x5410);
 }
 
-template <typename T, bool RGB, bool GRAY>
+struct NormArgs {            // optional fused model-input output (N1 of SURVEY 8f)
+  float* out;                // fp32 [B,3,H,W]: ((q/255) - mean) / std, torchvision ToTensor + Normalize
+  float mean[3], stdv[3];
+};
+
+template <typename T, bool RGB, bool GRAY, bool NORM>
 __global__ void __launch_bounds__(256)
 decode_tail_vec16_kernel(const T* __restrict__ img, uint8_t* __restrict__ rgb,
                          uint8_t* __restrict__ gray, int64_t hw, int groups_per_img,
-                         int64_t gray_batch_stride) {
+                         int64_t gray_batch_stride, NormArgs na) {
+  // a channel value has 256 possible inputs: the two IEEE divisions are tabulated once per block
+  __shared__ float s_norm[NORM ? 3 * 256 : 1];
+  if (NORM) {
+    for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) {
+      const int c = i >> 8, q = i & 255;
+      s_norm[i] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)q, 255.f), na.mean[c]), na.stdv[c]);
+    }
+    __syncthreads();
+  }
   // grid = (blocks over one image, B): no division in the loop
   const int64_t b = blockIdx.y;
   const int stride = gridDim.x * blockDim.x;
@@ -132,6 +146,17 @@ decode_tail_vec16_kernel(const T* __restrict__ img, uint8_t* __restrict__ rgb,
       __stcs(o + 1, make_uint4(w[4], w[5], w[6], w[7]));
       __stcs(o + 2, make_uint4(w[8], w[9], w[10], w[11]));
     }
+    if (NORM) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float4* o = reinterpret_cast<float4*>(na.out + (b * 3 + c) * hw + p);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          __stcs(o + j, make_float4(s_norm[c * 256 + (q[c][4 * j] & 255)], s_norm[c * 256 + (q[c][4 * j + 1] & 255)],
+                                    s_norm[c * 256 + (q[c][4 * j + 2] & 255)],
+                                    s_norm[c * 256 + (q[c][4 * j + 3] & 255)]));
+      }
+    }
   }
 }
 
@@ -140,7 +165,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 decode_tail_scalar_kernel(const T* __restrict__ img, uint8_t* __restrict__ rgb,
                           uint8_t* __restrict__ gray, int64_t hw, int64_t total,
-                          int64_t gray_batch_stride) {
+                          int64_t gray_batch_stride, NormArgs na) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
     const int64_t b = i / hw, p = i - b * hw;
@@ -153,16 +178,23 @@ decode_tail_scalar_kernel(const T* __restrict__ img, uint8_t* __restrict__ rgb,
       uint8_t* o = rgb + i * 3;
       o[0] = (uint8_t)r; o[1] = (uint8_t)g; o[2] = (uint8_t)bl;
     }
+    if (na.out) {
+      const uint32_t qv[3] = {r & 255u, g & 255u, bl & 255u};
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        na.out[(b * 3 + c) * hw + p] =
+            __fdiv_rn(__fsub_rn(__fdiv_rn((float)qv[c], 255.f), na.mean[c]), na.stdv[c]);
+    }
   }
 }
 
 template <typename T>
 static int launch_decode_tail(const void* img, uint8_t* rgb, uint8_t* gray, int B, int H, int W,
-                              int64_t gray_batch_stride, cudaStream_t st) {
+                              int64_t gray_batch_stride, NormArgs na, cudaStream_t st) {
   const int64_t hw = (int64_t)H * W;
   const int threads = 256;
   const bool vec_ok = (hw % 16 == 0) && aligned16(img) && aligned16(rgb) && aligned16(gray) &&
-                      (gray_batch_stride % 16 == 0);
+                      aligned16(na.out) && (gray_batch_stride % 16 == 0);
   if (vec_ok) {
     if ((hw >> 4) > 0x7fffffff / 2 || B > 65535) return LDIFF_EUNSUPPORTED;
     const int gpi = (int)(hw >> 4);
@@ -175,16 +207,23 @@ static int launch_decode_tail(const void* img, uint8_t* rgb, uint8_t* gray, int 
     const int bx = (need + iters - 1) / iters;
     const dim3 grid(bx, B);
     const T* p = (const T*)img;
-    if (rgb && gray)
-      decode_tail_vec16_kernel<T, true, true><<<grid, threads, 0, st>>>(p, rgb, gray, hw, gpi, gray_batch_stride);
-    else if (gray)
-      decode_tail_vec16_kernel<T, false, true><<<grid, threads, 0, st>>>(p, rgb, gray, hw, gpi, gray_batch_stride);
-    else
-      decode_tail_vec16_kernel<T, true, false><<<grid, threads, 0, st>>>(p, rgb, gray, hw, gpi, gray_batch_stride);
+#define DT(R, G, N) \
+  decode_tail_vec16_kernel<T, R, G, N><<<grid, threads, 0, st>>>(p, rgb, gray, hw, gpi, gray_batch_stride, na)
+    if (na.out) {
+      if (rgb && gray) DT(true, true, true);
+      else if (gray) DT(false, true, true);
+      else if (rgb) DT(true, false, true);
+      else DT(false, false, true);
+    } else {
+      if (rgb && gray) DT(true, true, false);
+      else if (gray) DT(false, true, false);
+      else DT(true, false, false);
+    }
+#undef DT
   } else {
     const int64_t total = hw * B;
     decode_tail_scalar_kernel<T><<<grid_for(total, threads, 8), threads, 0, st>>>(
-        (const T*)img, rgb, gray, hw, total, gray_batch_stride);
+        (const T*)img, rgb, gray, hw, total, gray_batch_stride, na);
   }
   return check_launch();
 }
@@ -193,14 +232,38 @@ static int launch_decode_tail(const void* img, uint8_t* rgb, uint8_t* gray, int 
 
 using namespace ldiff;
 
+static int decode_tail_entry(const void* img, uint8_t* rgb_hwc, uint8_t* gray, float* model_input,
+                             const float* mean3, const float* std3, int B, int H, int W,
+                             int64_t gray_batch_stride, int dtype, void* stream) {
+  if (!img || (!rgb_hwc && !gray && !model_input) || B < 0 || H < 0 || W < 0) return LDIFF_EINVAL;
+  if (gray && gray_batch_stride < (int64_t)H * W) return LDIFF_EINVAL;
+  if (model_input && (!mean3 || !std3)) return LDIFF_EINVAL;
+  if (B == 0 || H == 0 || W == 0) return LDIFF_OK;
+  NormArgs na;
+  na.out = model_input;
+  for (int c = 0; c < 3; ++c) {
+    na.mean[c] = model_input ? mean3[c] : 0.f;          // host pointers: three floats each
+    na.stdv[c] = model_input ? std3[c] : 1.f;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == LDIFF_F32)
+    return launch_decode_tail<float>(img, rgb_hwc, gray, B, H, W, gray_batch_stride, na, st);
+  if (dtype == LDIFF_BF16)
+    return launch_decode_tail<__nv_bfloat16>(img, rgb_hwc, gray, B, H, W, gray_batch_stride, na, st);
+  return LDIFF_EUNSUPPORTED;
+}
+
 extern "C" int ldiff_decode_tail_gray(const void* img, uint8_t* rgb_hwc, uint8_t* gray, int B, int H,
                                       int W, int64_t gray_batch_stride, int dtype, void* stream) {
-  if (!img || (!rgb_hwc && !gray) || B < 0 || H < 0 || W < 0) return LDIFF_EINVAL;
-  if (gray && gray_batch_stride < (int64_t)H * W) return LDIFF_EINVAL;
-  if (B == 0 || H == 0 || W == 0) return LDIFF_OK;
-  cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == LDIFF_F32) return launch_decode_tail<float>(img, rgb_hwc, gray, B, H, W, gray_batch_stride, st);
-  if (dtype == LDIFF_BF16)
-    return launch_decode_tail<__nv_bfloat16>(img, rgb_hwc, gray, B, H, W, gray_batch_stride, st);
-  return LDIFF_EUNSUPPORTED;
+  return decode_tail_entry(img, rgb_hwc, gray, nullptr, nullptr, nullptr, B, H, W, gray_batch_stride,
+                           dtype, stream);
+}
+
+extern "C" int ldiff_decode_tail_model_input(const void* img, uint8_t* rgb_hwc, uint8_t* gray,
+                                             float* model_input, const float* host_mean3,
+                                             const float* host_std3, int B, int H, int W,
+                                             int64_t gray_batch_stride, int dtype, void* stream) {
+  if (!model_input) return LDIFF_EINVAL;
+  return decode_tail_entry(img, rgb_hwc, gray, model_input, host_mean3, host_std3, B, H, W,
+                           gray_batch_stride, dtype, stream);
 }

@@ -101,6 +101,18 @@ def _decode_tail_gray(img: Tensor, rgb: Optional[Tensor], gray: Optional[Tensor]
                                              _dt(img), _stream(img)))
 
 
+def _decode_tail_model_input(img: Tensor, rgb: Optional[Tensor], gray: Optional[Tensor], model_input: Tensor,
+                             mean: Sequence[float], std: Sequence[float]) -> None:
+    import ctypes
+    _cuda(img, rgb, gray, model_input)
+    B, _, H, W = img.shape
+    gstride = gray.stride(0) if gray is not None else 0
+    m3 = (ctypes.c_float * 3)(*[float(v) for v in mean])
+    s3 = (ctypes.c_float * 3)(*[float(v) for v in std])
+    check(_cabi.lib().ldiff_decode_tail_model_input(_ptr(img), _ptr(rgb), _ptr(gray), _ptr(model_input), m3, s3,
+                                                    B, H, W, gstride, _dt(img), _stream(img)))
+
+
 def _bilinear_lift(src: Tensor, dst: Tensor, dst_channel: int, gray: bool) -> None:
     _cuda(src, dst)
     B, C, h, w = src.shape
@@ -182,6 +194,8 @@ def _labels_to_u8(x: Tensor, out: Tensor) -> None:
 torch.library.custom_op("ldiff::laplace_qsample", mutates_args=("out", "noise_out"))(_laplace_qsample)
 torch.library.custom_op("ldiff::plms_step", mutates_args=("out",))(_plms_step)
 torch.library.custom_op("ldiff::decode_tail_gray", mutates_args=("rgb", "gray"))(_decode_tail_gray)
+torch.library.custom_op("ldiff::decode_tail_model_input",
+                        mutates_args=("rgb", "gray", "model_input"))(_decode_tail_model_input)
 torch.library.custom_op("ldiff::bilinear_lift", mutates_args=("dst",))(_bilinear_lift)
 torch.library.custom_op("ldiff::head_logits", mutates_args=("logits",))(_head_logits)
 torch.library.custom_op("ldiff::lift_argmax", mutates_args=("mask",))(_lift_argmax)
@@ -233,6 +247,29 @@ def plms_step(sample: Tensor, eps: Sequence[Tensor], mode: int, sample_coeff: fl
     out = torch.empty_like(sample) if out is None else out
     _plms_step(sample, eps, mode, float(sample_coeff), float(alpha_diff), float(denom), out)
     return out
+
+
+IMAGENET_MEAN = (0.485, 0.456, 0.406)
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+def decode_tail_model_input(img: Tensor, *, mean=IMAGENET_MEAN, std=IMAGENET_STD, want_rgb: bool = True,
+                            want_gray: bool = False, gray_out: Optional[Tensor] = None):
+    """Decode tail with the segmentor's model input fused in: returns (uint8 RGB | None, uint8 gray |
+    None, fp32 [B,3,H,W] = Normalize(mean, std)(ToTensor(image))) — the hand-off the reference does
+    through PIL + torchvision at segmentor.py:107-108 / :533-534, without leaving the device."""
+    if img.dim() != 4 or img.shape[1] != 3:
+        raise ValueError("img must be [B,3,H,W]")
+    _cuda(img)
+    _dense(img, "img")
+    B, _, H, W = img.shape
+    rgb = torch.empty((B, H, W, 3), dtype=torch.uint8, device=img.device) if want_rgb else None
+    gray = gray_out
+    if gray is None and want_gray:
+        gray = torch.empty((B, H, W), dtype=torch.uint8, device=img.device)
+    mi = torch.empty((B, 3, H, W), dtype=torch.float32, device=img.device)
+    _decode_tail_model_input(img, rgb, gray, mi, list(mean), list(std))
+    return rgb, gray, mi
 
 
 def decode_tail_gray(img: Tensor, *, want_rgb: bool = True, gray_out: Optional[Tensor] = None,

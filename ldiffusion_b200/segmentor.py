@@ -94,19 +94,26 @@ class Segmentor:
 
     # -- the hot loop (segmentor.py:96-107, :436-448, :518-530; utils.py:189-205) ----
     @torch.no_grad()
-    def _sample_and_decode(self, image, pipeline, unet, vae, text_embeddings, num_steps: int = 1):
-        """image [B,3,H,W] -> uint8 RGB [B,H,W,3] on the device (what numpy_to_pil would hold)."""
+    def _sample_and_decode(self, image, pipeline, unet, vae, text_embeddings, num_steps: int = 1,
+                           model_input: bool = False):
+        """image [B,3,H,W] -> uint8 RGB [B,H,W,3] on the device (what numpy_to_pil would hold);
+        with ``model_input`` also the segmentor's normalised input tensor, fused into the same
+        kernel (the reference goes decoded -> .cpu() -> PIL -> ToTensor -> Normalize -> device)."""
         sched = pipeline.scheduler
         latents = vae.encode(image).latent_dist.mean.to(dtype=torch.float32).contiguous()
         sched.set_timesteps(num_steps, device=self.device)
-        rgb = None
-        for t in sched.timesteps:
+        rgb, mi = None, None
+        n = len(sched.timesteps)
+        for i, t in enumerate(sched.timesteps):
             latents = sched.scale_model_input(latents, t)
             output = unet(latents, t, text_embeddings)
             latents = sched.step(output[0].contiguous(), t, latents).prev_sample
             decoded = vae.decode(latents / 0.18215).sample            # decode_latents' first half
-            rgb, _ = ops.decode_tail_gray(decoded.contiguous(), want_gray=False)
-        return rgb
+            if model_input and i == n - 1:
+                rgb, _, mi = ops.decode_tail_model_input(decoded.contiguous())
+            else:
+                rgb, _ = ops.decode_tail_gray(decoded.contiguous(), want_gray=False)
+        return (rgb, mi) if model_input else rgb
 
     def ldiffusion_augment(self, inputs, pipeline, unet, vae):
         """segmentor.py:86-112: [B,3,H,W] -> float [B,3,1024,1024] on the device (the
@@ -147,10 +154,13 @@ class Segmentor:
         if x.dim() != 4:
             raise ValueError(f"Input image tensor has invalid dimensions: {x.dim()} (expected 4).")
         text = self._get_text_embeddings("A pathological slide", 1, pipeline, unet)
-        rgb = self._sample_and_decode(x, pipeline, unet, vae, text)                  # uint8 [1,1024,1024,3]
+        rgb, mi = self._sample_and_decode(x, pipeline, unet, vae, text, model_input=True)   # uint8 [1,1024,1024,3]
         decoded_image = Image.fromarray(rgb[0].cpu().numpy())
-        # model input: Resize/ToTensor/Normalize of the decoded image, HWC numpy in the reference
-        model_input = _to_tensor_1024(decoded_image, self.device, normalize=True)[0].permute(1, 2, 0)
+        # model input: Resize/ToTensor/Normalize of the decoded image (HWC numpy in the reference);
+        # Resize is the identity when the decode already is 1024x1024, so the fused tensor is exact
+        if tuple(mi.shape[-2:]) != (1024, 1024):
+            mi = _to_tensor_1024(decoded_image, self.device, normalize=True)
+        model_input = mi[0].permute(1, 2, 0)
         inst_map, feats, ids = self.model.instances(model_input.cpu().numpy())
         clf = self.model.classifier
         mask = cell_mask(inst_map, feats.contiguous(), clf.weight.detach().contiguous(), clf.bias.detach(), ids,
@@ -173,11 +183,13 @@ class Segmentor:
         if width == height:                                                          # segmentor.py:427
             x = _to_tensor_1024(image, self.device, normalize=True)
             text = self._get_text_embeddings("A pathological slide", 1, pipeline, unet)
-            rgb = self._sample_and_decode(x, pipeline, unet, vae, text)
+            rgb, xin = self._sample_and_decode(x, pipeline, unet, vae, text, model_input=True)
             decoded_image = Image.fromarray(rgb[0].cpu().numpy())
+            if tuple(xin.shape[-2:]) != (1024, 1024):
+                xin = _to_tensor_1024(decoded_image, self.device, normalize=True)
         else:
             decoded_image = image
-        xin = _to_tensor_1024(decoded_image, self.device, normalize=True)
+            xin = _to_tensor_1024(decoded_image, self.device, normalize=True)
         feat = self.model.features(xin).contiguous()
         head = self.model.head
         K = head.weight.shape[0]

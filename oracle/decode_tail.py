@@ -61,3 +61,12 @@ def pixel_vectors_loop(decoded_steps, label):
             v.append(lab[i, j])
             out[(i, j)] = v
     return out
+
+
+def model_input_chain(rgb_u8, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225)):
+    """segmentor.py:501-510 / :533 applied to the decoded PIL image when it already is 1024x1024:
+    torchvision ``ToTensor`` (uint8 HWC -> float CHW / 255) then ``Normalize(mean, std)``.
+    rgb_u8: uint8 [B,H,W,3] -> float32 [B,3,H,W]."""
+    from torchvision import transforms
+    tf = transforms.Compose([transforms.ToTensor(), transforms.Normalize(mean=list(mean), std=list(std))])
+    return torch.stack([tf(Image.fromarray(im)) for im in rgb_u8])

@@ -41,6 +41,21 @@ def test_decode_tail_bit_exact(shape, dtype):
     assert torch.equal(gray2, gray) and torch.equal(rgb2, rgb)
 
 
+@pytest.mark.parametrize("shape", [(2, 3, 64, 48), (1, 3, 17, 13)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_decode_tail_fused_model_input(shape, dtype):
+    """N1: PIL -> ToTensor -> Normalize(ImageNet) hand-off fused into the decode tail, bit-exact."""
+    img = _decoded(shape, 9, dtype)
+    want_rgb = odt.decode_tail_chain(img)
+    want = odt.model_input_chain(want_rgb)
+    rgb, gray, mi = _ops().decode_tail_model_input(img.cuda(), want_gray=True)
+    assert np.array_equal(rgb.cpu().numpy(), want_rgb)
+    assert np.array_equal(gray.cpu().numpy(), odt.gray_spec(want_rgb))
+    assert torch.equal(mi.cpu(), want)
+    _, _, mi2 = _ops().decode_tail_model_input(img.cuda(), want_rgb=False, mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5))
+    assert torch.equal(mi2.cpu(), odt.model_input_chain(want_rgb, (0.5, 0.5, 0.5), (0.5, 0.5, 0.5)))
+
+
 def test_pixel_vectors_match_reference_loop():
     """pixel_latent_vector.py:84-93 incl. the literal per-pixel dict loop (small image)."""
     from ldiffusion_b200 import pixel_vectors
