@@ -201,14 +201,21 @@ static int launch_decode_tail(const void* img, uint8_t* rgb, uint8_t* gray, int 
     // blocks per image: cover it, but no more than ~8 resident blocks per SM over the batch
     // (balanced: every thread runs the same number of iterations, so the grid is one even wave)
     const int need = (gpi + threads - 1) / threads;
-    int cap = (sm_count() * 8) / B;
-    if (cap < 1) cap = 1;
-    const int iters = (need + cap - 1) / cap;
-    const int bx = (need + iters - 1) / iters;
-    const dim3 grid(bx, B);
     const T* p = (const T*)img;
-#define DT(R, G, N) \
-  decode_tail_vec16_kernel<T, R, G, N><<<grid, threads, 0, st>>>(p, rgb, gray, hw, gpi, gray_batch_stride, na)
+    // resident blocks per SM of THIS instantiation (register-limited: 4 for fp32, 6-7 for bf16)
+#define DT(R, G, N)                                                                                   \
+  do {                                                                                                \
+    static int occ = 0;                                                                               \
+    if (occ == 0 && cudaOccupancyMaxActiveBlocksPerMultiprocessor(                                    \
+                        &occ, decode_tail_vec16_kernel<T, R, G, N>, threads, 0) != cudaSuccess)       \
+      occ = 4;                                                                                        \
+    int cap = (sm_count() * (occ > 0 ? occ : 4)) / B;                                                 \
+    if (cap < 1) cap = 1;                                                                             \
+    const int iters = (need + cap - 1) / cap;                                                         \
+    const dim3 grid((need + iters - 1) / iters, B);                                                   \
+    decode_tail_vec16_kernel<T, R, G, N><<<grid, threads, 0, st>>>(p, rgb, gray, hw, gpi,             \
+                                                                   gray_batch_stride, na);           \
+  } while (0)
     if (na.out) {
       if (rgb && gray) DT(true, true, true);
       else if (gray) DT(false, true, true);
