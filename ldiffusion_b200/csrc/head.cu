@@ -144,8 +144,7 @@ __device__ __forceinline__ int tie_acc(const float (&v)[K], float thr, std::inte
 template <int K, int COLS, int MINB>
 __global__ void __launch_bounds__(256, MINB)   // the cold fp64 exp may spill, the hot loop must not
 lift_argmax_kernel(const float* __restrict__ logits, uint8_t* __restrict__ mask, AxisH ay, AxisH ax) {
-  __shared__ int s_i0[kBand], s_i1[kBand];
-  __shared__ float s_l0[kBand], s_l1[kBand];
+  __shared__ float2 s_l[kBand];                          // vertical weights (l0, l1) of the band's rows
   __shared__ uint32_t s_q[8][kQueue];                    // per-warp queue of near-tie pixels (row, column)
   __shared__ int s_qn[8];
   const int warp_in_block = threadIdx.x >> 5;
@@ -166,9 +165,9 @@ lift_argmax_kernel(const float* __restrict__ logits, uint8_t* __restrict__ mask,
   if (threadIdx.x < 8) s_qn[threadIdx.x] = 0;
   if (threadIdx.x < Y1 - Y0) {
     const TapH t = tap(ay, Y0 + threadIdx.x);
-    s_i0[threadIdx.x] = t.i0; s_i1[threadIdx.x] = t.i1;
-    s_l0[threadIdx.x] = t.l0; s_l1[threadIdx.x] = t.l1;
+    s_l[threadIdx.x] = make_float2(t.l0, t.l1);
   }
+  const int i0 = min(iy, ay.in - 1), i1 = min(iy + 1, ay.in - 1);   // the band's source row pair
   const int b = blockIdx.z;
   const int plane = ay.in * ax.in;
   const float* lb = logits + (int64_t)b * K * plane;
@@ -187,93 +186,111 @@ lift_argmax_kernel(const float* __restrict__ logits, uint8_t* __restrict__ mask,
   constexpr int KP = (K + 1) / 2;
   constexpr float kPad = -1e30f;
   float2 T[COLS][KP], U[COLS][KP];
-  uint32_t overflow[COLS];
+  if (active) {                                          // horizontal lift of the two source rows, once
 #pragma unroll
-  for (int c = 0; c < COLS; ++c) overflow[c] = 0;
-  int cy0 = -1, cy1 = -1;
-  for (int r = 0; active && r < Y1 - Y0; ++r) {
-    const int i0 = s_i0[r], i1 = s_i1[r];
-    const float l0 = s_l0[r], l1 = s_l1[r];
-    if (i0 != cy0 || i1 != cy1) {                      // warp-uniform
-      cy0 = i0; cy1 = i1;
+    for (int k = 0; k < 2 * KP; ++k) {
+      float t[COLS], u[COLS];
 #pragma unroll
-      for (int k = 0; k < 2 * KP; ++k) {
-        float t[COLS], u[COLS];
-#pragma unroll
-        for (int c = 0; c < COLS; ++c) { t[c] = kPad; u[c] = kPad; }
-        if (k < K) {
-          const float* r0 = lb + k * plane + i0 * ax.in;
-          const float* r1 = lb + k * plane + i1 * ax.in;
-#pragma unroll
-          for (int c = 0; c < COLS; ++c) {
-            t[c] = lerp2(tx[c].l0, __ldg(r0 + tx[c].i0), tx[c].l1, __ldg(r0 + tx[c].i1));
-            u[c] = lerp2(tx[c].l0, __ldg(r1 + tx[c].i0), tx[c].l1, __ldg(r1 + tx[c].i1));
-          }
-        }
+      for (int c = 0; c < COLS; ++c) { t[c] = kPad; u[c] = kPad; }
+      if (k < K) {
+        const float* r0 = lb + k * plane + i0 * ax.in;
+        const float* r1 = lb + k * plane + i1 * ax.in;
 #pragma unroll
         for (int c = 0; c < COLS; ++c) {
-          if (k & 1) { T[c][k >> 1].y = t[c]; U[c][k >> 1].y = u[c]; }
-          else { T[c][k >> 1].x = t[c]; U[c][k >> 1].x = u[c]; }
+          t[c] = lerp2(tx[c].l0, __ldg(r0 + tx[c].i0), tx[c].l1, __ldg(r0 + tx[c].i1));
+          u[c] = lerp2(tx[c].l0, __ldg(r1 + tx[c].i0), tx[c].l1, __ldg(r1 + tx[c].i1));
         }
       }
+#pragma unroll
+      for (int c = 0; c < COLS; ++c) {
+        if (k & 1) { T[c][k >> 1].y = t[c]; U[c][k >> 1].y = u[c]; }
+        else { T[c][k >> 1].x = t[c]; U[c][k >> 1].x = u[c]; }
+      }
     }
+  }
+  // one output pixel: candidate mask of the classes within kTieGap of the maximum
+  // (bit 2*KP-1-k set <=> class k is a candidate); exactly one bit set = the argmax
+  auto eval = [&](int c, float l0, float l1) -> uint32_t {
     const float2 l0p = make_float2(l0, l0), l1p = make_float2(l1, l1);
-    uint32_t packed = 0;
+    float2 v[KP];
+#pragma unroll
+    for (int j = 0; j < KP; ++j)
+      v[j] = __ffma2_rn(l0p, T[c][j], __fmul2_rn(l1p, U[c][j]));     // == fma(l0, T, fl(l1*U)) per class
+    float mp[KP];                                                     // max as a tree: short chains
+#pragma unroll
+    for (int j = 0; j < KP; ++j) mp[j] = fmaxf(v[j].x, v[j].y);
+#pragma unroll
+    for (int w = 1; w < KP; w *= 2)
+#pragma unroll
+      for (int j = 0; j + w < KP; j += 2 * w) mp[j] = fmaxf(mp[j], mp[j + w]);
+    // sign(v - thr) is set exactly when v < thr; the sign bits are funnel-shifted into
+    // per-group accumulators (independent chains) and concatenated
+    const float nthr = __fsub_rn(kTieGap, mp[0]);
+    const float2 nthr2 = make_float2(nthr, nthr);
+    constexpr int G = (KP + 1) / 2;                      // groups of two pairs (four classes)
+    uint32_t below = 0;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      uint32_t grp = 0;
+#pragma unroll
+      for (int j = 2 * g; j < 2 * g + 2 && j < KP; ++j) {
+        const float2 d = __fadd2_rn(v[j], nthr2);
+        grp = __funnelshift_l(__float_as_uint(d.x), grp, 1);
+        grp = __funnelshift_l(__float_as_uint(d.y), grp, 1);
+      }
+      below = (below << ((2 * g + 2 <= KP) ? 4 : 2)) | grp;
+    }
+    return ~below & ((1u << (2 * KP)) - 1u);
+  };
+  auto enqueue = [&](int r, int c) -> bool {             // false: the warp's queue is full
+    const int slot = atomicAdd(&s_qn[warp_in_block], 1);
+    if (slot >= kQueue) return false;
+    s_q[warp_in_block][slot] = ((uint32_t)r << 16) | (uint32_t)(threadIdx.x * COLS + c);
+    return true;
+  };
+  auto store = [&](uint8_t* p, uint32_t packed) {
+    if (COLS == 1) p[0] = (uint8_t)packed;
+    else if (COLS == 2) *reinterpret_cast<uint16_t*>(p) = (uint16_t)packed;
+    else *reinterpret_cast<uint32_t*>(p) = packed;
+  };
+
+  // two rows per iteration: their chains are independent, which is what hides the ALU
+  // latency at this occupancy; the rare near-tie bookkeeping is one branch per pair of rows
+  const int nrow = active ? Y1 - Y0 : 0;
+  bool ovf = false;
+  uint8_t* op = out;
+  int r = 0;
+  for (; r + 1 < nrow; r += 2, op += 2 * (int64_t)ax.out) {
+    const float2 la = s_l[r], lbw = s_l[r + 1];
+    uint32_t ca[COLS], cb[COLS], pa = 0, pb = 0, multi = 0;
 #pragma unroll
     for (int c = 0; c < COLS; ++c) {
-      float2 v[KP];
-#pragma unroll
-      for (int j = 0; j < KP; ++j)
-        v[j] = __ffma2_rn(l0p, T[c][j], __fmul2_rn(l1p, U[c][j]));   // == fma(l0, T, fl(l1*U)) per class
-      // running max as a tree (short dependency chains: the kernel runs at low occupancy)
-      float mp[KP];
-#pragma unroll
-      for (int j = 0; j < KP; ++j) mp[j] = fmaxf(v[j].x, v[j].y);
-      float m = mp[0];
-      if (KP == 2) m = fmaxf(mp[0], mp[1]);
-      if (KP == 3) m = fmaxf(fmaxf(mp[0], mp[1]), mp[2]);
-      if (KP == 4) m = fmaxf(fmaxf(mp[0], mp[1]), fmaxf(mp[2], mp[3]));
-      if (KP == 5) m = fmaxf(fmaxf(fmaxf(mp[0], mp[1]), mp[2]), fmaxf(mp[3], mp[4]));
-      if (KP == 6) m = fmaxf(fmaxf(fmaxf(mp[0], mp[1]), mp[2]), fmaxf(fmaxf(mp[3], mp[4]), mp[5]));
-      if (KP == 7) m = fmaxf(fmaxf(fmaxf(fmaxf(mp[0], mp[1]), mp[2]), fmaxf(fmaxf(mp[3], mp[4]), mp[5])), mp[6]);
-      if (KP == 8)
-        m = fmaxf(fmaxf(fmaxf(mp[0], mp[1]), fmaxf(mp[2], mp[3])), fmaxf(fmaxf(mp[4], mp[5]), fmaxf(mp[6], mp[7])));
-      // sign(v - thr) is set exactly when v < thr.  The sign bits are funnel-shifted into
-      // per-group accumulators (independent chains), then concatenated: bit (2*KP-1-k) == 0
-      // marks class k as being within kTieGap of the maximum
-      const float nthr = __fsub_rn(kTieGap, m);
-      const float2 nthr2 = make_float2(nthr, nthr);
-      constexpr int G = (KP + 1) / 2;                    // groups of two pairs (four classes)
-      uint32_t grp[G];
-#pragma unroll
-      for (int g = 0; g < G; ++g) {
-        grp[g] = 0;
-#pragma unroll
-        for (int j = 2 * g; j < 2 * g + 2 && j < KP; ++j) {
-          const float2 d = __fadd2_rn(v[j], nthr2);
-          grp[g] = __funnelshift_l(__float_as_uint(d.x), grp[g], 1);
-          grp[g] = __funnelshift_l(__float_as_uint(d.y), grp[g], 1);
-        }
-      }
-      uint32_t below = 0;
-#pragma unroll
-      for (int g = 0; g < G; ++g) {
-        const int nb = (2 * g + 2 <= KP) ? 4 : 2;        // classes in this group
-        below = (below << nb) | grp[g];
-      }
-      const uint32_t cand = ~below & ((1u << (2 * KP)) - 1u);
-      const int idx = __clz(cand) - (32 - 2 * KP);       // class of the highest candidate bit
-      if (cand & (cand - 1)) {                           // rare: more than one candidate -> queue for the epilogue
-        const int slot = atomicAdd(&s_qn[warp_in_block], 1);
-        if (slot < kQueue) s_q[warp_in_block][slot] = ((uint32_t)r << 16) | (uint32_t)(threadIdx.x * COLS + c);
-        else overflow[c] |= 1u << r;
-      }
-      packed |= (uint32_t)idx << (8 * c);
+      ca[c] = eval(c, la.x, la.y);
+      cb[c] = eval(c, lbw.x, lbw.y);
+      pa |= (uint32_t)(__clz(ca[c]) - (32 - 2 * KP)) << (8 * c);
+      pb |= (uint32_t)(__clz(cb[c]) - (32 - 2 * KP)) << (8 * c);
+      multi |= (ca[c] & (ca[c] - 1)) | (cb[c] & (cb[c] - 1));
     }
-    if (COLS == 1) out[0] = (uint8_t)packed;
-    else if (COLS == 2) *reinterpret_cast<uint16_t*>(out) = (uint16_t)packed;
-    else *reinterpret_cast<uint32_t*>(out) = packed;
-    out += ax.out;
+    store(op, pa);
+    store(op + ax.out, pb);
+    if (multi) {                                         // rare: queue the near-tie pixels for the epilogue
+#pragma unroll
+      for (int c = 0; c < COLS; ++c) {
+        if ((ca[c] & (ca[c] - 1)) && !enqueue(r, c)) ovf = true;
+        if ((cb[c] & (cb[c] - 1)) && !enqueue(r + 1, c)) ovf = true;
+      }
+    }
+  }
+  if (r < nrow) {                                        // odd band height: last row
+    const float2 la = s_l[r];
+    uint32_t pa = 0;
+#pragma unroll
+    for (int c = 0; c < COLS; ++c) {
+      const uint32_t ca = eval(c, la.x, la.y);
+      pa |= (uint32_t)(__clz(ca) - (32 - 2 * KP)) << (8 * c);
+      if ((ca & (ca - 1)) && !enqueue(r, c)) ovf = true;
+    }
+    store(op, pa);
   }
   // ---- cold epilogue: nothing of the hot loop is live any more.  The warp's queued pixels are
   // spread over its lanes (a vertical run of near-ties in ONE column would otherwise serialise
@@ -285,8 +302,7 @@ lift_argmax_kernel(const float* __restrict__ logits, uint8_t* __restrict__ mask,
     const uint32_t ent = s_q[warp_in_block][e];
     const int r = (int)(ent >> 16), x = xblock + (int)(ent & 0xffffu);
     const TapH t = tap(ax, x);
-    const int i0 = s_i0[r], i1 = s_i1[r];
-    const float l0 = s_l0[r], l1 = s_l1[r];
+    const float l0 = s_l[r].x, l1 = s_l[r].y;
     Vals<K> vals;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
@@ -297,15 +313,13 @@ lift_argmax_kernel(const float* __restrict__ logits, uint8_t* __restrict__ mask,
     }
     mask[((int64_t)b * ay.out + Y0 + r) * ax.out + x] = (uint8_t)exact_from_values<K>(vals);
   }
+  if (ovf) {                                             // queue overflowed (e.g. constant logits): this thread
+    for (int rr = 0; rr < nrow; ++rr)                    // re-resolves its whole column(s) with the exact rule
 #pragma unroll
-  for (int c = 0; c < COLS; ++c) {                       // queue overflow (> kQueue events in a warp)
-    uint32_t bits = overflow[c];
-    while (bits) {
-      const int r = __ffs(bits) - 1;
-      bits &= bits - 1;
-      mask[((int64_t)b * ay.out + Y0 + r) * ax.out + x0 + c] = (uint8_t)exact_pixel(
-          lb, K, plane, ax.in, s_i0[r], s_i1[r], s_l0[r], s_l1[r], tx[c].i0, tx[c].i1, tx[c].l0, tx[c].l1);
-    }
+      for (int c = 0; c < COLS; ++c)
+        if (x0 + c < ax.out)
+          mask[((int64_t)b * ay.out + Y0 + rr) * ax.out + x0 + c] = (uint8_t)exact_pixel(
+              lb, K, plane, ax.in, i0, i1, s_l[rr].x, s_l[rr].y, tx[c].i0, tx[c].i1, tx[c].l0, tx[c].l1);
   }
 }
 
@@ -560,9 +574,9 @@ extern "C" int ldiff_lift_argmax(const float* logits, uint8_t* mask, int B, int 
   AxisH ay{(float)h / (float)H, h, H}, ax{(float)w / (float)W, w, W};
   if (K <= 15 && H >= 4 * h && (H + h - 1) / h + 2 <= kBand && h <= 65535) {
     // two columns per thread while T/U (4K registers) fit the 80-register budget, else one
-    // variant: 0 = 2 columns/thread, 2 CTAs/SM; 1 = 1 column, 3 CTAs/SM; 2 = 1 column, 4 CTAs/SM
+    // variant: 0 = 2 columns/thread, 2 CTAs/SM; 1 = 1 column, 3 CTAs/SM; 2 = 1 column, 4 CTAs/SM; 3 = 1 column, 2 CTAs/SM
     static const int knob = [] { const char* e = getenv("LDIFF_ARGMAX_VARIANT"); return e ? atoi(e) : -1; }();
-    int variant = knob >= 0 ? knob : 1;                    // measured: 1 is fastest at 32x lift, K=11
+    int variant = knob >= 0 ? knob : 0;                    // measured at 32x lift, K=11: 34.8 / 36.0 / 35.9 us for 0 / 1 / 3
     if (K > 12 || (W % 2) != 0) variant = variant == 0 ? 1 : variant;
     const int cols = variant == 0 ? 2 : 1;
     dim3 grid((W / cols + 255) / 256, h, B);
@@ -570,6 +584,7 @@ extern "C" int ldiff_lift_argmax(const float* logits, uint8_t* mask, int B, int 
 #define LA2(KK) case KK:                                                                               \
       if (variant == 0) lift_argmax_kernel<KK, 2, 2><<<grid, 256, 0, st>>>(logits, mask, ay, ax);       \
       else if (variant == 1) lift_argmax_kernel<KK, 1, 3><<<grid, 256, 0, st>>>(logits, mask, ay, ax);  \
+      else if (variant == 3) lift_argmax_kernel<KK, 1, 2><<<grid, 256, 0, st>>>(logits, mask, ay, ax);  \
       else lift_argmax_kernel<KK, 1, 4><<<grid, 256, 0, st>>>(logits, mask, ay, ax);                    \
       break;
 #define LA1(KK) case KK: lift_argmax_kernel<KK, 1, 3><<<grid, 256, 0, st>>>(logits, mask, ay, ax); break;
