@@ -164,6 +164,42 @@ def summarize_images(per_image_C):
     }
 
 
+# ---------------------------------------------------------------------------
+# widening N4: nnU-Net's online validation counts and their collective
+# ---------------------------------------------------------------------------
+
+def tp_fp_fn_from_confusion(C: np.ndarray):
+    """nnU-Net ``get_tp_fp_fn_tn`` on hard one-hot predictions, summed over batch and space
+    (``nnUNetTrainer.py:954-986``; ``loss/dice.py:122-180``), from the confusion matrix.
+    gt values outside [0,K) (the ignore label) are masked out, as nnU-Net's ``mask`` does.
+    Returns float32 (tp, fp, fn) of length K-1 (background dropped, ``:982-984``)."""
+    K = C.shape[1]
+    inside = C[:K]
+    tp = np.diag(inside).astype(np.float32)
+    fp = (inside.sum(0) - np.diag(inside)).astype(np.float32)
+    fn = (inside.sum(1) - np.diag(inside)).astype(np.float32)
+    return tp[1:], fp[1:], fn[1:]
+
+
+def online_tp_fp_fn(output: torch.Tensor, target: torch.Tensor, allreduce: bool = False):
+    """Drop-in for the tail of ``nnUNetTrainer.validation_step`` (``:954-986``) plus, with
+    ``allreduce``, the three ``all_gather_object`` calls of ``on_validation_epoch_end``
+    (``:1004-1012``) as ONE int64 all-reduce.  output: logits [B,K,...]; target: labels
+    [B,1,...] or [B,...].  Returns float32 numpy (tp_hard, fp_hard, fn_hard)."""
+    K = output.shape[1]
+    C = confusion_matrix(output, target.reshape(output.shape[0], *output.shape[2:]), K)
+    if allreduce:
+        from .dist import allreduce_confusion
+        allreduce_confusion(C)
+    return tp_fp_fn_from_confusion(_to_host(C))
+
+
+def global_dice_from_counts(tp, fp, fn):
+    """``nnUNetTrainer.py:1021-1022``: per-class pseudo Dice and its nanmean."""
+    per_class = [i for i in [2 * i / (2 * i + j + k) for i, j, k in zip(tp, fp, fn)]]
+    return per_class, np.nanmean(per_class)
+
+
 def per_image_confusion(preds: torch.Tensor, gts: torch.Tensor, num_classes: int) -> torch.Tensor:
     """uint8 [N,H,W] x2 -> int64 [N,(K+1),K] in one launch, no syncs."""
     return ops.confusion_hist_batched(preds, gts, int(num_classes))

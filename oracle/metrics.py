@@ -213,3 +213,29 @@ def evaluate_images_chain(preds, gts, num_classes):
         "per_class_iou": np.mean(pc_iou, axis=0),
         "per_class_pa": np.mean(pc_pa, axis=0),
     }
+
+
+# --------------------------------------------------------------------------
+# widening N4: nnU-Net online validation counts (test infrastructure only)
+# --------------------------------------------------------------------------
+
+def nnunet_tp_fp_fn_chain(output, target, ignore_label=None):
+    """nnUNetTrainer.py:954-986 restated: argmax -> one-hot prediction -> masked products with
+    the one-hot target -> sums over batch and space; background dropped.  Pinned against the
+    vendored ``get_tp_fp_fn_tn`` by tests/golden/nnunet_counts.npz."""
+    K = output.shape[1]
+    seg = output.argmax(1)[:, None]
+    pred = torch.zeros(output.shape, dtype=torch.float32)
+    pred.scatter_(1, seg, 1)
+    tgt = target.clone()
+    mask = None
+    if ignore_label is not None:
+        mask = (tgt != ignore_label).float()
+        tgt[tgt == ignore_label] = 0
+    y = torch.zeros(output.shape, dtype=torch.float32)
+    y.scatter_(1, tgt.long(), 1)
+    tp, fp, fn = pred * y, pred * (1 - y), (1 - pred) * y
+    if mask is not None:
+        tp, fp, fn = tp * mask, fp * mask, fn * mask
+    axes = [0] + list(range(2, output.ndim))
+    return tuple(t.sum(dim=axes).numpy()[1:] for t in (tp, fp, fn))

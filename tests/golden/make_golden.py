@@ -104,8 +104,38 @@ def chain_golden():
     print("chain ops saved")
 
 
+def nnunet_golden():
+    """N4: the reference's vendored nnU-Net online validation counts (loss/dice.py:122-180 as
+    called at nnUNetTrainer.py:954-986), with and without an ignore label."""
+    sys.path.insert(0, os.path.join(_refshim.REF_ROOT, "model"))
+    from nnunetv2.training.loss.dice import get_tp_fp_fn_tn
+    g = torch.Generator().manual_seed(5)
+    K = 5
+    output = torch.randn(3, K, 40, 48, generator=g)
+    target = torch.randint(0, K + 1, (3, 1, 40, 48), generator=g)          # value K plays the ignore label
+    out = {}
+    for name, ignore in (("plain", None), ("ignore", K)):
+        tgt = target.clone()
+        if ignore is None:
+            tgt[tgt == K] = 0
+        seg = output.argmax(1)[:, None]
+        onehot = torch.zeros(output.shape, dtype=torch.float32)
+        onehot.scatter_(1, seg, 1)
+        mask = None
+        if ignore is not None:
+            mask = (tgt != ignore).float()
+            tgt[tgt == ignore] = 0
+        axes = [0] + list(range(2, output.ndim))
+        tp, fp, fn, _ = get_tp_fp_fn_tn(onehot, tgt, axes=axes, mask=mask)
+        out[name] = np.stack([tp.numpy()[1:], fp.numpy()[1:], fn.numpy()[1:]])
+    np.savez_compressed(os.path.join(HERE, "nnunet_counts.npz"), output=output.numpy(), target=target.numpy(),
+                        plain=out["plain"], ignore=out["ignore"], K=K)
+    print("nnunet counts saved")
+
+
 if __name__ == "__main__":
     if not _refshim.available():
         raise SystemExit("reference checkout not found; golden metric vectors need it")
     metrics_golden()
     chain_golden()
+    nnunet_golden()

@@ -242,3 +242,19 @@ def test_argmax_channels_first_max():
     assert torch.equal(_ops().argmax_channels(x.cuda()).cpu().long(), torch.argmax(x, 1))
     xb = torch.randn(1, 11, 64, 64, generator=g).bfloat16()
     assert torch.equal(_ops().argmax_channels(xb.cuda()).cpu().long(), torch.argmax(xb.float(), 1))
+
+
+def test_nnunet_online_counts_golden():
+    """Widening N4: nnUNetTrainer.validation_step's tp/fp/fn (vendored get_tp_fp_fn_tn, golden
+    vectors) from one argmax + one histogram pass."""
+    import os
+    from ldiffusion_b200.metrics import online_tp_fp_fn
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "nnunet_counts.npz"))
+    K = int(z["K"])
+    output, target = torch.from_numpy(z["output"]).cuda(), torch.from_numpy(z["target"])
+    plain = target.clone(); plain[plain == K] = 0
+    got = online_tp_fp_fn(output, plain.cuda())
+    assert np.array_equal(np.stack(got), z["plain"])
+    ign = target.clone(); ign[ign == K] = 255            # ignore label -> outside [0,K)
+    got = online_tp_fp_fn(output, ign.cuda())
+    assert np.array_equal(np.stack(got), z["ignore"])
