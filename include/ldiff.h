@@ -111,6 +111,14 @@ int ldiff_bilinear_lift(const void* src, int src_dtype, int C, int h, int w,
                         void* dst, int dst_dtype, int Ctot, int dst_channel, int H, int W,
                         int B, int gray, void* stream);
 
+/* n_src (<= 8) same-shaped sources in ONE launch; source i lands at channel
+ * dst_channel + i * (gray ? 1 : C): the per-step lift + gray + torch.cat loop of
+ * ldiffusion.py:240-247 as a single gather.  host_srcs: HOST array of device pointers. */
+int ldiff_bilinear_lift_multi(const void* const* host_srcs, int n_src, int src_dtype, int C, int h, int w,
+                              int64_t src_batch_stride, int64_t src_channel_stride, void* dst,
+                              int dst_dtype, int Ctot, int dst_channel, int H, int W, int B, int gray,
+                              void* stream);
+
 /* ---- a-5  classifier head + argmax ---------------------------------------
  * tissue form, replaces conductor.py:127 (1x1 conv 256->K), :135 (bilinear lift
  * to the input size) and segmentor.py:536 (argmax(softmax)) without ever

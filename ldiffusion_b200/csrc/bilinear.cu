@@ -52,10 +52,15 @@ __device__ __forceinline__ float gray3(float r, float g, float b) {
 }
 
 // ----------------------------------------------------------------------------
+constexpr int kMaxSrc = 8;
+struct SrcList { const void* p[kMaxSrc]; };   // same-shaped sources of one launch (blockIdx.y picks one)
+
 template <typename TS, typename TD>
 __global__ void __launch_bounds__(256)
-lift_gather_kernel(const TS* __restrict__ src, int C, int64_t sbs, int64_t scs, TD* __restrict__ dst,
-                   int Ctot, int dch, Axis ay, Axis ax, int B, int gray) {
+lift_gather_kernel(SrcList srcs, int C, int64_t sbs, int64_t scs, TD* __restrict__ dst,
+                   int Ctot, int dch0, Axis ay, Axis ax, int B, int gray) {
+  const TS* __restrict__ src = static_cast<const TS*>(srcs.p[blockIdx.y]);
+  const int dch = dch0 + (int)blockIdx.y * (gray ? 1 : C);
   const int64_t HW = (int64_t)ay.out * ax.out;
   const int64_t total = HW * B;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -309,15 +314,59 @@ static int launch_lift(const void* src, int C, int h, int w, int64_t sbs, int64_
     }
   } else {
     const int64_t total = (int64_t)H * W * B;
+    SrcList one{};
+    one.p[0] = src;
     lift_gather_kernel<TS, TD><<<grid_for(total, threads, 8), threads, 0, st>>>(
-        (const TS*)src, C, sbs, scs, (TD*)dst, Ctot, dch, ay, ax, B, gray);
+        one, C, sbs, scs, (TD*)dst, Ctot, dch, ay, ax, B, gray);
   }
+  return check_launch();
+}
+
+template <typename TS, typename TD>
+static int launch_lift_multi(const void* const* srcs, int n_src, int C, int h, int w, int64_t sbs, int64_t scs,
+                             void* dst, int Ctot, int dch, int H, int W, int B, int gray, cudaStream_t st) {
+  Axis ay{(float)h / (float)H, h, H}, ax{(float)w / (float)W, w, W};
+  SrcList list{};
+  for (int i = 0; i < n_src; ++i) list.p[i] = srcs[i];
+  const int64_t total = (int64_t)H * W * B;
+  int bx = grid_for(total, 256, 8);
+  const int cap = (sm_count() * 8 + n_src - 1) / n_src;
+  if (bx > cap) bx = cap;
+  lift_gather_kernel<TS, TD><<<dim3(bx, n_src), 256, 0, st>>>(list, C, sbs, scs, (TD*)dst, Ctot, dch, ay, ax, B,
+                                                            gray);
   return check_launch();
 }
 
 }  // namespace ldiff
 
 using namespace ldiff;
+
+extern "C" int ldiff_bilinear_lift_multi(const void* const* host_srcs, int n_src, int src_dtype, int C, int h,
+                                         int w, int64_t src_batch_stride, int64_t src_channel_stride, void* dst,
+                                         int dst_dtype, int Ctot, int dst_channel, int H, int W, int B, int gray,
+                                         void* stream) {
+  if (!host_srcs || n_src < 1 || n_src > kMaxSrc || !dst || C < 1 || h < 1 || w < 1 || H < 1 || W < 1 || B < 0 ||
+      dst_channel < 0)
+    return LDIFF_EINVAL;
+  for (int i = 0; i < n_src; ++i)
+    if (!host_srcs[i]) return LDIFF_EINVAL;
+  if (gray && C != 3) return LDIFF_EINVAL;
+  if (dst_channel + n_src * (gray ? 1 : C) > Ctot) return LDIFF_EINVAL;
+  if (B == 0) return LDIFF_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+#define LIFTM(TS, TD)                                                                                  \
+  return launch_lift_multi<TS, TD>(host_srcs, n_src, C, h, w, src_batch_stride, src_channel_stride, dst, \
+                                   Ctot, dst_channel, H, W, B, gray, st)
+  typedef __nv_bfloat16 bf16;
+  if (src_dtype == LDIFF_F32 && dst_dtype == LDIFF_F32) LIFTM(float, float);
+  if (src_dtype == LDIFF_BF16 && dst_dtype == LDIFF_BF16) LIFTM(bf16, bf16);
+  if (src_dtype == LDIFF_BF16 && dst_dtype == LDIFF_F32) LIFTM(bf16, float);
+  if (src_dtype == LDIFF_F32 && dst_dtype == LDIFF_BF16) LIFTM(float, bf16);
+  if (src_dtype == LDIFF_U8 && dst_dtype == LDIFF_U8) LIFTM(uint8_t, uint8_t);
+  if (src_dtype == LDIFF_U8 && dst_dtype == LDIFF_F32) LIFTM(uint8_t, float);
+#undef LIFTM
+  return LDIFF_EUNSUPPORTED;
+}
 
 extern "C" int ldiff_bilinear_lift(const void* src, int src_dtype, int C, int h, int w,
                                    int64_t src_batch_stride, int64_t src_channel_stride, void* dst,

@@ -74,8 +74,13 @@ def feature_concat(decoded_steps: Sequence[torch.Tensor], size=(64, 64), out_dty
     d0 = decoded_steps[0]
     out = torch.empty((d0.shape[0], len(decoded_steps), size[0], size[1]),
                       dtype=out_dtype or d0.dtype, device=d0.device)
-    for i, d in enumerate(decoded_steps):
-        ops.bilinear_lift(d, size, out=out, out_channel=i, gray=True)
+    same = all(d.shape == d0.shape and d.dtype == d0.dtype and d.stride() == d0.stride() for d in decoded_steps)
+    if same:
+        for i in range(0, len(decoded_steps), 8):                 # one gather launch per 8 steps
+            ops.bilinear_lift_multi(decoded_steps[i:i + 8], size, out=out, out_channel=i, gray=True)
+    else:
+        for i, d in enumerate(decoded_steps):
+            ops.bilinear_lift(d, size, out=out, out_channel=i, gray=True)
     return out
 
 

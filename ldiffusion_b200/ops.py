@@ -122,6 +122,18 @@ def _bilinear_lift(src: Tensor, dst: Tensor, dst_channel: int, gray: bool) -> No
                                           1 if gray else 0, _stream(src)))
 
 
+def _bilinear_lift_multi(srcs: Sequence[Tensor], dst: Tensor, dst_channel: int, gray: bool) -> None:
+    import ctypes
+    _cuda(dst, *srcs)
+    s0 = srcs[0]
+    B, C, h, w = s0.shape
+    _, Ctot, H, W = dst.shape
+    ptrs = (ctypes.c_void_p * len(srcs))(*[t.data_ptr() for t in srcs])
+    check(_cabi.lib().ldiff_bilinear_lift_multi(ptrs, len(srcs), _dt(s0), C, h, w, s0.stride(0), s0.stride(1),
+                                                _ptr(dst), _dt(dst), Ctot, dst_channel, H, W, B,
+                                                1 if gray else 0, _stream(s0)))
+
+
 def _head_logits(feat: Tensor, weight: Tensor, bias: Optional[Tensor], logits: Tensor) -> None:
     _cuda(feat, weight, bias, logits)
     B, Cin = feat.shape[:2]
@@ -197,6 +209,7 @@ torch.library.custom_op("ldiff::decode_tail_gray", mutates_args=("rgb", "gray"))
 torch.library.custom_op("ldiff::decode_tail_model_input",
                         mutates_args=("rgb", "gray", "model_input"))(_decode_tail_model_input)
 torch.library.custom_op("ldiff::bilinear_lift", mutates_args=("dst",))(_bilinear_lift)
+torch.library.custom_op("ldiff::bilinear_lift_multi", mutates_args=("dst",))(_bilinear_lift_multi)
 torch.library.custom_op("ldiff::head_logits", mutates_args=("logits",))(_head_logits)
 torch.library.custom_op("ldiff::lift_argmax", mutates_args=("mask",))(_lift_argmax)
 torch.library.custom_op("ldiff::cell_classify", mutates_args=("lut", "logits_out", "status"))(_cell_classify)
@@ -314,6 +327,28 @@ def bilinear_lift(src: Tensor, size, *, out: Optional[Tensor] = None, out_channe
     if out.shape[0] != B or out.shape[2:] != (H, W):
         raise ValueError("out must be [B,Ctot,H,W]")
     _bilinear_lift(src, out, out_channel, gray)
+    return out
+
+
+def bilinear_lift_multi(srcs: Sequence[Tensor], size, *, out: Optional[Tensor] = None, out_channel: int = 0,
+                        gray: bool = False, out_dtype=None) -> Tensor:
+    """lift (+ gray) of up to 8 same-shaped sources in one launch; source i is written at channel
+    ``out_channel + i * (1 if gray else C)`` of ``out`` — lift + gray + torch.cat of ldiffusion.py:240-247."""
+    s0 = srcs[0]
+    for t in srcs:
+        if t.shape != s0.shape or t.dtype != s0.dtype or t.stride() != s0.stride():
+            raise ValueError("sources must share shape, dtype and strides")
+        if t.stride(3) != 1 or t.stride(2) != t.shape[3]:
+            raise ValueError("source planes must be dense")
+    if len(srcs) > 8:
+        raise ValueError("at most 8 sources per launch")
+    B, C = s0.shape[:2]
+    H, W = size
+    per = 1 if gray else C
+    if out is None:
+        out = torch.empty((B, per * len(srcs), H, W), dtype=out_dtype or s0.dtype, device=s0.device)
+    _dense(out, "out")
+    _bilinear_lift_multi(list(srcs), out, out_channel, gray)
     return out
 
 

@@ -157,3 +157,12 @@ def test_rgb_up_full_size():
     x = torch.randn(8, 3, 64, 64, generator=torch.Generator().manual_seed(13))
     got = rgb_up(x.cuda()).cpu()
     assert torch.equal(got, obil.lift_chain(x, (1024, 1024)))
+
+
+def test_lift_multi_source_equals_single_launches():
+    steps = [torch.randn(2, 3, 256, 256, generator=torch.Generator().manual_seed(70 + i)).cuda() for i in range(5)]
+    multi = _ops().bilinear_lift_multi(steps, (64, 64), gray=True)
+    single = torch.cat([_ops().bilinear_lift(s, (64, 64), gray=True) for s in steps], dim=1)
+    assert torch.equal(multi, single)
+    multi3 = _ops().bilinear_lift_multi(steps[:2], (32, 48))
+    assert torch.equal(multi3, torch.cat([_ops().bilinear_lift(s, (32, 48)) for s in steps[:2]], dim=1))
