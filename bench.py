@@ -176,6 +176,9 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     _cabi.lib()
+    from ldiffusion_b200.dist import bind_to_gpu_numa
+    numa = bind_to_gpu_numa(local) if world > 1 else "single process: not bound"
+    torch.set_num_threads(max(1, min(8, len(os.sched_getaffinity(0)))))
 
     def barrier():
         if world > 1:
@@ -339,7 +342,7 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config(world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
-            "gpu_launches": launches_per_pass * args.steps,
+            "gpu_launches": launches_per_pass * args.steps, "host_binding": numa,
             "roofline": {"bound": "hbm", "kernel": "decode_tail_vec16_kernel<bf16> (gray)", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650",
