@@ -17,6 +17,8 @@
 //    1-D bulk TMA copies (cp.async.bulk + mbarrier), the horizontal pass is done
 //    once per source row into REGISTERS, and every output row is then one mul +
 //    one fma per pixel with 128-bit stores: HBM-write-bound.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace ldiff {
@@ -172,7 +174,7 @@ lift_separable_kernel(const TS* __restrict__ src, int64_t sbs, int64_t scs, TD* 
                       int Ctot, int dch, Axis ay, Axis ax, int band, int max_rows) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar;
-  __shared__ int4 s_tap[32];                           // {r0, r1, bits(l0), bits(l1)} per band row
+  __shared__ int4 s_tap[64];                           // {r0, r1, bits(l0), bits(l1)} per band row
   const int w = ax.in, W = ax.out, H = ay.out;
   TS* raw = reinterpret_cast<TS*>(smem);
 
@@ -289,7 +291,10 @@ static int launch_lift(const void* src, int C, int h, int w, int64_t sbs, int64_
   Axis ay{(float)h / (float)H, h, H}, ax{(float)w / (float)W, w, W};
   const int threads = 256;
   constexpr int V = OutVec<TD>::N;
-  const int band = 32;
+  static const int band_knob = [] { const char* e = getenv("LDIFF_LIFT_BAND"); return e ? atoi(e) : 0; }();
+  // measured at 64 -> 1024: 32-row bands are best for 4-byte outputs (16.6 vs 18.4 us), 64-row bands
+  // for 2-byte outputs (10.9 vs 11.3 us: half the bytes per band, same start-up cost)
+  const int band = (band_knob == 32 || band_knob == 64) ? band_knob : (sizeof(TD) <= 2 ? 64 : 32);
   // rows of source a band can touch: ceil(band * scale) + 2
   const int max_rows = (int)((double)band * h / H) + 3;
   const int NCg = gray ? 3 : 1;

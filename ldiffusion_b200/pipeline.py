@@ -22,7 +22,7 @@ Stages per batch (reference lines in brackets):
 5. confusion matrices of both masks vs gt                    [utils.py:55-104; evaluate.py:11-45]
 """
 from dataclasses import dataclass
-from typing import List, Optional
+from typing import List
 
 import torch
 

@@ -16,7 +16,6 @@ the real packages are not importable.
 """
 import numpy as np
 import torch
-import torch.nn.functional as F
 from PIL import Image
 
 from . import metrics, ops
