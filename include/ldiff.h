@@ -44,7 +44,7 @@ enum {
 };
 
 /* bits ORed into *status by kernels */
-enum { LDIFF_STATUS_PRED_RANGE = 1, LDIFF_STATUS_INST_RANGE = 2 };
+enum { LDIFF_STATUS_PRED_RANGE = 1, LDIFF_STATUS_INST_RANGE = 2, LDIFF_STATUS_SW_INF = 4 };
 
 int ldiff_abi_version(void);
 const char* ldiff_strerror(int code);
@@ -168,6 +168,22 @@ int ldiff_copy_planes_u8(const uint8_t* src, uint8_t* dst, int64_t n, int B, int
                          void* stream);
 /* int64 labels -> uint8 (values outside [0,254] become 255 = "other") */
 int ldiff_labels_to_u8(const int64_t* in, uint8_t* out, int64_t n, void* stream);
+
+/* ---- widening N2: nnU-Net sliding-window accumulate / mirror-TTA merge / export ----------
+ * (vendored nnU-Net: predict_from_raw_data.py:530-589, label_handling.py:128-173).  All
+ * tensors are fp16 as in the reference (its results arrays are torch.half); every reference
+ * op's rounding to half is reproduced. */
+/* acc[:, y0:y0+th, x0:x0+tw] += pred * gauss ; npred[y0:.., x0:..] += gauss  (gauss NULL: 1) */
+int ldiff_sw_accumulate(const void* pred_f16, const void* gauss_f16, void* acc_f16, void* npred_f16,
+                        int K, int th, int tw, int H, int W, int y0, int x0, void* stream);
+/* out = (preds[0] + sum_j flip(preds[j], flips[j])) / n, adds in order, each rounded to half.
+ * host_preds / host_flips are HOST arrays (n <= 8); flip bit 0 = rows, bit 1 = columns. */
+int ldiff_sw_tta_merge(const void* const* host_preds_f16, const int* host_flips, int n, void* out_f16,
+                       int K, int th, int tw, void* stream);
+/* logits = acc / npred (half); seg = argmax(softmax(logits.float(), 0), 0) as uint8.
+ * logits_out optional.  An infinite logit sets LDIFF_STATUS_SW_INF (the reference raises). */
+int ldiff_sw_finalize_argmax(const void* acc_f16, const void* npred_f16, uint8_t* seg, void* logits_out_f16,
+                             int K, int64_t hw, int* status, void* stream);
 
 #ifdef __cplusplus
 }

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libldiff_sm100.so")
 ABI_VERSION = 1
 
 F32, BF16, U8 = 0, 1, 2
-STATUS_PRED_RANGE, STATUS_INST_RANGE = 1, 2
+STATUS_PRED_RANGE, STATUS_INST_RANGE, STATUS_SW_INF = 1, 2, 4
 
 # name -> (restype, argtypes); mirrors include/ldiff.h one to one
 SIGNATURES = {
@@ -47,6 +47,11 @@ SIGNATURES = {
     "ldiff_confusion_hist_batched": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int,
                                              c_void_p, c_void_p]),
     "ldiff_labels_to_u8": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "ldiff_sw_accumulate": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                    c_int, c_int, c_void_p]),
+    "ldiff_sw_tta_merge": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "ldiff_sw_finalize_argmax": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p,
+                                         c_void_p]),
 }
 
 _lib = None

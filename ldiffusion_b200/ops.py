@@ -67,6 +67,11 @@ def check_status(device):
             raise RuntimeError("Class values must be smaller than num_classes.")
         if bits & _cabi.STATUS_INST_RANGE:
             raise RuntimeError("ldiff: instance id outside the class LUT")
+        if bits & _cabi.STATUS_SW_INF:
+            # predict_from_raw_data.py:581-585
+            raise RuntimeError("Encountered inf in predicted array. Aborting... If this problem persists, "
+                               "reduce value_scaling_factor in compute_gaussian or increase the dtype of "
+                               "predicted_logits to fp32")
 
 
 # ---------------------------------------------------------------------------
@@ -203,6 +208,34 @@ def _labels_to_u8(x: Tensor, out: Tensor) -> None:
     check(_cabi.lib().ldiff_labels_to_u8(_ptr(x), _ptr(out), x.numel(), _stream(x)))
 
 
+def _sw_accumulate(pred: Tensor, gauss: Optional[Tensor], acc: Tensor, npred: Tensor, y0: int, x0: int) -> None:
+    _cuda(pred, gauss, acc, npred)
+    K, th, tw = pred.shape
+    _, H, W = acc.shape
+    check(_cabi.lib().ldiff_sw_accumulate(_ptr(pred), _ptr(gauss), _ptr(acc), _ptr(npred), K, th, tw, H, W, y0, x0,
+                                          _stream(pred)))
+
+
+def _sw_tta_merge(preds: Sequence[Tensor], flips: Sequence[int], out: Tensor) -> None:
+    import ctypes
+    _cuda(out, *preds)
+    K, th, tw = out.shape
+    n = len(preds)
+    ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in preds])
+    fl = (ctypes.c_int * n)(*[int(f) for f in flips])
+    check(_cabi.lib().ldiff_sw_tta_merge(ptrs, fl, n, _ptr(out), K, th, tw, _stream(out)))
+
+
+def _sw_finalize_argmax(acc: Tensor, npred: Tensor, seg: Tensor, logits_out: Optional[Tensor],
+                        status: Tensor) -> None:
+    _cuda(acc, npred, seg, logits_out, status)
+    check(_cabi.lib().ldiff_sw_finalize_argmax(_ptr(acc), _ptr(npred), _ptr(seg), _ptr(logits_out), acc.shape[0],
+                                               npred.numel(), _ptr(status), _stream(acc)))
+
+
+torch.library.custom_op("ldiff::sw_accumulate", mutates_args=("acc", "npred"))(_sw_accumulate)
+torch.library.custom_op("ldiff::sw_tta_merge", mutates_args=("out",))(_sw_tta_merge)
+torch.library.custom_op("ldiff::sw_finalize_argmax", mutates_args=("seg", "logits_out", "status"))(_sw_finalize_argmax)
 torch.library.custom_op("ldiff::laplace_qsample", mutates_args=("out", "noise_out"))(_laplace_qsample)
 torch.library.custom_op("ldiff::plms_step", mutates_args=("out",))(_plms_step)
 torch.library.custom_op("ldiff::decode_tail_gray", mutates_args=("rgb", "gray"))(_decode_tail_gray)

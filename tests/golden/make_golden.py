@@ -133,9 +133,32 @@ def nnunet_golden():
     print("nnunet counts saved")
 
 
+def sliding_golden():
+    """N2: the vendored nnU-Net sliding-window helpers (sliding_window_prediction.py:10-56); the
+    module's unused acvl_utils import is stubbed."""
+    import types
+    sys.path.insert(0, os.path.join(_refshim.REF_ROOT, "model"))
+    for name in ("acvl_utils", "acvl_utils.cropping_and_padding", "acvl_utils.cropping_and_padding.padding"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["acvl_utils.cropping_and_padding.padding"].pad_nd_image = None
+    from nnunetv2.inference.sliding_window_prediction import compute_gaussian, compute_steps_for_sliding_window
+    out = {}
+    for ts in ((64, 64), (48, 80), (512, 512)):
+        g = compute_gaussian(ts, sigma_scale=1. / 8, value_scaling_factor=10, dtype=torch.float16,
+                             device=torch.device("cpu"))
+        out[f"gauss_{ts[0]}x{ts[1]}"] = g.numpy() if ts[0] <= 80 else g.numpy()[::8, ::8].copy()
+    cases = [((110, 110), (64, 64), 0.5), ((1024, 1024), (512, 512), 0.5), ((300, 260), (128, 96), 0.5),
+             ((64, 64), (64, 64), 0.5), ((1000, 700), (256, 256), 0.25)]
+    steps = [compute_steps_for_sliding_window(a, b, c) for a, b, c in cases]
+    np.savez_compressed(os.path.join(HERE, "nnunet_sliding.npz"), steps=np.array(repr(steps)),
+                        cases=np.array(repr(cases)), **out)
+    print("nnunet sliding saved", steps[0], steps[2])
+
+
 if __name__ == "__main__":
     if not _refshim.available():
         raise SystemExit("reference checkout not found; golden metric vectors need it")
     metrics_golden()
     chain_golden()
     nnunet_golden()
+    sliding_golden()

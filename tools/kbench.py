@@ -101,6 +101,21 @@ def main():
     C = torch.zeros(12, 11, dtype=torch.int64, device=dev)
     us = timeit(lambda i: ops.confusion_hist(rnd_p, rnd_g, 11, out=C), 1)
     res["confusion_random_8"] = (us, 2 * 8 * 1024 * 1024 / us / 1e3, 2 * 8 * 1024 * 1024 / us / 1e3 / PEAK)
+    # widening N2: nnU-Net sliding-window tail (K=7 heads, 512x512 tiles on a 1024x1024 image, fp16)
+    from ldiffusion_b200.sliding_window import SlidingWindowAccumulator, tta_merge
+    sw = SlidingWindowAccumulator(7, (1024, 1024), (512, 512), True, dev)
+    tiles = [(torch.randn(7, 512, 512, device=dev) * 3).half() for _ in range(4)]
+    us = timeit(lambda i: sw.add(tiles[i], 256 * (i % 3), 256 * (i % 2)), 4)
+    byt = 512 * 512 * (7 * 2 * 3 + 2 * 3)                  # pred in, acc in+out, gauss in, npred in+out
+    res["sw_accumulate_tile"] = (us, byt / us / 1e3, byt / us / 1e3 / PEAK)
+    us = timeit(lambda i: tta_merge(tiles, [0, 1, 2, 3]), 1)
+    byt = 7 * 512 * 512 * 2 * 5
+    res["sw_tta_merge_4"] = (us, byt / us / 1e3, byt / us / 1e3 / PEAK)
+    sw.acc.copy_((torch.randn(7, 1024, 1024, device=dev) * 30).half())     # sane accumulators (the timing loop above overflowed them)
+    sw.npred.fill_(10.0)
+    us = timeit(lambda i: sw.finalize(), 1)
+    byt = 1024 * 1024 * (7 * 2 + 2 + 1)
+    res["sw_finalize_argmax"] = (us, byt / us / 1e3, byt / us / 1e3 / PEAK)
     for k, (us, gbs, fr) in res.items():
         print(f"{k:32s} {us:10.2f} us  {gbs:9.1f} GB/s  {fr:6.3f} of measured peak")
     os.makedirs("gpurun_out", exist_ok=True)
