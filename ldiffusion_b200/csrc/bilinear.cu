@@ -186,9 +186,9 @@ lift_separable_kernel(const TS* __restrict__ src, int64_t sbs, int64_t scs, TD* 
   const int yhi = make_tap(ay, Y1 - 1).i1;
   const int nrows = yhi - ylo + 1;                      // <= max_rows by construction
 
-  if (threadIdx.x < Y1 - Y0) {
-    const Tap t = make_tap(ay, Y0 + threadIdx.x);
-    s_tap[threadIdx.x] = make_int4(t.i0 - ylo, t.i1 - ylo, __float_as_int(t.l0), __float_as_int(t.l1));
+  for (int i = threadIdx.x; i < Y1 - Y0; i += blockDim.x) {   // (blockDim.x can be smaller than the band)
+    const Tap t = make_tap(ay, Y0 + i);
+    s_tap[i] = make_int4(t.i0 - ylo, t.i1 - ylo, __float_as_int(t.l0), __float_as_int(t.l1));
   }
   if (threadIdx.x == 0) mbar_init(&bar, 1);
   __syncthreads();
