@@ -211,3 +211,33 @@ def test_sampler_stress_config():
     gr.replay()
     torch.cuda.synchronize()
     assert torch.equal(out.cpu(), x)
+
+
+def test_pass_full_size_patches():
+    """BASELINE configs[1] geometry (1024x1024, K=11, 5 steps, bf16, 800 instances) on 2 patches:
+    every integer output of the pass equals the oracle pipeline; masks equal the pinned decision
+    rule on the kernel's own logits."""
+    from ldiffusion_b200 import ops
+    from ldiffusion_b200.pipeline import HotPath, HotPathInputs, synth_inputs
+    B, H, W, K, n = 2, 1024, 1024, 11, 5
+    host = synth_inputs(B, H, W, K, n, dtype=torch.bfloat16, device="cpu", seed=99)
+    dev = HotPathInputs(*[([t.cuda() for t in f] if isinstance(f, list) else f.cuda())
+                          for f in (host.latents, host.eps, host.decoded, host.head_feat, host.inst_map,
+                                    host.inst_feats, host.gt)])
+    hp = HotPath(B, H, W, K, n, dtype=torch.bfloat16, device="cuda", seed=99)
+    hp.run(dev)
+    torch.cuda.synchronize()
+    ops.check_status("cuda")
+    res = hp.results()
+    ref = run_chain(host, K, hp.head_w.cpu(), hp.head_b.cpu(), hp.cell_w.cpu(), hp.cell_b.cpu(), metrics="none")
+    assert np.array_equal(res["pixel_planes"].cpu().numpy(), ref["pixel_planes"])
+    assert np.array_equal(res["rgb"].cpu().numpy(), ref["rgb"])
+    assert torch.equal(res["label_small"].cpu(), ref["label_small"])
+    torch.testing.assert_close(res["logits"].cpu(), ref["logits"], rtol=1e-3, atol=1e-3)
+    mt = res["mask_tissue"].cpu().numpy()
+    assert np.array_equal(mt, ohead.lift_argmax_spec(res["logits"].cpu().numpy(), (H, W)))
+    assert (mt != ref["mask_tissue"].numpy()).mean() < 1e-4              # logits differ by summation order only
+    assert (res["mask_cell"].cpu() != ref["mask_cell"]).float().mean() < 2e-3
+    want = np.stack([omet.confusion_matrix(res[m].cpu().numpy(), host.gt.numpy(), K) for m in ("mask_tissue", "mask_cell")])
+    assert np.array_equal(res["confusion"].cpu().numpy(), want)
+    assert int(res["confusion"].sum()) == 2 * B * H * W
