@@ -185,6 +185,22 @@ int ldiff_sw_tta_merge(const void* const* host_preds_f16, const int* host_flips,
 int ldiff_sw_finalize_argmax(const void* acc_f16, const void* npred_f16, uint8_t* seg, void* logits_out_f16,
                              int K, int64_t hw, int* status, void* stream);
 
+/* ---- widening N3: pixel-contrastive InfoNCE (model/loss.py:44-109) -------------------------
+ * feat fp32 [B,C,hw] (C <= 16: one channel per sampling step).  Triple p = (pair_batch[p],
+ * pair_anchor[p], pair_pos[p], pair_neg[p, 0..n_neg)) of pixel indices (int32, device).
+ * forward: loss_per_pair[p] = cross_entropy([a.pos, a.neg_1 ..] / T, target 0); lse_per_pair
+ * keeps the log-sum-exp for the backward.  The reference's result is mean(loss_per_pair). */
+int ldiff_infonce_forward(const float* feat, const int* pair_batch, const int* pair_anchor,
+                          const int* pair_pos, const int* pair_neg, float* loss_per_pair,
+                          float* lse_per_pair, int C, int64_t hw, int n_neg, int n_pairs,
+                          float temperature, void* stream);
+/* backward: grad_feat (fp32 [B,C,hw], caller-zeroed) += d(sum_p loss_p)/d(feat) * (*grad_scale);
+ * grad_scale is a DEVICE scalar (upstream gradient / n_pairs). */
+int ldiff_infonce_backward(const float* feat, const int* pair_batch, const int* pair_anchor,
+                           const int* pair_pos, const int* pair_neg, const float* lse_per_pair,
+                           const float* grad_scale, float* grad_feat, int C, int64_t hw, int n_neg,
+                           int n_pairs, float temperature, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,6 +8,7 @@ Public surface (drop-in seams, see DESIGN.md / INTEGRATION.md):
 * ``TissueHead`` / ``cell_mask``      - classifier head + argmax
 * ``micro_dice`` / ``mean_iou_and_per_class`` / ``pixel_accuracy`` /
   ``frequency_weighted_iou`` / ``evaluate``
+* ``pixel_contrastive_loss``          - InfoNCE term of the warm-up loss (forward + backward)
 * ``Segmentor`` / ``LDiffusionModel`` - orchestrator shims with the reference's signatures
 
 All tensor work runs in ``libldiff_sm100.so`` (hand-written CUDA behind the C ABI
@@ -20,6 +21,7 @@ from .head import TissueHead, cell_mask, tissue_mask  # noqa: F401
 from .metrics import (confusion_matrix, evaluate, frequency_weighted_iou, mean_iou_and_per_class,  # noqa: F401
                       micro_dice, pixel_accuracy)
 from .ldiffusion import LDiffusionModel  # noqa: F401
+from .loss import pixel_contrastive_loss, sample_contrastive_pairs  # noqa: F401
 from .scheduler import LaplacePLMSScheduler  # noqa: F401
 from .segmentor import Segmentor  # noqa: F401
 

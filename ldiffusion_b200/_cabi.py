@@ -47,6 +47,10 @@ SIGNATURES = {
     "ldiff_confusion_hist_batched": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int,
                                              c_void_p, c_void_p]),
     "ldiff_labels_to_u8": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "ldiff_infonce_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                      c_int64, c_int, c_int, c_float, c_void_p]),
+    "ldiff_infonce_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_int, c_int64, c_int, c_int, c_float, c_void_p]),
     "ldiff_sw_accumulate": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                     c_int, c_int, c_void_p]),
     "ldiff_sw_tta_merge": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),

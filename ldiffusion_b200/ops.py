@@ -233,6 +233,26 @@ def _sw_finalize_argmax(acc: Tensor, npred: Tensor, seg: Tensor, logits_out: Opt
                                                npred.numel(), _ptr(status), _stream(acc)))
 
 
+def _infonce_forward(feat: Tensor, pb: Tensor, pa: Tensor, pq: Tensor, neg: Tensor, loss: Tensor, lse: Tensor,
+                     temperature: float) -> None:
+    _cuda(feat, pb, pa, pq, neg, loss, lse)
+    B, C = feat.shape[:2]
+    check(_cabi.lib().ldiff_infonce_forward(_ptr(feat), _ptr(pb), _ptr(pa), _ptr(pq), _ptr(neg), _ptr(loss),
+                                            _ptr(lse), C, feat[0, 0].numel(), neg.shape[1], pa.numel(),
+                                            temperature, _stream(feat)))
+
+
+def _infonce_backward(feat: Tensor, pb: Tensor, pa: Tensor, pq: Tensor, neg: Tensor, lse: Tensor, gscale: Tensor,
+                      grad: Tensor, temperature: float) -> None:
+    _cuda(feat, pb, pa, pq, neg, lse, gscale, grad)
+    B, C = feat.shape[:2]
+    check(_cabi.lib().ldiff_infonce_backward(_ptr(feat), _ptr(pb), _ptr(pa), _ptr(pq), _ptr(neg), _ptr(lse),
+                                             _ptr(gscale), _ptr(grad), C, feat[0, 0].numel(), neg.shape[1],
+                                             pa.numel(), temperature, _stream(feat)))
+
+
+torch.library.custom_op("ldiff::infonce_forward", mutates_args=("loss", "lse"))(_infonce_forward)
+torch.library.custom_op("ldiff::infonce_backward", mutates_args=("grad",))(_infonce_backward)
 torch.library.custom_op("ldiff::sw_accumulate", mutates_args=("acc", "npred"))(_sw_accumulate)
 torch.library.custom_op("ldiff::sw_tta_merge", mutates_args=("out",))(_sw_tta_merge)
 torch.library.custom_op("ldiff::sw_finalize_argmax", mutates_args=("seg", "logits_out", "status"))(_sw_finalize_argmax)

@@ -139,3 +139,27 @@ def test_confusion_collectives_world_size_2(n_tiles):
     for _, total, tiles in got:
         assert np.array_equal(total, per_tile.sum(0))          # == single-process matrix, bit for bit
         assert np.array_equal(tiles, per_tile)                  # global tile order restored
+
+
+def test_contrastive_pair_sampling_rules_and_cpu_refusal():
+    """model/loss.py:64-87: 1 % of each class as anchors, positive = another pixel of the class,
+    negatives = num_negatives distinct pixels of other classes; classes without enough negatives
+    are skipped; the product refuses CPU feature tensors."""
+    from ldiffusion_b200 import ops
+    from ldiffusion_b200.loss import pixel_contrastive_loss, sample_contrastive_pairs
+    lab = torch.zeros(2, 1, 32, 32, dtype=torch.uint8)
+    lab[0, 0, :16] = 1
+    lab[1, 0, 0, :2] = 3
+    pb, pa, pq, neg = sample_contrastive_pairs(lab, 400, torch.Generator().manual_seed(1))
+    flat = lab.reshape(2, -1)
+    for b, a, q, ng in zip(pb.tolist(), pa.tolist(), pq.tolist(), neg):
+        assert flat[b, a] == flat[b, q] and a != q
+        assert (flat[b, ng.long()] != flat[b, a]).all() and len(set(ng.tolist())) == 400
+    # image 0: classes 0 and 1 of 512 px each -> 5 anchors each; image 1: class 3 (2 px, 1022 negatives)
+    # gives max(1, 0) = 1 anchor, class 0 (1022 px) has only 2 negatives -> skipped
+    assert pb.tolist().count(0) == 10 and pb.tolist().count(1) == 1
+    again = sample_contrastive_pairs(lab, 400, torch.Generator().manual_seed(1))
+    assert all(torch.equal(x, y) for x, y in zip((pb, pa, pq, neg), again))
+    assert sample_contrastive_pairs(torch.zeros(1, 1, 8, 8, dtype=torch.uint8), 16) is None
+    with pytest.raises(ops.LdiffError):
+        pixel_contrastive_loss(torch.zeros(1, 5, 32, 32), lab[:1])

@@ -116,6 +116,22 @@ def main():
     us = timeit(lambda i: sw.finalize(), 1)
     byt = 1024 * 1024 * (7 * 2 + 2 + 1)
     res["sw_finalize_argmax"] = (us, byt / us / 1e3, byt / us / 1e3 / PEAK)
+    # widening N3: pixel-contrastive InfoNCE, 8 x 5 x 64 x 64 features, 1024 negatives per anchor
+    from ldiffusion_b200.loss import sample_contrastive_pairs
+    lab = torch.zeros(8, 1, 64, 64, dtype=torch.uint8)
+    for b in range(8):
+        for q in range(6):
+            lab[b, 0, 8 * q:8 * q + 16, 5 * q:5 * q + 24] = 1 + (b + q) % 6
+    pairs = [t.to(dev) for t in sample_contrastive_pairs(lab, 1024, torch.Generator().manual_seed(0))]
+    feat = torch.randn(8, 5, 64, 64, device=dev)
+    A = pairs[1].numel()
+    loss, lse = torch.empty(A, device=dev), torch.empty(A, device=dev)
+    grad, gs = torch.zeros_like(feat), torch.full((1,), 1.0 / A, device=dev)
+    byt = A * 1026 * 5 * 4                                   # gathered candidate features (L2-resident map)
+    us = timeit(lambda i: ops._infonce_forward(feat, *pairs, loss, lse, 0.5), 1)
+    res[f"infonce_forward_{A}x1025"] = (us, byt / us / 1e3, byt / us / 1e3 / PEAK)
+    us = timeit(lambda i: ops._infonce_backward(feat, *pairs, lse, gs, grad, 0.5), 1)
+    res[f"infonce_backward_{A}x1025"] = (us, 2 * byt / us / 1e3, 2 * byt / us / 1e3 / PEAK)
     for k, (us, gbs, fr) in res.items():
         print(f"{k:32s} {us:10.2f} us  {gbs:9.1f} GB/s  {fr:6.3f} of measured peak")
     os.makedirs("gpurun_out", exist_ok=True)
