@@ -48,10 +48,15 @@ def parse():
     return ap.parse_args()
 
 
+AR_NOTE = {"peer": "histogram kernel pushes into NVLink peer windows + one-block reduce, inside the graph",
+           "nccl": "NCCL all-reduce behind each graph"}
+
+
 def config(n_gpus):
     return {"workload": WORKLOAD, "batch_per_gpu": B, "patch": [H, W], "classes": K, "sampling_steps": NSTEPS,
             "instances_per_patch": NINST, "storage": "bf16", "arithmetic": "fp32",
-            "parallelism": f"patch-sharded x{n_gpus} (no data-path collective; int64 confusion all-reduce per step)",
+            "parallelism": f"patch-sharded x{n_gpus} (no data-path collective; the two int64 confusion matrices are "
+                           f"summed across ranks every step: {AR_NOTE.get(os.environ.get('LDIFF_ALLREDUCE', 'peer'), '')})",
             "l2": "two rotating input sets of 0.35 GB each (> 126 MB L2)",
             "backbone": "SD-v1.5 UNet/VAE outputs are synthetic resident tensors (cuDNN calls, out of scope)"}
 
@@ -196,19 +201,28 @@ def run_ours(args):
                                         for f in (hs.latents, hs.eps, hs.decoded, hs.head_feat, hs.inst_map,
                                                   hs.inst_feats, hs.gt)]))
     hp = HotPath(B, H, W, K, NSTEPS, dtype=dt, device=dev, n_instances=NINST, seed=1234 + rank)
+    # N > 1: the only cross-rank step is the sum of the two int64 confusion matrices.  Default "peer":
+    # the histogram kernels push their matrices into every rank's window over NVLink peer memory and a
+    # one-block kernel adds the W rows, all inside the pass (graph-captured, no collective library on
+    # the path).  LDIFF_ALLREDUCE=nccl keeps the separate NCCL all-reduce behind each pass instead.
+    ar_mode = os.environ.get("LDIFF_ALLREDUCE", "peer") if world > 1 else "none"
+    if ar_mode == "peer":
+        from ldiffusion_b200.dist import ConfusionExchange
+        hp.attach_exchange(ConfusionExchange(K, channels=2, device=dev),
+                           deferred=os.environ.get("LDIFF_XCHG_DEFERRED", "1") == "1")
     launches_per_pass = hp.launches_per_pass()
 
-    # ---- value: graph-replayed passes over resident inputs.  With N > 1 every step ends with the
-    # only collective of the path: one all-reduce of the int64 confusion matrices, issued on the
-    # buffer the histogram kernels accumulated into (eager NCCL call right behind the graph;
-    # LDIFF_GRAPH_ALLREDUCE=1 captures it into the graph instead).
+    # ---- value: graph-replayed passes over resident inputs (N > 1: the exchange is part of the graph;
+    # in nccl mode an eager async all-reduce follows each graph, LDIFF_GRAPH_ALLREDUCE=1 captures it).
     stream = torch.cuda.Stream(dev)
-    graph_ar = world > 1 and os.environ.get("LDIFF_GRAPH_ALLREDUCE", "0") == "1"
+    nccl_ar = ar_mode == "nccl"
+    graph_ar = nccl_ar and os.environ.get("LDIFF_GRAPH_ALLREDUCE", "0") == "1"
     graphs = []
+    barrier()                                         # ranks enter the first exchanged pass together
     with torch.cuda.stream(stream):
         for s in range(2):
             hp.run(dev_sets[s])                       # warm-up outside capture
-            if world > 1:
+            if nccl_ar:
                 dist.all_reduce(hp.C)                 # creates the NCCL communicator
         stream.synchronize()
         c0 = _cabi.launch_count()
@@ -228,7 +242,7 @@ def run_ours(args):
 
     def step(i):
         graphs[i & 1].replay()
-        if world > 1 and not graph_ar:
+        if nccl_ar and not graph_ar:
             k = i & 1
             if works[k] is not None:
                 works[k].wait()                       # stream-side wait, the host does not block
@@ -262,6 +276,12 @@ def run_ours(args):
         t_wall1 = time.perf_counter()
     ms = ev0.elapsed_time(ev1)
     ops.check_status(dev)
+    if ar_mode == "peer":                             # untimed check: the in-pass exchange equals an NCCL all-reduce
+        with torch.cuda.stream(stream):
+            ref = hp.C.clone()
+            dist.all_reduce(ref)
+            assert torch.equal(ref, hp.flush_exchange()), "peer exchange differs from the NCCL all-reduce"
+            assert int(hp.C_global.sum()) == 2 * world * B * H * W, "exchange lost pixels"
 
     # ---- roofline of the dominant kernel: decode_tail_gray alone, rotating over 10 decoded tensors (0.5 GB)
     imgs = dev_sets[0].decoded + dev_sets[1].decoded
@@ -310,7 +330,7 @@ def run_ours(args):
     h2d = host.nbytes()
     host_out = [hp.alloc_host_results() for _ in range(2)]
     d2h = sum(t.numel() * t.element_size() for t in host_out[0].values())
-    after = (lambda: dist.all_reduce(hp.C)) if world > 1 else None
+    after = (lambda: dist.all_reduce(hp.C)) if nccl_ar else None
     e2e_steps = max(4, min(args.steps, 12))
     with torch.cuda.stream(stream):
         hp.run_host([host] * 3, host_out, after_run=after)

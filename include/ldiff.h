@@ -44,7 +44,8 @@ enum {
 };
 
 /* bits ORed into *status by kernels */
-enum { LDIFF_STATUS_PRED_RANGE = 1, LDIFF_STATUS_INST_RANGE = 2, LDIFF_STATUS_SW_INF = 4 };
+enum { LDIFF_STATUS_PRED_RANGE = 1, LDIFF_STATUS_INST_RANGE = 2, LDIFF_STATUS_SW_INF = 4,
+       LDIFF_STATUS_XCHG_TIMEOUT = 8 };
 
 int ldiff_abi_version(void);
 const char* ldiff_strerror(int code);
@@ -162,6 +163,43 @@ int ldiff_confusion_hist(const uint8_t* pred, const uint8_t* gt, const uint8_t* 
 int ldiff_confusion_hist_batched(const uint8_t* pred, const uint8_t* gt, const uint8_t* gt_lut,
                                  int64_t* C, int64_t n_per_image, int n_images, int K, int* status,
                                  void* stream);
+
+/* ---- a-6 across GPUs: histogram fused with its all-reduce over NVLink peer memory -------------
+ * Replaces the only cross-rank exchange the reference has for these counts, nnU-Net's three
+ * pickled all_gather_object calls (nnUNetTrainer.py:1004-1012), and a separate NCCL all-reduce
+ * behind the histogram.  One process per GPU; each rank owns a small "window" in device memory
+ * that every peer maps through CUDA IPC.
+ *
+ *   ldiff_xchg_create        allocate + zero this rank's window (world <= 16, channels <= 4,
+ *                            n_i64 = (K+1)*K counters per channel)
+ *   ldiff_xchg_ipc_handle    64-byte CUDA IPC handle of the window (exchange it with any host
+ *                            transport, e.g. torch.distributed.all_gather_object)
+ *   ldiff_xchg_connect_ipc   handles = world * 64 bytes in rank order (own entry ignored)
+ *   ldiff_xchg_connect_local same-process windows (several "ranks" on one GPU: tests)
+ *   ldiff_confusion_hist_push  ldiff_confusion_hist whose last block stores the finished matrix C
+ *                            into row `rank`, channel `channel` of EVERY rank's window and raises
+ *                            that row's flag (st.release.sys after a system fence)
+ *   ldiff_xchg_reduce        one block: the j-th reduce of a rank waits for the j-th push of
+ *                            every rank and channel, then writes the sum of the world rows to
+ *                            out [channels][n_i64]
+ *   ldiff_xchg_destroy       unmap peers, free the window (synchronise all ranks first)
+ *
+ * Ordering contract: every rank pushes every channel once per step and reduces once per step;
+ * pushes and reduces are matched by count, so a reduce may be enqueued right behind its pushes
+ * or a whole step later, concurrently with the next step's work (it then never waits).  Rows
+ * live in a ring of 4 slots: push j of a rank must be stream-ordered after that rank's reduce
+ * j-2 (at most two steps outstanding).  Integer sums: bit-exact at any world size.  A rank that
+ * never arrives trips a 2 s device-side timeout (LDIFF_STATUS_XCHG_TIMEOUT), not a hang.
+ * Both kernels are plain launches and can be captured into CUDA graphs. */
+int ldiff_xchg_create(int world, int rank, int channels, int n_i64, void** handle);
+int ldiff_xchg_ipc_handle(void* handle, void* out64);
+int ldiff_xchg_connect_ipc(void* handle, const void* handles);
+int ldiff_xchg_connect_local(void* handle, void* const* peer_handles);
+int ldiff_xchg_destroy(void* handle);
+int ldiff_confusion_hist_push(const uint8_t* pred, const uint8_t* gt, const uint8_t* gt_lut,
+                              int64_t* C, int64_t n, int K, void* xchg, int channel, int* status,
+                              void* stream);
+int ldiff_xchg_reduce(void* xchg, int64_t* out, int* status, void* stream);
 /* B planes of n bytes -> a strided slot (the label plane of the pixel vectors,
  * pixel_latent_vector.py:92); n and dst_stride multiples of 16 */
 int ldiff_copy_planes_u8(const uint8_t* src, uint8_t* dst, int64_t n, int B, int64_t dst_stride,

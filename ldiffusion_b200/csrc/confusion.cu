@@ -14,6 +14,7 @@
 //    buffer handed to ncclAllReduce).
 // Larger K (16..128) takes the same kernel with per-pixel integer bin math.
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -24,17 +25,63 @@ __device__ __forceinline__ uint32_t bytes_ge(uint32_t w, uint32_t k) {
   return (((w & 0x7f7f7f7fu) + (0x80u - k) * 0x01010101u) | w) & 0x80808080u;
 }
 
-template <int R, bool SMALLK, bool HAS_LUT>
-__global__ void __launch_bounds__(512)
-confusion_hist_kernel(const uint8_t* __restrict__ pred, const uint8_t* __restrict__ gt,
-                      const uint8_t* __restrict__ gt_lut, unsigned long long* __restrict__ C,
-                      int64_t n, int K, int* __restrict__ status) {
+// ---- peer exchange window (multi-GPU): one per rank, mapped into every peer over NVLink -------------
+// The only cross-rank step of the path is the SUM of the int64 matrices.  Instead of a separate
+// collective, the LAST block of the histogram kernel stores the finished matrix straight into every
+// peer's window (plain 8-byte stores over NVLink peer mappings); a one-block kernel on each rank then
+// waits for the W rows and adds them.  Every 8-byte word carries half a counter and the step number
+// (data and "it has landed" travel in one atomic store, as in NCCL's LL protocol), so the pusher
+// needs no system fence and no separate flag: its tail is one dependent read of the matrix and a
+// burst of fire-and-forget stores.  Rows are overwritten, never accumulated, so nothing is zeroed
+// between steps; kXSlots ring slots keep a row alive until every rank has read it (ordering
+// contract in ldiff.h).
+constexpr int kXSlots = 4, kXMaxWorld = 16, kXMaxChan = 4, kXHeaderBytes = 256;
+struct XchgHeader {
+  unsigned long long step[kXMaxChan];                          // pushes completed by THIS rank, per channel
+  unsigned long long reduced;                                  // reduces completed by THIS rank
+  unsigned int ticket[kXMaxChan];                              // last-block election of the histogram grid
+};
+static_assert(sizeof(XchgHeader) <= kXHeaderBytes, "header does not fit");
+struct XchgPush {                                              // by-value kernel argument; win == nullptr: off
+  XchgHeader* win;
+  int world, rank, channels, channel, n;
+  unsigned long long peers[kXMaxWorld];                        // window base of every rank, as mapped here
+};
+// row of (slot, source rank, channel): 2*n words, word 2*bin = lo32 | tag<<32, word 2*bin+1 = hi32 | tag<<32
+__device__ __forceinline__ unsigned long long* xchg_row(unsigned long long base, int slot, int src, int chan,
+                                                        int world, int channels, int n) {
+  return reinterpret_cast<unsigned long long*>(base + kXHeaderBytes) +
+         ((int64_t)(slot * world + src) * channels + chan) * (2 * n);
+}
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+template <int R, bool SMALLK, bool HAS_LUT, bool PUSH>
+__device__ __forceinline__ void
+confusion_hist_body(const uint8_t* __restrict__ pred, const uint8_t* __restrict__ gt,
+                    const uint8_t* __restrict__ gt_lut, unsigned long long* __restrict__ C,
+                    int64_t n, int K, int* __restrict__ status, XchgPush px) {
   extern __shared__ uint32_t hist[];                 // [nbins][R]
   __shared__ uint8_t lut[256];
   const int nbins = (K + 1) * K;
   for (int i = threadIdx.x; i < nbins * R; i += blockDim.x) hist[i] = 0;
   if (HAS_LUT)
     for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = gt_lut[i];
+  // (push) this launch's step number: only the previous launch's last block ever changes the counter,
+  // so it is read here, long before the tail needs it, instead of on the tail's dependent chain
+  __shared__ unsigned long long s_step;
+  if (PUSH && threadIdx.x == 0) s_step = __ldcg(&px.win->step[px.channel]) + 1;
   __syncthreads();
 
   // grid.y = image (batched form: one matrix per image)
@@ -100,6 +147,85 @@ confusion_hist_kernel(const uint8_t* __restrict__ pred, const uint8_t* __restric
     for (int r = 0; r < R; ++r) s += hist[bin * R + ((r + threadIdx.x) & (R - 1))];
     if (s) atomicAdd(C + bin, s);
   }
+  if (!PUSH) return;
+
+  // ---- fused exchange: the last block to finish owns the complete matrix and pushes it to every rank
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0)
+    s_last = atomicAdd(&px.win->ticket[px.channel], 1u) == gridDim.x * gridDim.y - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const unsigned long long step = s_step;
+  const unsigned long long tag = (step & 0xffffffffull) << 32;
+  const int slot = (int)(step % kXSlots);
+  for (int bin = threadIdx.x; bin < px.n; bin += blockDim.x) {
+    const unsigned long long v = __ldcg(C + bin);
+    const unsigned long long w0 = (v & 0xffffffffull) | tag, w1 = (v >> 32) | tag;
+    for (int q = 0; q < px.world; ++q) {
+      unsigned long long* row = xchg_row(px.peers[q], slot, px.rank, px.channel, px.world, px.channels, px.n);
+      st_relaxed_sys(row + 2 * bin, w0);
+      st_relaxed_sys(row + 2 * bin + 1, w1);
+    }
+  }
+  if (threadIdx.x == 0) {
+    px.win->step[px.channel] = step;
+    px.win->ticket[px.channel] = 0;                  // re-armed for the next launch (stream-ordered)
+  }
+}
+
+template <int R, bool SMALLK, bool HAS_LUT>
+__global__ void __launch_bounds__(512)
+confusion_hist_kernel(const uint8_t* __restrict__ pred, const uint8_t* __restrict__ gt,
+                      const uint8_t* __restrict__ gt_lut, unsigned long long* __restrict__ C,
+                      int64_t n, int K, int* __restrict__ status) {
+  confusion_hist_body<R, SMALLK, HAS_LUT, false>(pred, gt, gt_lut, C, n, K, status, XchgPush{});
+}
+
+// same histogram with the fused push (its own entry so the plain kernel's register allocation
+// stays what it was: the longer tail otherwise makes ptxas spill in the hot loop)
+template <int R, bool SMALLK, bool HAS_LUT>
+__global__ void __launch_bounds__(512, 2)
+confusion_hist_push_kernel(const uint8_t* __restrict__ pred, const uint8_t* __restrict__ gt,
+                           const uint8_t* __restrict__ gt_lut, unsigned long long* __restrict__ C,
+                           int64_t n, int K, int* __restrict__ status, XchgPush px) {
+  confusion_hist_body<R, SMALLK, HAS_LUT, true>(pred, gt, gt_lut, C, n, K, status, px);
+}
+
+// One block per rank.  The j-th reduce of a rank adds the rows of every rank's j-th push: each thread
+// owns a few (channel, bin) counters and, per source rank, spins until both words of the counter carry
+// the step's tag.  A peer that never arrives (crashed rank) trips a timeout (2 s;
+// LDIFF_XCHG_TIMEOUT_MS) that sets LDIFF_STATUS_XCHG_TIMEOUT instead of hanging the GPU.
+__global__ void __launch_bounds__(256)
+xchg_reduce_kernel(XchgHeader* __restrict__ win, unsigned long long* __restrict__ out, int world,
+                   int channels, int n, unsigned long long timeout_ns, int* __restrict__ status) {
+  const unsigned long long want = win->reduced + 1;
+  const unsigned long long tag = want & 0xffffffffull;
+  const int slot = (int)(want % kXSlots);
+  const unsigned long long t0 = globaltimer_ns();
+  bool late = false;
+  for (int i = threadIdx.x; i < channels * n; i += blockDim.x) {
+    const int ch = i / n, bin = i - ch * n;
+    unsigned long long s = 0;
+    for (int src = 0; src < world; ++src) {
+      const unsigned long long* w =
+          xchg_row(reinterpret_cast<unsigned long long>(win), slot, src, ch, world, channels, n) + 2 * bin;
+      unsigned long long w0 = ld_relaxed_sys(w), w1 = ld_relaxed_sys(w + 1);
+      while (!late && ((w0 >> 32) != tag || (w1 >> 32) != tag)) {
+        if (globaltimer_ns() - t0 > timeout_ns) { late = true; break; }
+        __nanosleep(100);
+        w0 = ld_relaxed_sys(w);
+        w1 = ld_relaxed_sys(w + 1);
+      }
+      if ((w0 >> 32) == tag && (w1 >> 32) == tag) s += (w0 & 0xffffffffull) | (w1 << 32);
+    }
+    out[i] = s;
+  }
+  if (late) atomicOr(status, LDIFF_STATUS_XCHG_TIMEOUT);
+  __syncthreads();                                   // every thread has read `reduced`
+  if (threadIdx.x == 0) win->reduced = want;
 }
 
 __global__ void __launch_bounds__(256)
@@ -124,7 +250,8 @@ labels_to_u8_kernel(const int64_t* __restrict__ in, uint8_t* __restrict__ out, i
 using namespace ldiff;
 
 static int launch_confusion(const uint8_t* pred, const uint8_t* gt, const uint8_t* gt_lut, int64_t* C,
-                            int64_t n_per_image, int n_images, int K, int* status, cudaStream_t st) {
+                            int64_t n_per_image, int n_images, int K, int* status, cudaStream_t st,
+                            XchgPush px = XchgPush{}) {
   const int threads = 512;
   const int nbins = (K + 1) * K;
   int R = 32;
@@ -142,11 +269,19 @@ static int launch_confusion(const uint8_t* pred, const uint8_t* gt, const uint8_
   const bool smallk = K <= 15;
 #define CH3(RR, SK, LUT)                                                                            \
   do {                                                                                              \
-    if (smem > 48 * 1024)                                                                           \
+    if (smem > 48 * 1024) {                                                                         \
       cudaFuncSetAttribute(confusion_hist_kernel<RR, SK, LUT>,                                      \
                            cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);                 \
-    confusion_hist_kernel<RR, SK, LUT><<<grid, threads, smem, st>>>(pred, gt, gt_lut, Cu,           \
-                                                                    n_per_image, K, status);        \
+      cudaFuncSetAttribute(confusion_hist_push_kernel<RR, SK, LUT>,                                 \
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);                 \
+    }                                                                                               \
+    if (px.win)                                                                                     \
+      confusion_hist_push_kernel<RR, SK, LUT><<<grid, threads, smem, st>>>(pred, gt, gt_lut, Cu,    \
+                                                                           n_per_image, K, status,  \
+                                                                           px);                     \
+    else                                                                                            \
+      confusion_hist_kernel<RR, SK, LUT><<<grid, threads, smem, st>>>(pred, gt, gt_lut, Cu,         \
+                                                                      n_per_image, K, status);      \
   } while (0)
 #define CH(RR, SK)                                \
   do {                                            \
@@ -185,6 +320,119 @@ extern "C" int ldiff_confusion_hist_batched(const uint8_t* pred, const uint8_t* 
   if (K > 128 || n_images > 65535) return LDIFF_EUNSUPPORTED;
   if (n_per_image == 0 || n_images == 0) return LDIFF_OK;
   return launch_confusion(pred, gt, gt_lut, C, n_per_image, n_images, K, status, (cudaStream_t)stream);
+}
+
+// ---- exchange window management (host side) ----------------------------------------------------
+namespace {
+struct Xchg {
+  int world, rank, channels, n;
+  size_t bytes;
+  char* base;                          // this rank's window (cudaMalloc: IPC-exportable)
+  void* mapped[kXMaxWorld];            // peers opened through CUDA IPC (closed in destroy)
+  unsigned long long peers[kXMaxWorld];  // window base of every rank as mapped in this process
+};
+}  // namespace
+
+extern "C" int ldiff_xchg_create(int world, int rank, int channels, int n_i64, void** handle) {
+  if (!handle || world < 1 || world > kXMaxWorld || rank < 0 || rank >= world || channels < 1 ||
+      channels > kXMaxChan || n_i64 < 1)
+    return LDIFF_EINVAL;
+  Xchg* x = new Xchg();
+  x->world = world; x->rank = rank; x->channels = channels; x->n = n_i64;
+  x->bytes = kXHeaderBytes + (size_t)kXSlots * world * channels * n_i64 * 2 * sizeof(int64_t);
+  for (int i = 0; i < kXMaxWorld; ++i) { x->mapped[i] = nullptr; x->peers[i] = 0; }
+  if (cudaMalloc(&x->base, x->bytes) != cudaSuccess || cudaMemset(x->base, 0, x->bytes) != cudaSuccess ||
+      cudaDeviceSynchronize() != cudaSuccess) {
+    cudaGetLastError();
+    delete x;
+    return LDIFF_ELAUNCH;
+  }
+  *handle = x;
+  return LDIFF_OK;
+}
+
+extern "C" int ldiff_xchg_ipc_handle(void* handle, void* out64) {
+  if (!handle || !out64) return LDIFF_EINVAL;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  if (cudaIpcGetMemHandle(&h, static_cast<Xchg*>(handle)->base) != cudaSuccess) {
+    cudaGetLastError();
+    return LDIFF_ELAUNCH;
+  }
+  memcpy(out64, &h, 64);
+  return LDIFF_OK;
+}
+
+static int xchg_set_peers(Xchg* x, void* const* bases) {
+  for (int q = 0; q < kXMaxWorld; ++q)
+    x->peers[q] = q < x->world ? reinterpret_cast<unsigned long long>(bases[q]) : 0ull;
+  return LDIFF_OK;
+}
+
+extern "C" int ldiff_xchg_connect_ipc(void* handle, const void* handles) {
+  if (!handle || !handles) return LDIFF_EINVAL;
+  Xchg* x = static_cast<Xchg*>(handle);
+  void* bases[kXMaxWorld];
+  for (int q = 0; q < x->world; ++q) {
+    if (q == x->rank) { bases[q] = x->base; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, static_cast<const char*>(handles) + 64 * q, 64);
+    if (cudaIpcOpenMemHandle(&x->mapped[q], h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      return LDIFF_ELAUNCH;
+    }
+    bases[q] = x->mapped[q];
+  }
+  return xchg_set_peers(x, bases);
+}
+
+extern "C" int ldiff_xchg_connect_local(void* handle, void* const* peer_handles) {
+  if (!handle || !peer_handles) return LDIFF_EINVAL;
+  Xchg* x = static_cast<Xchg*>(handle);
+  void* bases[kXMaxWorld];
+  for (int q = 0; q < x->world; ++q) {
+    if (!peer_handles[q]) return LDIFF_EINVAL;
+    bases[q] = static_cast<Xchg*>(peer_handles[q])->base;
+  }
+  return xchg_set_peers(x, bases);
+}
+
+extern "C" int ldiff_xchg_destroy(void* handle) {
+  if (!handle) return LDIFF_EINVAL;
+  Xchg* x = static_cast<Xchg*>(handle);
+  cudaDeviceSynchronize();
+  for (int q = 0; q < kXMaxWorld; ++q)
+    if (x->mapped[q]) cudaIpcCloseMemHandle(x->mapped[q]);
+  cudaFree(x->base);
+  cudaGetLastError();
+  delete x;
+  return LDIFF_OK;
+}
+
+extern "C" int ldiff_confusion_hist_push(const uint8_t* pred, const uint8_t* gt, const uint8_t* gt_lut,
+                                         int64_t* C, int64_t n, int K, void* xchg, int channel,
+                                         int* status, void* stream) {
+  if (!pred || !gt || !C || !status || !xchg || n < 1 || K < 1) return LDIFF_EINVAL;
+  if (K > 128) return LDIFF_EUNSUPPORTED;
+  Xchg* x = static_cast<Xchg*>(xchg);
+  if (channel < 0 || channel >= x->channels || x->n != (K + 1) * K) return LDIFF_EINVAL;
+  if (!x->peers[x->rank]) return LDIFF_EINVAL;       // not connected yet
+  XchgPush px{reinterpret_cast<XchgHeader*>(x->base), x->world, x->rank, x->channels, channel, x->n, {0}};
+  for (int q = 0; q < x->world; ++q) px.peers[q] = x->peers[q];
+  return launch_confusion(pred, gt, gt_lut, C, n, 1, K, status, (cudaStream_t)stream, px);
+}
+
+extern "C" int ldiff_xchg_reduce(void* xchg, int64_t* out, int* status, void* stream) {
+  if (!xchg || !out || !status) return LDIFF_EINVAL;
+  Xchg* x = static_cast<Xchg*>(xchg);
+  static const unsigned long long timeout_ns = [] {
+    const char* e = getenv("LDIFF_XCHG_TIMEOUT_MS");
+    return (unsigned long long)(e && atoll(e) > 0 ? atoll(e) : 2000) * 1000000ull;
+  }();
+  xchg_reduce_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<XchgHeader*>(x->base),
+                                                          reinterpret_cast<unsigned long long*>(out), x->world,
+                                                          x->channels, x->n, timeout_ns, status);
+  return check_launch();
 }
 
 extern "C" int ldiff_labels_to_u8(const int64_t* in, uint8_t* out, int64_t n, void* stream) {

@@ -76,6 +76,99 @@ def gather_tile_confusions(local: torch.Tensor, n_tiles: int) -> torch.Tensor:
     return out
 
 
+class ConfusionExchange:
+    """The histogram's all-reduce without a collective library: every rank owns a small window in
+    device memory that all peers map through CUDA IPC; ``hist_push`` is the confusion histogram
+    whose last block stores the finished matrix into every rank's window over NVLink, ``reduce``
+    is a one-block kernel that waits for the W rows and adds them (``include/ldiff.h``, "a-6
+    across GPUs").  Integer sums, so the result equals ``allreduce_confusion`` bit for bit.
+
+    ``channels`` independent matrices travel per step (the pass has two: tissue and cell).  Every
+    rank pushes every channel once per step and reduces once per step; the j-th ``reduce`` returns
+    the sum of the j-th pushes, whether it is enqueued right behind them or a step later next to
+    the following step's work (at most two steps may be outstanding).  Both kernels can be captured
+    into CUDA graphs.
+
+    Replaces nnU-Net's pickled ``all_gather_object`` of tp/fp/fn (``nnUNetTrainer.py:1004-1012``).
+    """
+
+    def __init__(self, num_classes: int, channels: int = 1, device=None, _local_group=None):
+        import ctypes
+        from . import _cabi
+        self.K, self.channels = int(num_classes), int(channels)
+        self.n = (self.K + 1) * self.K
+        self._lib, self._ct = _cabi.lib(), ctypes
+        if _local_group is not None:                       # (rank, world): same-process windows, see connect_local
+            self.rank, self.world = _local_group
+        else:
+            self.rank, self.world = world()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            self._check(self._lib.ldiff_xchg_create(self.world, self.rank, self.channels, self.n, ctypes.byref(h)))
+        self._h = h
+        if _local_group is None:
+            self._connect_ipc()
+
+    def _check(self, rc):
+        from . import ops
+        ops.check(rc)
+
+    def _connect_ipc(self):
+        ct = self._ct
+        mine = ct.create_string_buffer(64)
+        self._check(self._lib.ldiff_xchg_ipc_handle(self._h, mine))
+        if self.world > 1:
+            gathered = [None] * self.world
+            dist.all_gather_object(gathered, bytes(mine.raw))    # every window is zeroed before its handle exists
+        else:
+            gathered = [bytes(mine.raw)]
+        blob = ct.create_string_buffer(b"".join(gathered), 64 * self.world)
+        with torch.cuda.device(self.device):
+            self._check(self._lib.ldiff_xchg_connect_ipc(self._h, blob))
+        if self.world > 1:
+            dist.barrier()                                       # nobody pushes into a window that is not mapped yet
+
+    @staticmethod
+    def connect_local(group):
+        """Wire several same-process windows to each other (several "ranks" on one GPU: tests)."""
+        import ctypes
+        arr = (ctypes.c_void_p * len(group))(*[g._h for g in group])
+        for g in group:
+            g._check(g._lib.ldiff_xchg_connect_local(g._h, arr))
+
+    def hist_push(self, pred: torch.Tensor, gt: torch.Tensor, C: torch.Tensor, channel: int = 0, gt_lut=None):
+        """``ops.confusion_hist(pred, gt, K, out=C)`` + push of the finished C to every rank."""
+        from . import ops
+        if C.dtype != torch.int64 or C.numel() != self.n or not C.is_contiguous():
+            raise ValueError("C must be a contiguous int64 [(K+1), K] matrix")
+        if pred.dtype != torch.uint8 or gt.dtype != torch.uint8 or pred.numel() != gt.numel():
+            raise ValueError("pred and gt must be uint8 maps of the same size")
+        ops._cuda(pred, gt, C)
+        self._check(self._lib.ldiff_confusion_hist_push(
+            pred.data_ptr(), gt.data_ptr(), None if gt_lut is None else gt_lut.data_ptr(), C.data_ptr(),
+            pred.numel(), self.K, self._h, int(channel), ops.status_word(pred.device).data_ptr(),
+            torch.cuda.current_stream(pred.device).cuda_stream))
+        return C
+
+    def reduce(self, out: torch.Tensor = None) -> torch.Tensor:
+        """Sum over ranks of the next not-yet-reduced step's matrices: int64 [channels, K+1, K]."""
+        from . import ops
+        if out is None:
+            out = torch.empty(self.channels, self.K + 1, self.K, dtype=torch.int64, device=self.device)
+        if out.dtype != torch.int64 or out.numel() != self.channels * self.n or not out.is_contiguous():
+            raise ValueError("out must be a contiguous int64 [channels, K+1, K] tensor")
+        self._check(self._lib.ldiff_xchg_reduce(self._h, out.data_ptr(), ops.status_word(out.device).data_ptr(),
+                                                torch.cuda.current_stream(out.device).cuda_stream))
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            torch.cuda.synchronize(self.device)
+            self._lib.ldiff_xchg_destroy(self._h)
+            self._h = None
+
+
 def bind_to_gpu_numa(device_index: int) -> str:
     """Pin this process (and therefore its first-touch pinned host buffers) to the CPUs local to
     its GPU's PCIe root.  With one process per GPU every rank streams ~0.3 GB per step over its

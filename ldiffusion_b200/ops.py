@@ -72,6 +72,8 @@ def check_status(device):
             raise RuntimeError("Encountered inf in predicted array. Aborting... If this problem persists, "
                                "reduce value_scaling_factor in compute_gaussian or increase the dtype of "
                                "predicted_logits to fp32")
+        if bits & _cabi.STATUS_XCHG_TIMEOUT:
+            raise RuntimeError("ldiff: a rank did not deliver its confusion matrix within 2 s (peer exchange)")
 
 
 # ---------------------------------------------------------------------------

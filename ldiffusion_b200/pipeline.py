@@ -81,10 +81,36 @@ class HotPath:
         self.cell_w = (torch.randn(num_classes, head_channels, generator=g) / 16).to(dev, dtype)
         self.cell_b = torch.zeros(num_classes, device=dev)
         self.status = ops.status_word(dev)
+        self.exchange = None                                               # set by attach_exchange (multi-GPU)
+
+    def attach_exchange(self, exchange, deferred: bool = True):
+        """Multi-GPU: fuse the cross-rank sum of the two confusion matrices into the pass
+        (``dist.ConfusionExchange``, 2 channels).  The histogram kernels push their finished
+        matrices into every rank's window over NVLink; the one-block reduce into ``self.C_global``
+        runs either at the end of the same pass, or (``deferred``) inside the FOLLOWING pass behind
+        its short sampler chain, where it never waits for a slower rank and is off the critical path —
+        ``C_global`` then holds the previous pass's sum until ``flush_exchange()``."""
+        if exchange.channels != 2 or exchange.K != self.K:
+            raise ValueError("the pass exchanges two (K+1) x K matrices")
+        self.exchange, self.exchange_deferred, self._unreduced = exchange, bool(deferred), 0
+        self.C_global = torch.zeros_like(self.C)
+
+    def flush_exchange(self):
+        """Reduce the passes whose matrices were pushed but not summed yet (deferred mode)."""
+        while self.exchange is not None and self._unreduced > 0:
+            self.exchange.reduce(out=self.C_global)
+            self._unreduced -= 1
+        return self.C_global
 
     # number of ldiff kernels one pass launches
     def launches_per_pass(self) -> int:
-        return 4 * self.n + 1 + 3 + 2 + 2 + 2
+        return 4 * self.n + 1 + 3 + 2 + 2 + 2 + (1 if self.exchange is not None else 0)   # steady state
+
+    def _confusion(self, mask, gt, channel):
+        if self.exchange is None:
+            ops.confusion_hist(mask.view(-1), gt.view(-1), self.K, out=self.C[channel])
+        else:
+            self.exchange.hist_push(mask.view(-1), gt.view(-1), self.C[channel], channel=channel)
 
     def run(self, inp: HotPathInputs, concurrent: bool = True):
         """Enqueue one pass; returns nothing (results live in the preallocated buffers).
@@ -106,6 +132,11 @@ class HotPath:
             side = [cur] * 4
         with torch.cuda.stream(side[0]):
             self._chain_sampler(inp)
+            if self.exchange is not None and self.exchange_deferred and self._unreduced > 0:
+                # the previous pass's sum rides at the end of the short sampler chain: off the critical
+                # path, no extra branch in the graph, and long after every rank has pushed
+                self.exchange.reduce(out=self.C_global)
+                self._unreduced -= 1
         with torch.cuda.stream(side[1]):
             self._chain_lifts(inp)
         with torch.cuda.stream(side[2]):
@@ -121,6 +152,10 @@ class HotPath:
         if concurrent:
             for s in side:
                 cur.wait_stream(s)
+        if self.exchange is not None:
+            self._unreduced += 1
+            if not self.exchange_deferred:
+                self.flush_exchange()
 
     def _side_streams(self):
         st = getattr(self, "_side", None)
@@ -154,12 +189,12 @@ class HotPath:
     def _chain_tissue(self, inp):
         ops._head_logits(inp.head_feat, self.head_w, self.head_b, self.logits)
         ops._lift_argmax(self.logits, self.mask_tissue)
-        ops.confusion_hist(self.mask_tissue.view(-1), inp.gt.view(-1), self.K, out=self.C[0])
+        self._confusion(self.mask_tissue, inp.gt, 0)
 
     def _chain_cell(self, inp):
         ops._cell_classify(inp.inst_feats, self.cell_w, self.cell_b, self.inst_ids, self.lut, None, self.status)
         ops.lut_paint(inp.inst_map, self.lut, out=self.mask_cell)
-        ops.confusion_hist(self.mask_cell.view(-1), inp.gt.view(-1), self.K, out=self.C[1])
+        self._confusion(self.mask_cell, inp.gt, 1)
 
     # ------------------------------------------------------------------
     # host-facing API: pinned host batches in, pinned host results out
