@@ -175,3 +175,28 @@ def test_pass_with_fused_exchange_matches_plain_pass(deferred, world):
     ops.check_status("cuda")
     for x in g:
         x.close()
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_tiling_config_through_the_exchange(world):
+    """configs[3]: 64 tiles, tile i -> rank i mod W; the matrix every rank reads from the
+    fused exchange equals the single-pass matrix and the oracle's, bit for bit."""
+    from ldiffusion_b200 import ops
+    from ldiffusion_b200.dist import shard_tiles
+    K, T, S = 11, 64, 128
+    rng = np.random.default_rng(0)
+    preds = rng.integers(0, K, (T, S, S)).astype(np.uint8)
+    gts = rng.integers(0, K + 1, (T, S, S)).astype(np.uint8)
+    gts[gts == K] = 255
+    pd, gd = torch.from_numpy(preds).cuda(), torch.from_numpy(gts).cuda()
+    want = om.confusion_matrix(preds, gts, K)
+    g = _group(world, K, 1)
+    C = torch.zeros(world, K + 1, K, dtype=torch.int64, device="cuda")
+    for r in range(world):
+        idx = shard_tiles(T, r, world)
+        g[r].hist_push(pd[idx].contiguous().view(-1), gd[idx].contiguous().view(-1), C[r])
+    for r in range(world):
+        np.testing.assert_array_equal(g[r].reduce()[0].cpu().numpy(), want)
+    ops.check_status("cuda")
+    for x in g:
+        x.close()
