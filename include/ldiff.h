@@ -45,7 +45,7 @@ enum {
 
 /* bits ORed into *status by kernels */
 enum { LDIFF_STATUS_PRED_RANGE = 1, LDIFF_STATUS_INST_RANGE = 2, LDIFF_STATUS_SW_INF = 4,
-       LDIFF_STATUS_XCHG_TIMEOUT = 8 };
+       LDIFF_STATUS_XCHG_TIMEOUT = 8, LDIFF_STATUS_LABEL_RANGE = 16 };
 
 int ldiff_abi_version(void);
 const char* ldiff_strerror(int code);
@@ -232,6 +232,17 @@ int ldiff_infonce_forward(const float* feat, const int* pair_batch, const int* p
                           const int* pair_pos, const int* pair_neg, float* loss_per_pair,
                           float* lse_per_pair, int C, int64_t hw, int n_neg, int n_pairs,
                           float temperature, void* stream);
+/* The sampling of loss.py:64-87 on the device: labels uint8 [B,hw] (values < 32, hw <= 16384).  Per
+ * image and per class (ascending) with more than one pixel and more than n_neg pixels outside it:
+ * max(1, count/100) anchors = a keyed random permutation's prefix over the class, the positive =
+ * a uniform draw among the class's other pixels, n_neg distinct negatives = a keyed random
+ * permutation's prefix over the pixels outside the class.  Image b owns pair slots
+ * [b*cap, (b+1)*cap) (cap >= hw/100 + 32 holds every case); unused slots get pair_batch = -1, which
+ * forward/backward skip (loss 0).  n_valid[b] = triples of image b.  Deterministic in (seed, offset).
+ * A label >= 32 sets LDIFF_STATUS_LABEL_RANGE. */
+int ldiff_infonce_sample(const uint8_t* labels, int B, int64_t hw, int n_neg, int cap, uint64_t seed,
+                         uint64_t offset, int* pair_batch, int* pair_anchor, int* pair_pos, int* pair_neg,
+                         int* n_valid, int* status, void* stream);
 /* backward: grad_feat (fp32 [B,C,hw], caller-zeroed) += d(sum_p loss_p)/d(feat) * (*grad_scale);
  * grad_scale is a DEVICE scalar (upstream gradient / n_pairs). */
 int ldiff_infonce_backward(const float* feat, const int* pair_batch, const int* pair_anchor,

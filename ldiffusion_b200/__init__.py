@@ -21,7 +21,7 @@ from .head import TissueHead, cell_mask, tissue_mask  # noqa: F401
 from .metrics import (confusion_matrix, evaluate, frequency_weighted_iou, mean_iou_and_per_class,  # noqa: F401
                       micro_dice, pixel_accuracy)
 from .ldiffusion import LDiffusionModel  # noqa: F401
-from .loss import pixel_contrastive_loss, sample_contrastive_pairs  # noqa: F401
+from .loss import pixel_contrastive_loss, sample_contrastive_pairs, sample_contrastive_pairs_device  # noqa: F401
 from .scheduler import LaplacePLMSScheduler  # noqa: F401
 from .segmentor import Segmentor  # noqa: F401
 

@@ -72,6 +72,8 @@ def check_status(device):
             raise RuntimeError("Encountered inf in predicted array. Aborting... If this problem persists, "
                                "reduce value_scaling_factor in compute_gaussian or increase the dtype of "
                                "predicted_logits to fp32")
+        if bits & _cabi.STATUS_LABEL_RANGE:
+            raise RuntimeError("ldiff: label value >= 32 in the contrastive sampler")
         if bits & _cabi.STATUS_XCHG_TIMEOUT:
             raise RuntimeError("ldiff: a rank did not deliver its confusion matrix within 2 s (peer exchange)")
 
@@ -235,6 +237,15 @@ def _sw_finalize_argmax(acc: Tensor, npred: Tensor, seg: Tensor, logits_out: Opt
                                                npred.numel(), _ptr(status), _stream(acc)))
 
 
+def _infonce_sample(labels: Tensor, n_neg: int, cap: int, seed: int, offset: int, pb: Tensor, pa: Tensor, pq: Tensor,
+                    neg: Tensor, n_valid: Tensor, status: Tensor) -> None:
+    _cuda(labels, pb, pa, pq, neg, n_valid, status)
+    B = labels.shape[0]
+    check(_cabi.lib().ldiff_infonce_sample(_ptr(labels), B, labels[0].numel(), n_neg, cap, seed & (2 ** 64 - 1),
+                                           offset & (2 ** 64 - 1), _ptr(pb), _ptr(pa), _ptr(pq), _ptr(neg),
+                                           _ptr(n_valid), _ptr(status), _stream(labels)))
+
+
 def _infonce_forward(feat: Tensor, pb: Tensor, pa: Tensor, pq: Tensor, neg: Tensor, loss: Tensor, lse: Tensor,
                      temperature: float) -> None:
     _cuda(feat, pb, pa, pq, neg, loss, lse)
@@ -253,6 +264,7 @@ def _infonce_backward(feat: Tensor, pb: Tensor, pa: Tensor, pq: Tensor, neg: Ten
                                              pa.numel(), temperature, _stream(feat)))
 
 
+torch.library.custom_op("ldiff::infonce_sample", mutates_args=("pb", "pa", "pq", "neg", "n_valid", "status"))(_infonce_sample)
 torch.library.custom_op("ldiff::infonce_forward", mutates_args=("loss", "lse"))(_infonce_forward)
 torch.library.custom_op("ldiff::infonce_backward", mutates_args=("grad",))(_infonce_backward)
 torch.library.custom_op("ldiff::sw_accumulate", mutates_args=("acc", "npred"))(_sw_accumulate)
