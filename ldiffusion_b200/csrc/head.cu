@@ -580,9 +580,16 @@ extern "C" int ldiff_lift_argmax(const float* logits, uint8_t* mask, int B, int 
     if (K > 12 || (W % 2) != 0) variant = variant == 0 ? 1 : variant;
     const int cols = variant == 0 ? 2 : 1;
     dim3 grid((W / cols + 255) / 256, h, B);
+    // experiment knob: unused dynamic shared memory that caps how many of these register-heavy CTAs
+    // are resident per SM, leaving register file for the bandwidth-bound kernels they run beside
+    static const int pad = [] { const char* e = getenv("LDIFF_ARGMAX_SMEM_PAD"); return e ? atoi(e) : 0; }();
     switch (K) {
 #define LA2(KK) case KK:                                                                               \
-      if (variant == 0) lift_argmax_kernel<KK, 2, 2><<<grid, 256, 0, st>>>(logits, mask, ay, ax);       \
+      if (variant == 0) {                                                                              \
+        if (pad > 48 * 1024)                                                                           \
+          cudaFuncSetAttribute(lift_argmax_kernel<KK, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad); \
+        lift_argmax_kernel<KK, 2, 2><<<grid, 256, pad, st>>>(logits, mask, ay, ax);                    \
+      }                                                                                                \
       else if (variant == 1) lift_argmax_kernel<KK, 1, 3><<<grid, 256, 0, st>>>(logits, mask, ay, ax);  \
       else if (variant == 3) lift_argmax_kernel<KK, 1, 2><<<grid, 256, 0, st>>>(logits, mask, ay, ax);  \
       else lift_argmax_kernel<KK, 1, 4><<<grid, 256, 0, st>>>(logits, mask, ay, ax);                    \
