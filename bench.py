@@ -55,7 +55,8 @@ AR_NOTE = {"peer": "histogram kernel pushes into NVLink peer windows + one-block
 def config(n_gpus):
     return {"workload": WORKLOAD, "batch_per_gpu": B, "patch": [H, W], "classes": K, "sampling_steps": NSTEPS,
             "instances_per_patch": NINST, "storage": "bf16", "arithmetic": "fp32",
-            "parallelism": f"patch-sharded x{n_gpus} (no data-path collective; the two int64 confusion matrices are "
+            "parallelism": "single GPU" if n_gpus == 1 else
+                           f"patch-sharded x{n_gpus} (no data-path collective; the two int64 confusion matrices are "
                            f"summed across ranks every step: {AR_NOTE.get(os.environ.get('LDIFF_ALLREDUCE', 'peer'), '')})",
             "l2": "two rotating input sets of 0.35 GB each (> 126 MB L2)",
             "backbone": "SD-v1.5 UNet/VAE outputs are synthetic resident tensors (cuDNN calls, out of scope)"}

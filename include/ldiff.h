@@ -237,7 +237,7 @@ int ldiff_infonce_forward(const float* feat, const int* pair_batch, const int* p
  * max(1, count/100) anchors = a keyed random permutation's prefix over the class, the positive =
  * a uniform draw among the class's other pixels, n_neg distinct negatives = a keyed random
  * permutation's prefix over the pixels outside the class.  Image b owns pair slots
- * [b*cap, (b+1)*cap) (cap >= hw/100 + 32 holds every case); unused slots get pair_batch = -1, which
+ * [b*cap, (b+1)*cap) (cap >= hw/100 + 32 holds every case); unused slots are filled with -1, which
  * forward/backward skip (loss 0).  n_valid[b] = triples of image b.  Deterministic in (seed, offset).
  * A label >= 32 sets LDIFF_STATUS_LABEL_RANGE. */
 int ldiff_infonce_sample(const uint8_t* labels, int B, int64_t hw, int n_neg, int cap, uint64_t seed,

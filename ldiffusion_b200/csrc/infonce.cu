@@ -184,8 +184,9 @@ infonce_sample_kernel(const uint8_t* __restrict__ labels, int hw, int n_neg, int
   const int total = s_aoff[kNceLabels];
   for (int pair = wid; pair < cap; pair += 8) {      // one warp per triple
     const int o = b * cap + pair;
-    if (pair >= total) {
-      if (lane == 0) pb[o] = -1;
+    if (pair >= total) {                             // unused slot: fully defined, skipped downstream
+      if (lane == 0) { pb[o] = -1; pa[o] = -1; pq[o] = -1; }
+      for (int j = lane; j < n_neg; j += 32) neg[(int64_t)o * n_neg + j] = -1;
       continue;
     }
     int l = 0;
