@@ -189,12 +189,14 @@ int ldiff_confusion_hist_batched(const uint8_t* pred, const uint8_t* gt, const u
  * or a whole step later, concurrently with the next step's work (it then never waits).  Rows
  * live in a ring of 4 slots: push j of a rank must be stream-ordered after that rank's reduce
  * j-2 (at most two steps outstanding).  Integer sums: bit-exact at any world size.  A rank that
- * never arrives trips a 2 s device-side timeout (LDIFF_STATUS_XCHG_TIMEOUT), not a hang.
+ * never arrives trips a device-side timeout (10 s, ldiff_xchg_set_timeout) that sets
+ * LDIFF_STATUS_XCHG_TIMEOUT, not a hang; while that bit is set later reduces do not wait again.
  * Both kernels are plain launches and can be captured into CUDA graphs. */
 int ldiff_xchg_create(int world, int rank, int channels, int n_i64, void** handle);
 int ldiff_xchg_ipc_handle(void* handle, void* out64);
 int ldiff_xchg_connect_ipc(void* handle, const void* handles);
 int ldiff_xchg_connect_local(void* handle, void* const* peer_handles);
+int ldiff_xchg_set_timeout(void* handle, int64_t timeout_ms);
 int ldiff_xchg_destroy(void* handle);
 int ldiff_confusion_hist_push(const uint8_t* pred, const uint8_t* gt, const uint8_t* gt_lut,
                               int64_t* C, int64_t n, int K, void* xchg, int channel, int* status,

@@ -50,6 +50,7 @@ SIGNATURES = {
     "ldiff_xchg_ipc_handle": (c_int, [c_void_p, c_void_p]),
     "ldiff_xchg_connect_ipc": (c_int, [c_void_p, c_void_p]),
     "ldiff_xchg_connect_local": (c_int, [c_void_p, c_void_p]),
+    "ldiff_xchg_set_timeout": (c_int, [c_void_p, c_int64]),
     "ldiff_xchg_destroy": (c_int, [c_void_p]),
     "ldiff_confusion_hist_push": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int,
                                           c_void_p, c_void_p]),

@@ -196,8 +196,8 @@ confusion_hist_push_kernel(const uint8_t* __restrict__ pred, const uint8_t* __re
 
 // One block per rank.  The j-th reduce of a rank adds the rows of every rank's j-th push: each thread
 // owns a few (channel, bin) counters and, per source rank, spins until both words of the counter carry
-// the step's tag.  A peer that never arrives (crashed rank) trips a timeout (2 s;
-// LDIFF_XCHG_TIMEOUT_MS) that sets LDIFF_STATUS_XCHG_TIMEOUT instead of hanging the GPU.
+// the step's tag.  A peer that never arrives (crashed rank) trips a timeout (10 s by default,
+// ldiff_xchg_set_timeout) that sets LDIFF_STATUS_XCHG_TIMEOUT instead of hanging the GPU.
 __global__ void __launch_bounds__(256)
 xchg_reduce_kernel(XchgHeader* __restrict__ win, unsigned long long* __restrict__ out, int world,
                    int channels, int n, unsigned long long timeout_ns, int* __restrict__ status) {
@@ -205,7 +205,8 @@ xchg_reduce_kernel(XchgHeader* __restrict__ win, unsigned long long* __restrict_
   const unsigned long long tag = want & 0xffffffffull;
   const int slot = (int)(want % kXSlots);
   const unsigned long long t0 = globaltimer_ns();
-  bool late = false;
+  // a timeout that is already on record (crashed peer) is not waited for again: one timeout per failure
+  bool late = (*reinterpret_cast<volatile int*>(status) & LDIFF_STATUS_XCHG_TIMEOUT) != 0;
   for (int i = threadIdx.x; i < channels * n; i += blockDim.x) {
     const int ch = i / n, bin = i - ch * n;
     unsigned long long s = 0;
@@ -330,6 +331,7 @@ struct Xchg {
   char* base;                          // this rank's window (cudaMalloc: IPC-exportable)
   void* mapped[kXMaxWorld];            // peers opened through CUDA IPC (closed in destroy)
   unsigned long long peers[kXMaxWorld];  // window base of every rank as mapped in this process
+  unsigned long long timeout_ns;       // how long a reduce waits for a missing rank
 };
 }  // namespace
 
@@ -339,6 +341,7 @@ extern "C" int ldiff_xchg_create(int world, int rank, int channels, int n_i64, v
     return LDIFF_EINVAL;
   Xchg* x = new Xchg();
   x->world = world; x->rank = rank; x->channels = channels; x->n = n_i64;
+  x->timeout_ns = 10000000000ull;
   x->bytes = kXHeaderBytes + (size_t)kXSlots * world * channels * n_i64 * 2 * sizeof(int64_t);
   for (int i = 0; i < kXMaxWorld; ++i) { x->mapped[i] = nullptr; x->peers[i] = 0; }
   if (cudaMalloc(&x->base, x->bytes) != cudaSuccess || cudaMemset(x->base, 0, x->bytes) != cudaSuccess ||
@@ -397,6 +400,12 @@ extern "C" int ldiff_xchg_connect_local(void* handle, void* const* peer_handles)
   return xchg_set_peers(x, bases);
 }
 
+extern "C" int ldiff_xchg_set_timeout(void* handle, int64_t timeout_ms) {
+  if (!handle || timeout_ms < 1) return LDIFF_EINVAL;
+  static_cast<Xchg*>(handle)->timeout_ns = (unsigned long long)timeout_ms * 1000000ull;
+  return LDIFF_OK;
+}
+
 extern "C" int ldiff_xchg_destroy(void* handle) {
   if (!handle) return LDIFF_EINVAL;
   Xchg* x = static_cast<Xchg*>(handle);
@@ -425,13 +434,9 @@ extern "C" int ldiff_confusion_hist_push(const uint8_t* pred, const uint8_t* gt,
 extern "C" int ldiff_xchg_reduce(void* xchg, int64_t* out, int* status, void* stream) {
   if (!xchg || !out || !status) return LDIFF_EINVAL;
   Xchg* x = static_cast<Xchg*>(xchg);
-  static const unsigned long long timeout_ns = [] {
-    const char* e = getenv("LDIFF_XCHG_TIMEOUT_MS");
-    return (unsigned long long)(e && atoll(e) > 0 ? atoll(e) : 2000) * 1000000ull;
-  }();
   xchg_reduce_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<XchgHeader*>(x->base),
                                                           reinterpret_cast<unsigned long long*>(out), x->world,
-                                                          x->channels, x->n, timeout_ns, status);
+                                                          x->channels, x->n, x->timeout_ns, status);
   return check_launch();
 }
 

@@ -3,9 +3,9 @@
 // Reference: model/loss.py:44-109 (InfoNceLoss.compute_contrastive_loss).  For every sampled
 // (anchor, positive, N negatives) triple the reference builds logits = [a.p, a.n_1 .. a.n_N] / T
 // with a 1 x C times C x (1+N) matmul and adds cross_entropy(logits, target=0); the result is the
-// mean over all triples.  That Python triple loop becomes one warp per triple: the anchor's C
+// mean over all triples.  That Python triple loop becomes one 128-thread block per triple: the anchor's C
 // (= number of sampling steps, <= 16) features sit in registers, the 1+N candidates are gathered
-// from the planar [C, h*w] feature map, a two-pass (max, sum-exp) log-softmax gives the loss, and
+// from the planar [C, h*w] feature map (logits stay in registers), a max / sum-exp log-softmax gives the loss, and
 // the backward kernel recomputes the probabilities and scatters the gradient with fp32 atomics
 // (candidate pixels repeat across triples).  Parity is with injected index sets; the sampling
 // procedure itself (loss.py:64-87: 1 % of each class as anchors, one other pixel of the class as
@@ -24,74 +24,113 @@ struct NceDims { int C; int64_t hw; int n_neg; int n_pairs; float inv_t; };
 __device__ __forceinline__ float nce_dot(const float* __restrict__ fb, const float (&a)[kMaxC], int C, int64_t hw,
                                          int idx) {
   float s = 0.f;
-  for (int c = 0; c < C; ++c) s = fmaf(a[c], __ldg(fb + (int64_t)c * hw + idx), s);
+#pragma unroll
+  for (int c = 0; c < kMaxC; ++c)                    // full unroll + uniform guard: a[] stays in registers
+    if (c < C) s = fmaf(a[c], __ldg(fb + (int64_t)c * hw + idx), s);
   return s;
 }
 
-__global__ void __launch_bounds__(256)
+constexpr int kNceThreads = 128;                     // one block per triple: 4 warps walk the 1+N candidates
+constexpr int kNceCache = 9;                         // logits kept in registers per thread (covers N <= 1151)
+
+__device__ __forceinline__ float nce_block_max(float v, float* s_red) {
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  v = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
+  __syncthreads();
+  return v;
+}
+__device__ __forceinline__ float nce_block_sum(float v, float* s_red) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  v = (s_red[0] + s_red[1]) + (s_red[2] + s_red[3]);
+  __syncthreads();
+  return v;
+}
+
+__global__ void __launch_bounds__(kNceThreads)
 infonce_forward_kernel(const float* __restrict__ feat, const int* __restrict__ pb, const int* __restrict__ pa,
                        const int* __restrict__ pq, const int* __restrict__ neg, float* __restrict__ loss,
                        float* __restrict__ lse, NceDims d) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= d.n_pairs) return;
-  if (pb[warp] < 0) {                                              // unused slot of a padded pair list
-    if (lane == 0) { loss[warp] = 0.f; lse[warp] = 0.f; }
+  __shared__ float s_red[4];
+  const int pair = blockIdx.x, tid = threadIdx.x;
+  if (pb[pair] < 0) {                                              // unused slot of a padded pair list
+    if (tid == 0) { loss[pair] = 0.f; lse[pair] = 0.f; }
     return;
   }
-  const float* fb = feat + (int64_t)pb[warp] * d.C * d.hw;
+  const float* fb = feat + (int64_t)pb[pair] * d.C * d.hw;
   float a[kMaxC];
-  for (int c = 0; c < d.C; ++c) a[c] = __ldg(fb + (int64_t)c * d.hw + pa[warp]);
-  const int* ng = neg + (int64_t)warp * d.n_neg;
+#pragma unroll
+  for (int c = 0; c < kMaxC; ++c) a[c] = c < d.C ? __ldg(fb + (int64_t)c * d.hw + pa[pair]) : 0.f;
+  const int* ng = neg + (int64_t)pair * d.n_neg;
   const int n = d.n_neg + 1;
+  auto logit = [&](int j) { return nce_dot(fb, a, d.C, d.hw, j == 0 ? pq[pair] : ng[j - 1]) * d.inv_t; };
+  float xs[kNceCache];
   float m = -INFINITY;
-  for (int j = lane; j < n; j += 32) {
-    const int idx = j == 0 ? pq[warp] : ng[j - 1];
-    m = fmaxf(m, nce_dot(fb, a, d.C, d.hw, idx) * d.inv_t);
+#pragma unroll
+  for (int i = 0; i < kNceCache; ++i) {
+    const int j = tid + i * kNceThreads;
+    xs[i] = j < n ? logit(j) : -INFINITY;
+    m = fmaxf(m, xs[i]);
   }
-  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  for (int j = tid + kNceCache * kNceThreads; j < n; j += kNceThreads) m = fmaxf(m, logit(j));
+  m = nce_block_max(m, s_red);
   float s = 0.f;
-  for (int j = lane; j < n; j += 32) {
-    const int idx = j == 0 ? pq[warp] : ng[j - 1];
-    s += expf(nce_dot(fb, a, d.C, d.hw, idx) * d.inv_t - m);
-  }
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (lane == 0) {
+#pragma unroll
+  for (int i = 0; i < kNceCache; ++i) s += expf(xs[i] - m);        // exp(-inf) = 0 for the padding
+  for (int j = tid + kNceCache * kNceThreads; j < n; j += kNceThreads) s += expf(logit(j) - m);
+  s = nce_block_sum(s, s_red);
+  if (tid == 0) {
     const float l = m + logf(s);                                   // logsumexp of the logits
-    lse[warp] = l;
-    loss[warp] = l - nce_dot(fb, a, d.C, d.hw, pq[warp]) * d.inv_t;  // cross_entropy(logits, 0)
+    lse[pair] = l;
+    loss[pair] = l - xs[0];                                        // cross_entropy(logits, 0)
   }
 }
 
 // grad_feat += d(mean loss)/d(feat) * gscale, gscale = upstream gradient / n_pairs
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kNceThreads)
 infonce_backward_kernel(const float* __restrict__ feat, const int* __restrict__ pb, const int* __restrict__ pa,
                         const int* __restrict__ pq, const int* __restrict__ neg, const float* __restrict__ lse,
                         const float* __restrict__ gscale, float* __restrict__ grad, NceDims d) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= d.n_pairs || pb[warp] < 0) return;
-  const int64_t boff = (int64_t)pb[warp] * d.C * d.hw;
+  __shared__ float s_ga[4][kMaxC];
+  const int pair = blockIdx.x, tid = threadIdx.x;
+  if (pb[pair] < 0) return;
+  const int64_t boff = (int64_t)pb[pair] * d.C * d.hw;
   const float* fb = feat + boff;
   float* gb = grad + boff;
   const float g = __ldg(gscale) * d.inv_t;
   float a[kMaxC], ga[kMaxC];
-  for (int c = 0; c < d.C; ++c) { a[c] = __ldg(fb + (int64_t)c * d.hw + pa[warp]); ga[c] = 0.f; }
-  const int* ng = neg + (int64_t)warp * d.n_neg;
+#pragma unroll
+  for (int c = 0; c < kMaxC; ++c) { a[c] = c < d.C ? __ldg(fb + (int64_t)c * d.hw + pa[pair]) : 0.f; ga[c] = 0.f; }
+  const int* ng = neg + (int64_t)pair * d.n_neg;
   const int n = d.n_neg + 1;
-  const float l = lse[warp];
-  for (int j = lane; j < n; j += 32) {
-    const int idx = j == 0 ? pq[warp] : ng[j - 1];
-    const float p = expf(nce_dot(fb, a, d.C, d.hw, idx) * d.inv_t - l) - (j == 0 ? 1.f : 0.f);   // softmax - onehot
-    const float w = p * g;
-    for (int c = 0; c < d.C; ++c) {
-      ga[c] = fmaf(w, __ldg(fb + (int64_t)c * d.hw + idx), ga[c]);
-      atomicAdd(gb + (int64_t)c * d.hw + idx, w * a[c]);
+  const float l = lse[pair];
+  for (int j = tid; j < n; j += kNceThreads) {
+    const int idx = j == 0 ? pq[pair] : ng[j - 1];
+    float f[kMaxC], dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < kMaxC; ++c) {                              // the candidate's features, loaded once
+      f[c] = c < d.C ? __ldg(fb + (int64_t)c * d.hw + idx) : 0.f;
+      dot = fmaf(a[c], f[c], dot);
+    }
+    const float w = (expf(dot * d.inv_t - l) - (j == 0 ? 1.f : 0.f)) * g;   // (softmax - onehot) * scale
+#pragma unroll
+    for (int c = 0; c < kMaxC; ++c) {
+      ga[c] = fmaf(w, f[c], ga[c]);
+      if (c < d.C) atomicAdd(gb + (int64_t)c * d.hw + idx, w * a[c]);
     }
   }
-  for (int c = 0; c < d.C; ++c) {
+#pragma unroll
+  for (int c = 0; c < kMaxC; ++c) {
     float v = ga[c];
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) atomicAdd(gb + (int64_t)c * d.hw + pa[warp], v);
+    if ((tid & 31) == 0) s_ga[tid >> 5][c] = v;
   }
+  __syncthreads();
+  if (tid < d.C)
+    atomicAdd(gb + (int64_t)tid * d.hw + pa[pair], (s_ga[0][tid] + s_ga[1][tid]) + (s_ga[2][tid] + s_ga[3][tid]));
 }
 
 // ---- on-device sampling of the (anchor, positive, negatives) triples --------------------------------
@@ -243,7 +282,7 @@ extern "C" int ldiff_infonce_forward(const float* feat, const int* pair_batch, c
   if (rc != LDIFF_OK || !loss_per_pair || !lse_per_pair) return rc != LDIFF_OK ? rc : LDIFF_EINVAL;
   if (n_pairs == 0) return LDIFF_OK;
   NceDims d{C, hw, n_neg, n_pairs, 1.f / temperature};
-  infonce_forward_kernel<<<(n_pairs * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+  infonce_forward_kernel<<<n_pairs, kNceThreads, 0, (cudaStream_t)stream>>>(
       feat, pair_batch, pair_anchor, pair_pos, pair_neg, loss_per_pair, lse_per_pair, d);
   return check_launch();
 }
@@ -256,7 +295,7 @@ extern "C" int ldiff_infonce_backward(const float* feat, const int* pair_batch, 
   if (rc != LDIFF_OK || !lse_per_pair || !grad_scale || !grad_feat) return rc != LDIFF_OK ? rc : LDIFF_EINVAL;
   if (n_pairs == 0) return LDIFF_OK;
   NceDims d{C, hw, n_neg, n_pairs, 1.f / temperature};
-  infonce_backward_kernel<<<(n_pairs * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+  infonce_backward_kernel<<<n_pairs, kNceThreads, 0, (cudaStream_t)stream>>>(
       feat, pair_batch, pair_anchor, pair_pos, pair_neg, lse_per_pair, grad_scale, grad_feat, d);
   return check_launch();
 }

@@ -92,7 +92,7 @@ class ConfusionExchange:
     Replaces nnU-Net's pickled ``all_gather_object`` of tp/fp/fn (``nnUNetTrainer.py:1004-1012``).
     """
 
-    def __init__(self, num_classes: int, channels: int = 1, device=None, _local_group=None):
+    def __init__(self, num_classes: int, channels: int = 1, device=None, timeout_ms: int = 10000, _local_group=None):
         import ctypes
         from . import _cabi
         self.K, self.channels = int(num_classes), int(channels)
@@ -107,6 +107,7 @@ class ConfusionExchange:
         with torch.cuda.device(self.device):
             self._check(self._lib.ldiff_xchg_create(self.world, self.rank, self.channels, self.n, ctypes.byref(h)))
         self._h = h
+        self._check(self._lib.ldiff_xchg_set_timeout(h, int(timeout_ms)))
         if _local_group is None:
             self._connect_ipc()
 

@@ -75,7 +75,7 @@ def check_status(device):
         if bits & _cabi.STATUS_LABEL_RANGE:
             raise RuntimeError("ldiff: label value >= 32 in the contrastive sampler")
         if bits & _cabi.STATUS_XCHG_TIMEOUT:
-            raise RuntimeError("ldiff: a rank did not deliver its confusion matrix within 2 s (peer exchange)")
+            raise RuntimeError("ldiff: a rank did not deliver its confusion matrix in time (peer exchange)")
 
 
 # ---------------------------------------------------------------------------

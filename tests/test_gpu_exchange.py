@@ -18,9 +18,9 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _group(world, K, channels):
+def _group(world, K, channels, timeout_ms=10000):
     from ldiffusion_b200.dist import ConfusionExchange
-    g = [ConfusionExchange(K, channels, _local_group=(r, world)) for r in range(world)]
+    g = [ConfusionExchange(K, channels, timeout_ms=timeout_ms, _local_group=(r, world)) for r in range(world)]
     ConfusionExchange.connect_local(g)
     return g
 
@@ -89,13 +89,23 @@ def test_push_reduce_in_cuda_graph():
 
 def test_missing_rank_times_out_instead_of_hanging():
     from ldiffusion_b200 import ops
+    import time
     K = 5
-    g = _group(2, K, 1)
+    g = _group(2, K, 1, timeout_ms=500)
     p = torch.zeros(4096, dtype=torch.uint8, device="cuda")
-    g[0].hist_push(p, p, torch.zeros(K + 1, K, dtype=torch.int64, device="cuda"))
+    C = torch.zeros(K + 1, K, dtype=torch.int64, device="cuda")
+    g[0].hist_push(p, p, C)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
     got = g[0].reduce()                                      # rank 1 never pushed
     torch.cuda.synchronize()
+    assert 0.4 < time.perf_counter() - t0 < 3.0
     assert int(got[0, 0, 0]) == 4096                         # own row only
+    g[0].hist_push(p, p, C)
+    t0 = time.perf_counter()
+    g[0].reduce()                                            # the timeout is on record: no second wait
+    torch.cuda.synchronize()
+    assert time.perf_counter() - t0 < 0.3
     with pytest.raises(RuntimeError, match="did not deliver"):
         ops.check_status("cuda")
     for x in g:

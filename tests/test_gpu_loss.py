@@ -39,7 +39,8 @@ def test_infonce_forward_backward_match_reference_loop(n, N, T):
     # upstream gradient scaling
     f2 = feats.cuda().requires_grad_(True)
     (3.0 * pixel_contrastive_loss(f2, labels, temperature=T, num_negatives=N, pairs=pairs)).backward()
-    torch.testing.assert_close(f2.grad, 3.0 * f_dev.grad, rtol=1e-5, atol=1e-8)
+    # two runs of the atomics-based backward: same sums in a different order
+    torch.testing.assert_close(f2.grad, 3.0 * f_dev.grad, rtol=1e-4, atol=3e-7)
 
 
 def test_infonce_sampling_follows_reference_rules():
