@@ -3,10 +3,12 @@ only thing exchanged.
 
 One process per GPU (torchrun).  Stages a-1..a-5 are per-patch with no
 cross-patch state, so tile ``i`` simply goes to rank ``i mod W`` and no data-path
-collective is needed.  Evaluation adds the integer matrices: one
-``all_reduce(SUM)`` of ``(K+1)*K`` int64 (1056 bytes for K=11, latency-bound,
-order-independent and therefore bit-exact at any world size), issued straight on
-the buffer the histogram kernel accumulated into.  Per-image metrics (the
+collective is needed.  Evaluation adds the integer matrices ((K+1)*K int64, 1056
+bytes for K=11; order-independent and therefore bit-exact at any world size):
+either ``ConfusionExchange`` — the histogram kernel itself stores its matrix into
+every rank's NVLink-mapped window and a one-block kernel adds the rows — or one
+NCCL ``all_reduce(SUM)`` issued straight on the buffer the histogram kernel
+accumulated into (``allreduce_confusion``).  Per-image metrics (the
 reference averages per-image Dice, ``evaluate.py:95-102``) need the per-tile
 matrices: one ``all_gather`` of ``[tiles_per_rank, K+1, K]``.
 

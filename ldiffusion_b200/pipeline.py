@@ -50,6 +50,23 @@ class HotPathInputs:
         return sum(t.numel() * t.element_size() for t in self.tensors())
 
 
+class _nvtx:
+    """NVTX range around a chain when LDIFF_NVTX=1 (the reference has no tracing hooks at all,
+    SURVEY 5); lets ``ncu --nvtx --nvtx-include`` pick one chain of the pass."""
+    on = os.environ.get("LDIFF_NVTX", "0") == "1"
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if self.on:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if self.on:
+            torch.cuda.nvtx.range_pop()
+
+
 class HotPath:
     def __init__(self, batch: int, height: int, width: int, num_classes: int, num_steps: int = 5,
                  dtype=torch.bfloat16, device="cuda", head_hw=(32, 32), feat_size=(64, 64),
@@ -132,20 +149,20 @@ class HotPath:
                 s.wait_stream(cur)
         else:
             side = [cur] * 5
-        with torch.cuda.stream(side[0]):
+        with torch.cuda.stream(side[0]), _nvtx("ldiff.sampler"):
             self._chain_sampler(inp)
             if self.exchange is not None and self.exchange_deferred and self._unreduced > 0:
                 # the previous pass's sum rides at the end of the short sampler chain: off the critical
                 # path, no extra branch in the graph, and long after every rank has pushed
                 self.exchange.reduce(out=self.C_global)
                 self._unreduced -= 1
-        with torch.cuda.stream(side[1]):
+        with torch.cuda.stream(side[1]), _nvtx("ldiff.lifts"):
             self._chain_lifts(inp)
-        with torch.cuda.stream(side[2]):
+        with torch.cuda.stream(side[2]), _nvtx("ldiff.tissue"):
             self._chain_tissue(inp)
-        with torch.cuda.stream(side[3]):
+        with torch.cuda.stream(side[3]), _nvtx("ldiff.cell"):
             self._chain_cell(inp)
-        with torch.cuda.stream(side[4]):                                   # the bandwidth-heavy chain
+        with torch.cuda.stream(side[4]), _nvtx("ldiff.decode_tails"):      # the bandwidth-heavy chain
             for i in range(n):
                 last = i == n - 1
                 ops.decode_tail_gray(inp.decoded[i], want_rgb=False, rgb_out=self.rgb if last else None,
