@@ -66,6 +66,26 @@ int ldiff_laplace_qsample(const void* x, void* out, const void* noise_in, const 
                           void* noise_out, float b, uint64_t seed, uint64_t offset,
                           int64_t n, int dtype, void* stream);
 
+/* a-1, multimodal variant: Laplace(0,1) noise modulated by a per-pixel scale map, and its
+ * inverse.  Replaces segmentor.py:339,344-345
+ *     latents = vae.encode(rgb_i).latent_dist.sample() * 0.18215
+ *     noise = Laplace(0.0, 1.0).sample(latents.shape);  latents_noisy = latents + noise * depth_resized
+ * and segmentor.py:375,379
+ *     latents_denoised = latents_noisy - noise_pred * depth_resized;  vae.decode(latents_denoised / 0.18215)
+ *   ldiff_laplace_qsample_map : out = fl(x_mul * x) + fl(noise * s)      (x_mul = 1: exact, no scaling)
+ *   ldiff_scaled_residual     : out = fl(fl(x - fl(eps * s)) / out_div)  (out_div = 1: exact)
+ * x, eps, out, noise_*: [B, channels, plane] flattened to n elements.  scale: scale_channels ==
+ * channels -> same shape; scale_channels == 1 -> [B, 1, plane], broadcast over the channels (what
+ * depth_resized.repeat(1, C, 1, 1) materialises at segmentor.py:341).  Randomness as in
+ * ldiff_laplace_qsample (noise_in / u_in / Philox); noise_out receives the UNIT Laplace noise. */
+int ldiff_laplace_qsample_map(const void* x, const void* scale, void* out, const void* noise_in,
+                              const void* u_in, void* noise_out, float x_mul, uint64_t seed,
+                              uint64_t offset, int64_t n, int64_t plane, int channels,
+                              int scale_channels, int dtype, void* stream);
+int ldiff_scaled_residual(const void* x, const void* eps, const void* scale, void* out, float out_div,
+                          int64_t n, int64_t plane, int channels, int scale_channels, int dtype,
+                          void* stream);
+
 /* ---- a-2  PLMS reverse step ----------------------------------------------
  * replaces scheduler.step(...).prev_sample at segmentor.py:102-104, :443-445,
  * :525-527, utils.py:200-202, pixel_latent_vector.py:77-79, sample.py:62-64

@@ -22,6 +22,10 @@ SIGNATURES = {
     "ldiff_launch_count": (c_int64, []),
     "ldiff_laplace_qsample": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
                                       c_uint64, c_uint64, c_int64, c_int, c_void_p]),
+    "ldiff_laplace_qsample_map": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
+                                          c_uint64, c_uint64, c_int64, c_int64, c_int, c_int, c_int, c_void_p]),
+    "ldiff_scaled_residual": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int64, c_int64, c_int,
+                                      c_int, c_int, c_void_p]),
     "ldiff_plms_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float,
                                 c_float, c_float, c_void_p, c_int64, c_int, c_void_p]),
     "ldiff_decode_tail_gray": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64,

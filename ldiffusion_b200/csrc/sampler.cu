@@ -200,6 +200,142 @@ static int launch_plms(const void* x, const void* e0, const void* e1, const void
   return check_launch();
 }
 
+
+// ---------------------------------------------------------------------------
+// a-1 variant (segmentor.py:344-345 / :375): Laplace(0,1) noise modulated by a per-pixel
+// scale map, and its inverse.
+//   noising : out = fl(x_mul * x) + fl(noise * s)          noise ~ Laplace(0, 1)
+//   inverse : out = fl(fl(x - fl(eps * s)) / out_div)
+// The map is either element-for-element ([B,C,plane], span == 0) or one plane per image
+// broadcast over the C channels ([B,1,plane], span == C*plane: what the reference
+// materialises with .repeat(1, C, 1, 1)).  Vector path: 8 elements per thread; with a
+// broadcast map it needs plane % 8 == 0 so that a vector never straddles two planes.
+// Everything the vector path does not cover is done by a scalar grid-stride loop.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int64_t map_index(int64_t i, int64_t plane, int64_t span) {
+  return span == 0 ? i : (i / span) * plane + (i % plane);
+}
+
+template <typename T, int SRC, bool EMIT>
+__global__ void __launch_bounds__(256)
+laplace_qsample_map_kernel(const T* __restrict__ x, const T* __restrict__ scale, T* __restrict__ out,
+                           const T* __restrict__ inj, T* __restrict__ noise_out, float x_mul, uint2 key,
+                           uint64_t offset, int64_t n, int64_t plane, int64_t span, int64_t nvec) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int64_t v = tid; v < nvec; v += stride) {
+    const int64_t base = v << 3;
+    float xv[8], nz[8], sv[8];
+    Vec8<T>::load(x + base, xv);
+    Vec8<T>::load(scale + map_index(base, plane, span), sv);
+    if (SRC == SRC_PHILOX) {
+      const uint64_t c0 = offset + (uint64_t)(base >> 2);
+      const uint4 r0 = philox4x32_10(make_uint4((uint32_t)c0, (uint32_t)(c0 >> 32), 0u, 0u), key);
+      const uint64_t c1 = c0 + 1;
+      const uint4 r1 = philox4x32_10(make_uint4((uint32_t)c1, (uint32_t)(c1 >> 32), 0u, 0u), key);
+      const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) nz[i] = laplace_from_uniform_fast(uniform_pm1(w[i]), 1.f);
+    } else {
+      Vec8<T>::load(inj + base, nz);
+      if (SRC == SRC_UNIFORM) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) nz[i] = laplace_from_uniform(nz[i], 1.f);
+      }
+    }
+    if (EMIT) Vec8<T>::store(noise_out + base, nz);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) xv[i] = __fadd_rn(__fmul_rn(x_mul, xv[i]), __fmul_rn(nz[i], sv[i]));
+    Vec8<T>::store(out + base, xv);
+  }
+  for (int64_t t = (nvec << 3) + tid; t < n; t += stride) {
+    float nzs;
+    if (SRC == SRC_PHILOX) {
+      const uint64_t c = offset + (uint64_t)(t >> 2);
+      const uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0u, 0u), key);
+      const uint32_t w = (t & 2) ? ((t & 1) ? r.w : r.z) : ((t & 1) ? r.y : r.x);
+      nzs = laplace_from_uniform_fast(uniform_pm1(w), 1.f);
+    } else {
+      nzs = to_f32(inj[t]);
+      if (SRC == SRC_UNIFORM) nzs = laplace_from_uniform(nzs, 1.f);
+    }
+    if (EMIT) noise_out[t] = from_f32<T>(nzs);
+    const float s = to_f32(scale[map_index(t, plane, span)]);
+    out[t] = from_f32<T>(__fadd_rn(__fmul_rn(x_mul, to_f32(x[t])), __fmul_rn(nzs, s)));
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+scaled_residual_kernel(const T* __restrict__ x, const T* __restrict__ eps, const T* __restrict__ scale,
+                       T* __restrict__ out, float out_div, int64_t n, int64_t plane, int64_t span,
+                       int64_t nvec) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int64_t v = tid; v < nvec; v += stride) {
+    const int64_t base = v << 3;
+    float xv[8], ev[8], sv[8];
+    Vec8<T>::load(x + base, xv);
+    Vec8<T>::load(eps + base, ev);
+    Vec8<T>::load(scale + map_index(base, plane, span), sv);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      xv[i] = __fdiv_rn(__fsub_rn(xv[i], __fmul_rn(ev[i], sv[i])), out_div);
+    Vec8<T>::store(out + base, xv);
+  }
+  for (int64_t t = (nvec << 3) + tid; t < n; t += stride) {
+    const float s = to_f32(scale[map_index(t, plane, span)]);
+    out[t] = from_f32<T>(__fdiv_rn(__fsub_rn(to_f32(x[t]), __fmul_rn(to_f32(eps[t]), s)), out_div));
+  }
+}
+
+// vector count of the map kernels: 0 when a broadcast plane is not a multiple of the vector width
+static int64_t map_nvec(int64_t n, int64_t plane, int64_t span) {
+  return (span != 0 && (plane & 7)) ? 0 : (n >> 3);
+}
+
+template <typename T>
+static int launch_qsample_map(const void* x, const void* scale, void* out, const void* noise_in,
+                              const void* u_in, void* noise_out, float x_mul, uint64_t seed,
+                              uint64_t offset, int64_t n, int64_t plane, int64_t span, cudaStream_t st) {
+  const int threads = 256;
+  const int64_t nvec = map_nvec(n, plane, span), rest = n - (nvec << 3);
+  const int grid = grid_for(nvec > rest ? nvec : rest, threads, 8);
+  const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  T* no = (T*)noise_out;
+#define LQM(SRC, EMIT, INJ)                                                                          \
+  laplace_qsample_map_kernel<T, SRC, EMIT><<<grid, threads, 0, st>>>(                                \
+      (const T*)x, (const T*)scale, (T*)out, (const T*)(INJ), no, x_mul, key, offset, n, plane, span, nvec)
+  if (noise_in) {
+    if (no) LQM(SRC_NOISE, true, noise_in); else LQM(SRC_NOISE, false, noise_in);
+  } else if (u_in) {
+    if (no) LQM(SRC_UNIFORM, true, u_in); else LQM(SRC_UNIFORM, false, u_in);
+  } else {
+    if (no) LQM(SRC_PHILOX, true, nullptr); else LQM(SRC_PHILOX, false, nullptr);
+  }
+#undef LQM
+  return check_launch();
+}
+
+template <typename T>
+static int launch_scaled_residual(const void* x, const void* eps, const void* scale, void* out,
+                                  float out_div, int64_t n, int64_t plane, int64_t span, cudaStream_t st) {
+  const int64_t nvec = map_nvec(n, plane, span), rest = n - (nvec << 3);
+  const int grid = grid_for(nvec > rest ? nvec : rest, 256, 8);
+  scaled_residual_kernel<T><<<grid, 256, 0, st>>>((const T*)x, (const T*)eps, (const T*)scale, (T*)out,
+                                                  out_div, n, plane, span, nvec);
+  return check_launch();
+}
+
+// shared argument check of the two map entry points; *span = 0 (full map) or C*plane (broadcast)
+static int map_args(int64_t n, int64_t plane, int channels, int scale_channels, int64_t* span) {
+  if (n < 0 || plane <= 0 || channels <= 0) return LDIFF_EINVAL;
+  if (scale_channels != 1 && scale_channels != channels) return LDIFF_EINVAL;
+  if (n % (plane * (int64_t)channels)) return LDIFF_EINVAL;
+  *span = (scale_channels == channels) ? 0 : plane * (int64_t)channels;
+  return LDIFF_OK;
+}
+
 }  // namespace ldiff
 
 using namespace ldiff;
@@ -236,5 +372,44 @@ extern "C" int ldiff_plms_step(const void* sample, const void* e0, const void* e
   if (dtype == LDIFF_BF16)
     return launch_plms<__nv_bfloat16>(sample, e0, e1, e2, e3, mode, sample_coeff, alpha_diff, denom,
                                       prev_sample, n, st);
+  return LDIFF_EUNSUPPORTED;
+}
+
+extern "C" int ldiff_laplace_qsample_map(const void* x, const void* scale, void* out, const void* noise_in,
+                                         const void* u_in, void* noise_out, float x_mul, uint64_t seed,
+                                         uint64_t offset, int64_t n, int64_t plane, int channels,
+                                         int scale_channels, int dtype, void* stream) {
+  if (!x || !scale || !out || (noise_in && u_in)) return LDIFF_EINVAL;
+  int64_t span = 0;
+  const int rc = map_args(n, plane, channels, scale_channels, &span);
+  if (rc != LDIFF_OK) return rc;
+  if (n == 0) return LDIFF_OK;
+  if (!aligned16(x) || !aligned16(scale) || !aligned16(out) || !aligned16(noise_in) || !aligned16(u_in) ||
+      !aligned16(noise_out))
+    return LDIFF_EALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == LDIFF_F32)
+    return launch_qsample_map<float>(x, scale, out, noise_in, u_in, noise_out, x_mul, seed, offset, n, plane,
+                                     span, st);
+  if (dtype == LDIFF_BF16)
+    return launch_qsample_map<__nv_bfloat16>(x, scale, out, noise_in, u_in, noise_out, x_mul, seed, offset, n,
+                                             plane, span, st);
+  return LDIFF_EUNSUPPORTED;
+}
+
+extern "C" int ldiff_scaled_residual(const void* x, const void* eps, const void* scale, void* out,
+                                     float out_div, int64_t n, int64_t plane, int channels,
+                                     int scale_channels, int dtype, void* stream) {
+  if (!x || !eps || !scale || !out || !(out_div != 0.f)) return LDIFF_EINVAL;
+  int64_t span = 0;
+  const int rc = map_args(n, plane, channels, scale_channels, &span);
+  if (rc != LDIFF_OK) return rc;
+  if (n == 0) return LDIFF_OK;
+  if (!aligned16(x) || !aligned16(eps) || !aligned16(scale) || !aligned16(out)) return LDIFF_EALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == LDIFF_F32)
+    return launch_scaled_residual<float>(x, eps, scale, out, out_div, n, plane, span, st);
+  if (dtype == LDIFF_BF16)
+    return launch_scaled_residual<__nv_bfloat16>(x, eps, scale, out, out_div, n, plane, span, st);
   return LDIFF_EUNSUPPORTED;
 }

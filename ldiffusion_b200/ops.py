@@ -93,6 +93,30 @@ def _laplace_qsample(x: Tensor, out: Tensor, noise: Optional[Tensor], u: Optiona
                                             b, seed, offset, x.numel(), _dt(x), _stream(x)))
 
 
+def _map_dims(x: Tensor, scale: Tensor):
+    """(plane, channels, scale_channels) of a [B,C,...] tensor and its [B,C,...] / [B,1,...] scale map."""
+    plane = 1
+    for d in x.shape[2:]:
+        plane *= d
+    return plane, x.shape[1], scale.shape[1]
+
+
+def _laplace_qsample_map(x: Tensor, scale: Tensor, out: Tensor, noise: Optional[Tensor], u: Optional[Tensor],
+                         noise_out: Optional[Tensor], x_mul: float, seed: int, offset: int) -> None:
+    _cuda(x, scale, out, noise, u, noise_out)
+    plane, C, Cs = _map_dims(x, scale)
+    check(_cabi.lib().ldiff_laplace_qsample_map(_ptr(x), _ptr(scale), _ptr(out), _ptr(noise), _ptr(u),
+                                                _ptr(noise_out), x_mul, seed, offset, x.numel(), plane, C, Cs,
+                                                _dt(x), _stream(x)))
+
+
+def _scaled_residual(x: Tensor, eps: Tensor, scale: Tensor, out: Tensor, out_div: float) -> None:
+    _cuda(x, eps, scale, out)
+    plane, C, Cs = _map_dims(x, scale)
+    check(_cabi.lib().ldiff_scaled_residual(_ptr(x), _ptr(eps), _ptr(scale), _ptr(out), out_div, x.numel(),
+                                            plane, C, Cs, _dt(x), _stream(x)))
+
+
 def _plms_step(sample: Tensor, eps: Sequence[Tensor], mode: int, sample_coeff: float,
                alpha_diff: float, denom: float, out: Tensor) -> None:
     _cuda(sample, out, *eps)
@@ -272,6 +296,8 @@ torch.library.custom_op("ldiff::sw_tta_merge", mutates_args=("out",))(_sw_tta_me
 torch.library.custom_op("ldiff::sw_finalize_argmax", mutates_args=("seg", "logits_out", "status"))(_sw_finalize_argmax)
 torch.library.custom_op("ldiff::laplace_qsample", mutates_args=("out", "noise_out"))(_laplace_qsample)
 torch.library.custom_op("ldiff::plms_step", mutates_args=("out",))(_plms_step)
+torch.library.custom_op("ldiff::laplace_qsample_map", mutates_args=("out", "noise_out"))(_laplace_qsample_map)
+torch.library.custom_op("ldiff::scaled_residual", mutates_args=("out",))(_scaled_residual)
 torch.library.custom_op("ldiff::decode_tail_gray", mutates_args=("rgb", "gray"))(_decode_tail_gray)
 torch.library.custom_op("ldiff::decode_tail_model_input",
                         mutates_args=("rgb", "gray", "model_input"))(_decode_tail_model_input)
@@ -311,6 +337,55 @@ def laplace_qsample(x: Tensor, b: float, *, noise: Optional[Tensor] = None, u: O
     nz = torch.empty_like(x) if return_noise else None
     _laplace_qsample(x, out, noise, u, nz, float(b), int(seed), int(offset))
     return (out, nz) if return_noise else out
+
+
+def _check_scale_map(x: Tensor, scale: Tensor):
+    if x.dim() < 3:
+        raise ValueError("x must be [B,C,...]")
+    if scale.dtype != x.dtype or not scale.is_contiguous() or scale.dim() != x.dim() \
+            or scale.shape[0] != x.shape[0] or scale.shape[2:] != x.shape[2:] \
+            or scale.shape[1] not in (1, x.shape[1]):
+        raise ValueError("scale must be contiguous [B,C,...] or [B,1,...] matching x in dtype and size")
+
+
+def laplace_qsample_map(x: Tensor, scale: Tensor, *, noise: Optional[Tensor] = None, u: Optional[Tensor] = None,
+                        seed: int = 0, offset: int = 0, x_mul: float = 1.0, return_noise: bool = False,
+                        out: Optional[Tensor] = None):
+    """noisy = x_mul * x + Laplace(0, 1) noise * scale  (segmentor.py:339,344-345; the multimodal variant).
+
+    ``scale`` is the per-pixel map (``depth_resized``): [B,C,h,w], or [B,1,h,w] broadcast over the
+    channels instead of the reference's ``.repeat(1, C, 1, 1)`` copy.  Randomness as in
+    ``laplace_qsample``; ``return_noise`` gives the unit noise (the reference's ``noise`` tensor)."""
+    _dense(x, "x")
+    _check_scale_map(x, scale)
+    if noise is not None and u is not None:
+        raise ValueError("pass at most one of noise / u")
+    for t in (noise, u):
+        if t is not None and (t.shape != x.shape or t.dtype != x.dtype or not t.is_contiguous()):
+            raise ValueError("injected tensor must match x in shape, dtype and be contiguous")
+    out = torch.empty_like(x) if out is None else out
+    nz = torch.empty_like(x) if return_noise else None
+    if x.numel() == 0:
+        return (out, nz) if return_noise else out
+    _laplace_qsample_map(x, scale, out, noise, u, nz, float(x_mul), int(seed), int(offset))
+    return (out, nz) if return_noise else out
+
+
+def scaled_residual(x: Tensor, eps: Tensor, scale: Tensor, *, out_div: float = 1.0,
+                    out: Optional[Tensor] = None) -> Tensor:
+    """(x - eps * scale) / out_div  (segmentor.py:375,379: the inverse of ``laplace_qsample_map`` with
+    the UNet's noise prediction, then the VAE's 1/0.18215)."""
+    _dense(x, "x")
+    _check_scale_map(x, scale)
+    if eps.shape != x.shape or eps.dtype != x.dtype or not eps.is_contiguous():
+        raise ValueError("eps must match x in shape, dtype and be contiguous")
+    if not out_div:
+        raise ValueError("out_div must be non-zero")
+    out = torch.empty_like(x) if out is None else out
+    if x.numel() == 0:
+        return out
+    _scaled_residual(x, eps, scale, out, float(out_div))
+    return out
 
 
 def plms_step(sample: Tensor, eps: Sequence[Tensor], mode: int, sample_coeff: float, alpha_diff: float,

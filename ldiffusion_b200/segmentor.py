@@ -2,7 +2,9 @@
 running on the B200 kernels.
 
 Drop-in surface kept: ``Segmentor(train_loader, val_loader, level, num_classes)``,
-``ldiffusion_augment(inputs, pipeline, unet, vae)``, ``micro_dice(...)``,
+``ldiffusion_augment(inputs, pipeline, unet, vae)``,
+``ldiffusion_augment_for_multimodal(rgb, dtm, pipeline, unet, vae, controlnet, batch_size, device)``,
+``micro_dice(...)``,
 ``inference_cell_model(...)``, ``inference_tissue_model_nnUNetv2(...)``,
 ``load_ldiffusion(...)``, same ``ValueError``s.  The six copies of the sampling loop
 in the reference are one method here (``_sample_and_decode``): scheduler
@@ -129,6 +131,42 @@ class Segmentor:
                 x = torch.from_numpy(np.asarray(pil).copy()).to(self.device).permute(2, 0, 1).float().div_(255.0)[None]
             outs.append(x)
         return torch.cat(outs, dim=0)
+
+    @torch.no_grad()
+    def ldiffusion_augment_for_multimodal(self, rgb, dtm, pipeline, unet, vae, controlnet, batch_size, device,
+                                          *, noise=None, seed: int = 0):
+        """segmentor.py:301-386: RGB + depth (DTM) -> list of fp32 ``[256,256,3]`` reconstructions.
+
+        The Laplace(0,1) noise modulated by the resized depth map (``:339-345``) and its removal
+        with the UNet's prediction (``:375,379``) are one launch each, for the whole batch, with the
+        VAE's 0.18215 factors fused in; the depth map stays ``[B,1,h,w]`` and is broadcast over the
+        latent channels inside the kernels (the reference materialises ``.repeat(1, C, 1, 1)`` and
+        loops over the images with B = 1).  ControlNet / UNet / VAE are out of scope (injected).
+        ``noise`` injects the Laplace(0,1) tensor (parity); otherwise Philox(``seed``)."""
+        device = torch.device(device)
+        self._ensure_ldiffusion_proj(pipeline, unet)
+        rgb = ops.bilinear_lift(rgb.to(device, torch.float32).contiguous(), (256, 256))      # :322-323
+        dtm = ops.bilinear_lift(dtm.to(device, torch.float32).contiguous(), (256, 256))      # :324-325
+        B = dtm.shape[0]
+        depth_condition = dtm.expand(B, 3, 256, 256)                                          # :335
+        latents = vae.encode(rgb).latent_dist.sample().to(torch.float32).contiguous()        # :339 (x 0.18215 below)
+        depth_resized = ops.bilinear_lift(dtm, tuple(latents.shape[-2:]))                    # :340, [B,1,32,32]
+        latents_noisy = ops.laplace_qsample_map(latents, depth_resized, x_mul=0.18215, noise=noise,
+                                                seed=seed)                                   # :339,344-345
+        text = self._get_text_embeddings("A remote sense image", B, pipeline, unet)          # :348-351
+        pipeline.scheduler.set_timesteps(1, device=device)                                   # :354
+        noise_pred = None
+        for timestep in pipeline.scheduler.timesteps:
+            down, mid = controlnet(sample=latents_noisy, timestep=timestep, encoder_hidden_states=text,
+                                   controlnet_cond=depth_condition, return_dict=False)       # :357-363
+            noise_pred = unet(latents_noisy, timestep, encoder_hidden_states=text,
+                              down_block_additional_residuals=down,
+                              mid_block_additional_residual=mid).sample                      # :366-372
+        z = ops.scaled_residual(latents_noisy, noise_pred.to(torch.float32).contiguous(), depth_resized,
+                                out_div=0.18215)                                             # :375,379
+        recon = vae.decode(z).sample                                                         # :379
+        recon_np = recon.permute(0, 2, 3, 1).contiguous().cpu().numpy()                      # :381-383, one copy
+        return [recon_np[i] for i in range(B)]
 
     def micro_dice(self, predicted_labels, true_labels, num_classes=7):
         """segmentor.py:114-142 (identical to utils.micro_dice)."""

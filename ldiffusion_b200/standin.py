@@ -54,8 +54,24 @@ class StandInUNet(nn.Module):
         h = self.inp(sample) + self.t_proj(t)[:, :, None, None]
         if encoder_hidden_states is not None:
             h = h + self.c_proj(encoder_hidden_states.to(sample.dtype).mean(1))[:, :, None, None]
-        h = self.out(F.silu(self.mid(F.silu(h))))
+        h = self.mid(F.silu(h))
+        if kw.get("mid_block_additional_residual") is not None:          # ControlNet hook (segmentor.py:366-372)
+            h = h + kw["mid_block_additional_residual"]
+        h = self.out(F.silu(h))
         return UNetOutput(h)
+
+
+class StandInControlNet(nn.Module):
+    """``ControlNetModel`` as far as segmentor.py:357-363 touches it: (down residuals, mid residual)."""
+
+    def __init__(self, width: int = 32):
+        super().__init__()
+        self.cond = nn.Conv2d(3, width, 8, 8)
+        self.inp = nn.Conv2d(4, width, 3, 1, 1)
+
+    def forward(self, sample, timestep, encoder_hidden_states=None, controlnet_cond=None, return_dict=False):
+        mid = F.silu(self.inp(sample) + self.cond(controlnet_cond.to(sample.dtype)))
+        return [mid], mid
 
 
 class UNetOutput(tuple):
@@ -81,8 +97,9 @@ class StandInTextEncoder(nn.Module):
 
 class StandInTokenizer:
     def __call__(self, prompts, **kw):
-        rng = np.random.default_rng(0)
-        ids = [[49406] + rng.integers(1000, 2000, 5).tolist() + [49407] for _ in prompts]
+        import zlib
+        ids = [[49406] + np.random.default_rng(zlib.crc32(str(p).encode())).integers(1000, 2000, 5).tolist() + [49407]
+               for p in prompts]                                   # a prompt always maps to the same ids
         return {"input_ids": ids}
 
 

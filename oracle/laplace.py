@@ -50,6 +50,40 @@ def qsample_injected(latents, noise):
     return (latents + noise).to(torch.float32)
 
 
+def depth_noising_chain(latents, depth_resized, noise=None, generator=None, x_mul=None):
+    """segmentor.py:339-345 (``ldiffusion_augment_for_multimodal``), op for op::
+
+        latents = vae.encode(rgb_i).latent_dist.sample() * 0.18215      # x_mul, when given
+        depth_resized = depth_resized.repeat(1, latents.shape[1], 1, 1)
+        noise = torch.distributions.laplace.Laplace(0.0, 1.0).sample(latents.shape)
+        latents_noisy = latents + noise * depth_resized
+
+    ``depth_resized`` is [B,1,h,w] (repeated here as the reference does) or already [B,C,h,w].
+    ``noise`` injects the Laplace(0,1) tensor; otherwise torch's sampler draws it (``generator``
+    replays ``rsample`` on a seeded uniform).  Returns (latents_noisy, noise)."""
+    if x_mul is not None:
+        latents = latents * x_mul
+    if depth_resized.shape[1] != latents.shape[1]:
+        depth_resized = depth_resized.repeat(1, latents.shape[1], 1, 1)
+    if noise is None:
+        if generator is None:
+            noise = torch.distributions.laplace.Laplace(0.0, 1.0).sample(latents.shape)
+        else:
+            finfo = torch.finfo(torch.float32)
+            u = torch.empty(latents.shape, dtype=torch.float32).uniform_(finfo.eps - 1, 1, generator=generator)
+            noise = laplace_from_uniform_chain(u, 1.0)
+    return latents + noise * depth_resized, noise
+
+
+def depth_unnoise_chain(latents_noisy, noise_pred, depth_resized, out_div=None):
+    """segmentor.py:375,379: ``latents_denoised = latents_noisy - noise_pred * depth_resized`` and, when
+    ``out_div`` is given, the ``latents_denoised / 0.18215`` handed to ``vae.decode``."""
+    if depth_resized.shape[1] != latents_noisy.shape[1]:
+        depth_resized = depth_resized.repeat(1, latents_noisy.shape[1], 1, 1)
+    out = latents_noisy - noise_pred * depth_resized
+    return out if out_div is None else out / out_div
+
+
 # ---- the counter-based generator of the CUDA kernel, restated -------------
 # (Philox4x32-10 is a published algorithm: Salmon et al., SC'11.  torch's RNG
 # stream cannot and need not be matched; the kernel's own stream is pinned by

@@ -43,6 +43,17 @@ def test_argument_errors_are_reported_without_a_gpu(built_lib):
     assert lib.ldiff_plms_step(16, 16, None, None, None, 0, 1.0, 0.0, 1.0, 16, 8, 9, None) == EUNSUP  # dtype
     assert lib.ldiff_plms_step(16, 16, None, None, None, 0, 1.0, 0.0, 1.0, 16, 0, 0, None) == 0        # n == 0
     assert lib.ldiff_laplace_qsample(16, 16, 16, 16, None, 1.0, 0, 0, 8, 0, None) == EINVAL            # noise and u
+    qm = lib.ldiff_laplace_qsample_map
+    assert qm(16, None, 16, None, None, None, 1.0, 0, 0, 64, 16, 4, 1, 0, None) == EINVAL              # no scale map
+    assert qm(16, 16, 16, None, None, None, 1.0, 0, 0, 64, 16, 4, 2, 0, None) == EINVAL                # map channels 2 of 4
+    assert qm(16, 16, 16, None, None, None, 1.0, 0, 0, 60, 16, 4, 1, 0, None) == EINVAL                # n % (C*plane)
+    assert qm(16, 24, 16, None, None, None, 1.0, 0, 0, 64, 16, 4, 1, 0, None) == EALIGN
+    assert qm(16, 16, 16, None, None, None, 1.0, 0, 0, 64, 16, 4, 1, 2, None) == EUNSUP                # u8 storage
+    assert qm(16, 16, 16, None, None, None, 1.0, 0, 0, 0, 16, 4, 1, 0, None) == 0                      # empty batch
+    sr = lib.ldiff_scaled_residual
+    assert sr(16, 16, 16, 16, 0.0, 64, 16, 4, 1, 0, None) == EINVAL                                    # division by 0
+    assert sr(16, None, 16, 16, 1.0, 64, 16, 4, 4, 0, None) == EINVAL
+    assert sr(16, 16, 16, 40, 1.0, 64, 16, 4, 4, 0, None) == EALIGN
     assert lib.ldiff_decode_tail_gray(16, None, None, 1, 4, 4, 16, 0, None) == EINVAL                  # no output
     assert lib.ldiff_decode_tail_gray(16, None, 16, 1, 4, 4, 8, 0, None) == EINVAL                     # stride < H*W
     assert lib.ldiff_bilinear_lift(16, 0, 2, 4, 4, 32, 16, 16, 0, 1, 0, 8, 8, 1, 1, None) == EINVAL    # gray needs C==3
@@ -68,7 +79,7 @@ def test_ops_refuse_cpu_tensors():
 def test_custom_ops_are_registered():
     import torch
     import ldiffusion_b200  # noqa: F401
-    for name in ("laplace_qsample", "plms_step", "decode_tail_gray", "bilinear_lift", "head_logits", "lift_argmax",
+    for name in ("laplace_qsample", "laplace_qsample_map", "scaled_residual", "plms_step", "decode_tail_gray", "bilinear_lift", "head_logits", "lift_argmax",
                  "cell_classify", "lut_paint", "argmax_channels", "confusion_hist", "confusion_hist_batched"):
         assert hasattr(torch.ops.ldiff, name), name
 

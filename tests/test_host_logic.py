@@ -163,3 +163,73 @@ def test_contrastive_pair_sampling_rules_and_cpu_refusal():
     assert sample_contrastive_pairs(torch.zeros(1, 1, 8, 8, dtype=torch.uint8), 16) is None
     with pytest.raises(ops.LdiffError):
         pixel_contrastive_loss(torch.zeros(1, 5, 32, 32), lab[:1])
+
+
+def _reference_multimodal_loop(rgb, dtm, pipe, controlnet, proj, noise):
+    """segmentor.py:322-386 restated op for op on the CPU (per-image loop, B = 1, the
+    ``.repeat`` copies, separate 0.18215 passes) with the Laplace(0,1) noise injected."""
+    import torch.nn.functional as F
+    from oracle.laplace import depth_noising_chain, depth_unnoise_chain
+    rgb = F.interpolate(rgb, size=(256, 256), mode="bilinear", align_corners=False)
+    dtm = F.interpolate(dtm, size=(256, 256), mode="bilinear", align_corners=False)
+    out = []
+    for i in range(dtm.shape[0]):
+        dtm_i, rgb_i = dtm[i], rgb[i].unsqueeze(0)
+        depth_condition = dtm_i.unsqueeze(0).repeat(1, 3, 1, 1)
+        latents = pipe.vae.encode(rgb_i).latent_dist.sample() * 0.18215
+        depth_resized = F.interpolate(dtm_i.unsqueeze(0), size=(32, 32), mode="bilinear", align_corners=False)
+        depth_resized = depth_resized.repeat(1, latents.shape[1], 1, 1)
+        latents_noisy, _ = depth_noising_chain(latents, depth_resized, noise=noise[i:i + 1])
+        ids = torch.tensor(pipe.tokenizer(["A remote sense image"])["input_ids"], dtype=torch.long)
+        text = proj(pipe.text_encoder(ids)["last_hidden_state"].to(torch.float32)).to(torch.float32)
+        pipe.scheduler.set_timesteps(1)
+        for timestep in pipe.scheduler.timesteps:
+            down, mid = controlnet(sample=latents_noisy, timestep=timestep, encoder_hidden_states=text,
+                                   controlnet_cond=depth_condition, return_dict=False)
+            noise_pred = pipe.unet(latents_noisy, timestep, encoder_hidden_states=text,
+                                   down_block_additional_residuals=down, mid_block_additional_residual=mid).sample
+        latents_denoised = depth_unnoise_chain(latents_noisy, noise_pred, depth_resized)
+        recon = pipe.vae.decode(latents_denoised / 0.18215).sample
+        out.append(recon.squeeze(0).permute(1, 2, 0).numpy())
+    return out
+
+
+def test_multimodal_augment_host_logic(monkeypatch):
+    """Segmentor.ldiffusion_augment_for_multimodal (batched, broadcast depth map, fused 0.18215
+    factors) against the reference's per-image loop, with the three ldiff operators it calls
+    emulated by their oracle chains — the GPU parity of those operators is tests/test_gpu_sampler.py."""
+    import torch.nn.functional as F
+    from oracle.laplace import depth_noising_chain, depth_unnoise_chain
+    from ldiffusion_b200 import ops
+    from ldiffusion_b200.segmentor import Segmentor
+    from ldiffusion_b200.standin import StandInControlNet, StandInPipeline
+
+    def fake_lift(src, size, **kw):
+        return F.interpolate(src, size=size, mode="bilinear", align_corners=False)
+
+    def fake_noising(x, scale, *, noise=None, x_mul=1.0, seed=0, **kw):
+        assert scale.shape[1] == 1 and noise is not None
+        return depth_noising_chain(x, scale, noise=noise, x_mul=x_mul)[0]
+
+    def fake_residual(x, eps, scale, *, out_div=1.0, out=None):
+        assert scale.shape[1] == 1
+        return depth_unnoise_chain(x, eps, scale, out_div=out_div)
+
+    monkeypatch.setattr(ops, "bilinear_lift", fake_lift)
+    monkeypatch.setattr(ops, "laplace_qsample_map", fake_noising)
+    monkeypatch.setattr(ops, "scaled_residual", fake_residual)
+    torch.manual_seed(0)
+    pipe = StandInPipeline("cpu", seed=4)
+    controlnet = StandInControlNet().eval()
+    seg = object.__new__(Segmentor)                      # the constructor insists on a CUDA device
+    seg.device, seg.ldiffusion_proj = torch.device("cpu"), None
+    g = torch.Generator().manual_seed(9)
+    rgb, dtm = torch.rand(3, 3, 300, 280, generator=g), torch.rand(3, 1, 300, 280, generator=g) * 2
+    noise = torch.distributions.Laplace(0.0, 1.0).sample((3, 4, 32, 32))
+    with torch.no_grad():
+        got = seg.ldiffusion_augment_for_multimodal(rgb, dtm, pipe, pipe.unet, pipe.vae, controlnet, 3, "cpu",
+                                                    noise=noise)
+        want = _reference_multimodal_loop(rgb, dtm, pipe, controlnet, seg.ldiffusion_proj, noise)
+    assert len(got) == 3 and got[0].shape == (256, 256, 3) and got[0].dtype == np.float32
+    for a, b in zip(got, want):                          # batched convolutions vs B = 1: not bit-identical
+        np.testing.assert_allclose(a, b, rtol=1e-4, atol=1e-5)
