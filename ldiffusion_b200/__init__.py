@@ -10,11 +10,13 @@ Public surface (drop-in seams, see DESIGN.md / INTEGRATION.md):
   ``frequency_weighted_iou`` / ``evaluate``
 * ``pixel_contrastive_loss``          - InfoNCE term of the warm-up loss (forward + backward)
 * ``Segmentor`` / ``LDiffusionModel`` - orchestrator shims with the reference's signatures
+* ``dataset`` / ``utils``             - label tables as LUTs, dataset-preparation callers of the loop
 
 All tensor work runs in ``libldiff_sm100.so`` (hand-written CUDA behind the C ABI
 of ``include/ldiff.h``); there is no CPU fallback.
 """
 from . import ops  # noqa: F401  (registers the ldiff:: custom ops)
+from . import dataset, utils  # noqa: F401
 from .features import (PixelVectorBuilder, feature_concat, label_down, pixel_latent_vector,  # noqa: F401
                        pixel_vectors, rgb_up)
 from .head import TissueHead, cell_mask, tissue_mask  # noqa: F401
