@@ -32,14 +32,29 @@ __device__ __forceinline__ float uniform_pm1(uint32_t w) {
   return __fmaf_rn(__fadd_rn(f, -1.5f), 2.f, 1.1920928955078125e-07f);
 }
 
+// log2 of a NORMAL positive number: the bare MUFU.LG2.  (__log2f without .ftz brackets the
+// MUFU with a denormal pre-scaling — FSETP, FMUL, FADD per element — that 1 - |u| >= 2^-23
+// never needs.)
+__device__ __forceinline__ float lg2_normal(float w) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(w));
+  return r;
+}
+
 // Philox mode only: -b * sign(u) * log1p(-|u|) with a short log1p.  w = 1 - |u| is exact;
 // |u| >= 2^-5 uses the hardware log2 (relative error <= 6e-6 there), smaller |u| a
 // 5-term series (relative error < 1e-8).  The result is the SAME random variate to
 // ~6e-6 relative, far below the 1e-3 contract, at a third of libm's instruction count
 // (which made the fused kernel issue-bound at 59 % of the HBM roofline).
+// SERIES = false (bf16 storage, where half the bytes move per element and the kernel is
+// ALU-bound): the hardware log2 everywhere, -b ln2 folded into one multiply.  Its absolute
+// error (<= 2^-22 in log2 near 1) is <= 1.7e-7 b in the noise, i.e. below a bf16 ulp of any
+// noise value above 5e-5 b; 7 instructions per element fewer.
+template <bool SERIES>
 __device__ __forceinline__ float laplace_from_uniform_fast(float u, float b) {
   const float a = fabsf(u);
-  const float lg = __log2f(__fsub_rn(1.f, a)) * 0.6931471805599453f;
+  if (!SERIES) return copysignf(lg2_normal(__fsub_rn(1.f, a)) * (b * -0.6931471805599453f), u);
+  const float lg = lg2_normal(__fsub_rn(1.f, a)) * 0.6931471805599453f;
   float p = __fmaf_rn(a, 0.2f, 0.25f);
   p = __fmaf_rn(a, p, 0.3333333333f);
   p = __fmaf_rn(a, p, 0.5f);
@@ -48,6 +63,8 @@ __device__ __forceinline__ float laplace_from_uniform_fast(float u, float b) {
   // noise = -b * sign(u) * l = copysign(b * (-l), u)
   return copysignf(b * -l, u);
 }
+template <typename T> struct FastLaplace { static constexpr bool kSeries = true; };
+template <> struct FastLaplace<__nv_bfloat16> { static constexpr bool kSeries = false; };
 
 // torch.distributions.Laplace.rsample with loc = 0:
 //   noise = 0 - (scale * sign(u)) * log1p(-|u|)
@@ -77,7 +94,7 @@ laplace_qsample_kernel(const T* __restrict__ x, T* __restrict__ out, const T* __
       const uint4 r1 = philox4x32_10(make_uint4((uint32_t)c1, (uint32_t)(c1 >> 32), 0u, 0u), key);
       const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
-      for (int i = 0; i < 8; ++i) nz[i] = laplace_from_uniform_fast(uniform_pm1(w[i]), b);
+      for (int i = 0; i < 8; ++i) nz[i] = laplace_from_uniform_fast<FastLaplace<T>::kSeries>(uniform_pm1(w[i]), b);
     } else {
       Vec8<T>::load(inj + base, nz);
       if (SRC == SRC_UNIFORM) {
@@ -98,7 +115,7 @@ laplace_qsample_kernel(const T* __restrict__ x, T* __restrict__ out, const T* __
       const uint64_t c = offset + (uint64_t)(t >> 2);
       const uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0u, 0u), key);
       const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-      nzs = laplace_from_uniform_fast(uniform_pm1(w[t & 3]), b);
+      nzs = laplace_from_uniform_fast<FastLaplace<T>::kSeries>(uniform_pm1(w[t & 3]), b);
     } else {
       nzs = to_f32(inj[t]);
       if (SRC == SRC_UNIFORM) nzs = laplace_from_uniform(nzs, b);
@@ -235,7 +252,7 @@ laplace_qsample_map_kernel(const T* __restrict__ x, const T* __restrict__ scale,
       const uint4 r1 = philox4x32_10(make_uint4((uint32_t)c1, (uint32_t)(c1 >> 32), 0u, 0u), key);
       const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
-      for (int i = 0; i < 8; ++i) nz[i] = laplace_from_uniform_fast(uniform_pm1(w[i]), 1.f);
+      for (int i = 0; i < 8; ++i) nz[i] = laplace_from_uniform_fast<FastLaplace<T>::kSeries>(uniform_pm1(w[i]), 1.f);
     } else {
       Vec8<T>::load(inj + base, nz);
       if (SRC == SRC_UNIFORM) {
@@ -254,7 +271,7 @@ laplace_qsample_map_kernel(const T* __restrict__ x, const T* __restrict__ scale,
       const uint64_t c = offset + (uint64_t)(t >> 2);
       const uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0u, 0u), key);
       const uint32_t w = (t & 2) ? ((t & 1) ? r.w : r.z) : ((t & 1) ? r.y : r.x);
-      nzs = laplace_from_uniform_fast(uniform_pm1(w), 1.f);
+      nzs = laplace_from_uniform_fast<FastLaplace<T>::kSeries>(uniform_pm1(w), 1.f);
     } else {
       nzs = to_f32(inj[t]);
       if (SRC == SRC_UNIFORM) nzs = laplace_from_uniform(nzs, 1.f);

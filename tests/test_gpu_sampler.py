@@ -80,6 +80,19 @@ def test_qsample_bf16_storage():
     assert torch.equal(got, want)
 
 
+def test_qsample_philox_bf16_storage():
+    """bf16 storage, Philox mode: the hardware log2 for every |u| (no small-|u| series; 1.7e-7*b
+    absolute in the noise) and one bf16 rounding — the restated variate to a bf16 ulp."""
+    n, seed, offset, b = 65536 + 24, 99, 3, 0.9166153
+    got, nz = _ops().laplace_qsample(torch.zeros(n, device="cuda", dtype=torch.bfloat16), b, seed=seed,
+                                     offset=offset, return_noise=True)
+    want = olap.laplace_philox(n, b, seed, offset)
+    err = (nz.float().cpu() - want).abs()
+    assert (err <= want.abs() * (2.0 ** -8 + 2e-5) + 3e-7).all()
+    big = want.abs() > 1e-6
+    assert torch.equal(got, nz) and (nz.float().cpu().sign()[big] == want.sign()[big]).all()
+
+
 @pytest.mark.parametrize("n_set,shape", [(1, (1, 4, 64, 64)), (4, (2, 4, 64, 64)), (5, (8, 4, 128, 128)),
                                          (10, (1, 4, 16, 16)), (50, (1, 4, 8, 8)), (4, (1, 3, 5, 7))])
 def test_plms_loop_bit_exact(n_set, shape):

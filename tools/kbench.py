@@ -73,6 +73,13 @@ def main():
             res[f"laplace_{name}_{tag}"] = (us, 2 * n * s / us / 1e3, 2 * n * s / us / 1e3 / PEAK)
             us = timeit(lambda i: ops.plms_step(x[i % len(x)], e, 4, 1.01, 0.02, 0.9, out=o), len(x))
             res[f"plms4_{name}_{tag}"] = (us, 6 * n * s / us / 1e3, 6 * n * s / us / 1e3 / PEAK)
+            # multimodal variant: depth map [B,1,h,w] broadcast over the 4 latent channels
+            sc = torch.rand(shape[0], 1, shape[2], shape[3], device=dev).to(dt)
+            us = timeit(lambda i: ops.laplace_qsample_map(x[i % len(x)], sc, seed=1, offset=i, x_mul=0.18215, out=o),
+                        len(x))
+            res[f"laplace_map_{name}_{tag}"] = (us, 2.25 * n * s / us / 1e3, 2.25 * n * s / us / 1e3 / PEAK)
+            us = timeit(lambda i: ops.scaled_residual(x[i % len(x)], e[0], sc, out_div=0.18215, out=o), len(x))
+            res[f"scaled_residual_{name}_{tag}"] = (us, 3.25 * n * s / us / 1e3, 3.25 * n * s / us / 1e3 / PEAK)
     # head
     feat = torch.randn(8, 256, 32, 32, device=dev).bfloat16()
     w = (torch.randn(11, 256, device=dev) / 16).bfloat16()
