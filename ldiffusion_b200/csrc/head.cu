@@ -141,7 +141,12 @@ __device__ __forceinline__ int tie_acc(const float (&v)[K], float thr, std::inte
   return acc;
 }
 
-template <int K, int COLS, int MINB>
+// DIFF: the vertical lerp as ONE fma per class, v' = fma(l1, U - T, T), with D = U - T formed once per
+// band (half the fma-pipe work of fma(l0, T, l1*U)).  v' is not the reference's rounding, so it only
+// RANKS: |v' - v_ref| <= 5 * 2^-24 * M (M = the column's largest |logit|; derivation in DESIGN.md a-5),
+// the near-tie gap is widened by 2^-20 * M >= twice that bound, and every pixel inside the gap is
+// resolved by the pinned softmax on the reference's own roundings exactly as before.
+template <int K, int COLS, int MINB, bool DIFF = false>
 __global__ void __launch_bounds__(256, MINB)   // the cold fp64 exp may spill, the hot loop must not
 lift_argmax_kernel(const float* __restrict__ logits, uint8_t* __restrict__ mask, AxisH ay, AxisH ax) {
   __shared__ float2 s_l[kBand];                          // vertical weights (l0, l1) of the band's rows
@@ -185,8 +190,14 @@ lift_argmax_kernel(const float* __restrict__ logits, uint8_t* __restrict__ mask,
   // never be within kTieGap of the maximum
   constexpr int KP = (K + 1) / 2;
   constexpr float kPad = -1e30f;
-  float2 T[COLS][KP], U[COLS][KP];
+  float2 T[COLS][KP], U[COLS][KP];                       // DIFF: U holds D = U - T
+  float gap[COLS];                                       // near-tie gap of the column (DIFF: + 2^-20 * M)
+#pragma unroll
+  for (int c = 0; c < COLS; ++c) gap[c] = kTieGap;
   if (active) {                                          // horizontal lift of the two source rows, once
+    float M[COLS];
+#pragma unroll
+    for (int c = 0; c < COLS; ++c) M[c] = 0.f;
 #pragma unroll
     for (int k = 0; k < 2 * KP; ++k) {
       float t[COLS], u[COLS];
@@ -199,13 +210,24 @@ lift_argmax_kernel(const float* __restrict__ logits, uint8_t* __restrict__ mask,
         for (int c = 0; c < COLS; ++c) {
           t[c] = lerp2(tx[c].l0, __ldg(r0 + tx[c].i0), tx[c].l1, __ldg(r0 + tx[c].i1));
           u[c] = lerp2(tx[c].l0, __ldg(r1 + tx[c].i0), tx[c].l1, __ldg(r1 + tx[c].i1));
+          if (DIFF) {
+            M[c] = fmaxf(M[c], fmaxf(fabsf(t[c]), fabsf(u[c])));
+            u[c] = __fsub_rn(u[c], t[c]);
+          }
         }
+      } else if (DIFF) {
+#pragma unroll
+        for (int c = 0; c < COLS; ++c) u[c] = 0.f;       // pad class: v' = kPad on every row
       }
 #pragma unroll
       for (int c = 0; c < COLS; ++c) {
         if (k & 1) { T[c][k >> 1].y = t[c]; U[c][k >> 1].y = u[c]; }
         else { T[c][k >> 1].x = t[c]; U[c][k >> 1].x = u[c]; }
       }
+    }
+    if (DIFF) {
+#pragma unroll
+      for (int c = 0; c < COLS; ++c) gap[c] = __fmaf_rn(M[c], 9.5367431640625e-07f, kTieGap);   // 2^-20 * M
     }
   }
   // one output pixel: candidate mask of the classes within kTieGap of the maximum
@@ -215,7 +237,8 @@ lift_argmax_kernel(const float* __restrict__ logits, uint8_t* __restrict__ mask,
     float2 v[KP];
 #pragma unroll
     for (int j = 0; j < KP; ++j)
-      v[j] = __ffma2_rn(l0p, T[c][j], __fmul2_rn(l1p, U[c][j]));     // == fma(l0, T, fl(l1*U)) per class
+      v[j] = DIFF ? __ffma2_rn(l1p, U[c][j], T[c][j])                 // ranks only (see the template comment)
+                  : __ffma2_rn(l0p, T[c][j], __fmul2_rn(l1p, U[c][j]));   // == fma(l0, T, fl(l1*U)) per class
     float mp[KP];                                                     // max as a tree: short chains
 #pragma unroll
     for (int j = 0; j < KP; ++j) mp[j] = fmaxf(v[j].x, v[j].y);
@@ -225,7 +248,7 @@ lift_argmax_kernel(const float* __restrict__ logits, uint8_t* __restrict__ mask,
       for (int j = 0; j + w < KP; j += 2 * w) mp[j] = fmaxf(mp[j], mp[j + w]);
     // sign(v - thr) is set exactly when v < thr; the sign bits are funnel-shifted into
     // per-group accumulators (independent chains) and concatenated
-    const float nthr = __fsub_rn(kTieGap, mp[0]);
+    const float nthr = __fsub_rn(gap[c], mp[0]);
     const float2 nthr2 = make_float2(nthr, nthr);
     constexpr int G = (KP + 1) / 2;                      // groups of two pairs (four classes)
     uint32_t below = 0;
@@ -574,11 +597,13 @@ extern "C" int ldiff_lift_argmax(const float* logits, uint8_t* mask, int B, int 
   AxisH ay{(float)h / (float)H, h, H}, ax{(float)w / (float)W, w, W};
   if (K <= 15 && H >= 4 * h && (H + h - 1) / h + 2 <= kBand && h <= 65535) {
     // two columns per thread while T/U (4K registers) fit the 80-register budget, else one
-    // variant: 0 = 2 columns/thread, 2 CTAs/SM; 1 = 1 column, 3 CTAs/SM; 2 = 1 column, 4 CTAs/SM; 3 = 1 column, 2 CTAs/SM
+    // variant: 0 = 2 columns/thread, 2 CTAs/SM; 1 = 1 column, 3 CTAs/SM; 2 = 1 column, 4 CTAs/SM; 3 = 1 column, 2 CTAs/SM;
+    // 4 / 5 = variants 0 / 1 with the one-fma lerp (DIFF).  Measured at 32x lift, K=11, alone: 31.7 / 32.0 us
+    // for 0 / 1, 30.6 / 29.2 us for 4 / 5; inside the whole pass 136.3 / 137.6 / 135.0 / 135.7 us for 0 / 1 / 4 / 5.
     static const int knob = [] { const char* e = getenv("LDIFF_ARGMAX_VARIANT"); return e ? atoi(e) : -1; }();
-    int variant = knob >= 0 ? knob : 0;                    // measured at 32x lift, K=11: 34.8 / 36.0 / 35.9 us for 0 / 1 / 3
-    if (K > 12 || (W % 2) != 0) variant = variant == 0 ? 1 : variant;
-    const int cols = variant == 0 ? 2 : 1;
+    int variant = knob >= 0 ? knob : 4;
+    if (K > 12 || (W % 2) != 0) variant = variant == 0 ? 1 : (variant == 4 ? 5 : variant);
+    const int cols = (variant == 0 || variant == 4) ? 2 : 1;
     dim3 grid((W / cols + 255) / 256, h, B);
     // experiment knob: unused dynamic shared memory that caps how many of these register-heavy CTAs
     // are resident per SM, leaving register file for the bandwidth-bound kernels they run beside
@@ -590,11 +615,16 @@ extern "C" int ldiff_lift_argmax(const float* logits, uint8_t* mask, int B, int 
           cudaFuncSetAttribute(lift_argmax_kernel<KK, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad); \
         lift_argmax_kernel<KK, 2, 2><<<grid, 256, pad, st>>>(logits, mask, ay, ax);                    \
       }                                                                                                \
+      else if (variant == 4) lift_argmax_kernel<KK, 2, 2, true><<<grid, 256, 0, st>>>(logits, mask, ay, ax); \
+      else if (variant == 5) lift_argmax_kernel<KK, 1, 3, true><<<grid, 256, 0, st>>>(logits, mask, ay, ax); \
       else if (variant == 1) lift_argmax_kernel<KK, 1, 3><<<grid, 256, 0, st>>>(logits, mask, ay, ax);  \
       else if (variant == 3) lift_argmax_kernel<KK, 1, 2><<<grid, 256, 0, st>>>(logits, mask, ay, ax);  \
       else lift_argmax_kernel<KK, 1, 4><<<grid, 256, 0, st>>>(logits, mask, ay, ax);                    \
       break;
-#define LA1(KK) case KK: lift_argmax_kernel<KK, 1, 3><<<grid, 256, 0, st>>>(logits, mask, ay, ax); break;
+#define LA1(KK) case KK:                                                                               \
+      if (variant == 5) lift_argmax_kernel<KK, 1, 3, true><<<grid, 256, 0, st>>>(logits, mask, ay, ax); \
+      else lift_argmax_kernel<KK, 1, 3><<<grid, 256, 0, st>>>(logits, mask, ay, ax);                    \
+      break;
       LA2(1) LA2(2) LA2(3) LA2(4) LA2(5) LA2(6) LA2(7) LA2(8) LA2(9) LA2(10) LA2(11) LA2(12)
       LA1(13) LA1(14) LA1(15)
 #undef LA2

@@ -229,22 +229,38 @@ static int launch_plms(const void* x, const void* e0, const void* e1, const void
 // broadcast map it needs plane % 8 == 0 so that a vector never straddles two planes.
 // Everything the vector path does not cover is done by a scalar grid-stride loop.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ int64_t map_index(int64_t i, int64_t plane, int64_t span) {
-  return span == 0 ? i : (i / span) * plane + (i % plane);
+// index into the scale map of element i.  span == 0: the map has the tensor's shape.  Otherwise the
+// map is [B, 1, plane] under a [B, C, plane] tensor (span = C * plane): image i / span, pixel i % plane.
+// Power-of-two planes and channel counts (32x32x4, 128x128x4 latents) take shifts; other shapes one
+// 32-bit division pair while the tensor has fewer than 2^31 elements (a 64-bit pair costs ~25
+// instructions per element of an 8-wide vector and made the kernel ALU-bound at 0.85 of the roofline).
+struct MapIdx {
+  int64_t plane, span;
+  int sh_span, sh_plane;          // >= 0: both are powers of two
+  int small;                      // n < 2^31: 32-bit arithmetic is exact
+};
+__device__ __forceinline__ int64_t map_index(int64_t i, const MapIdx& m) {
+  if (m.span == 0) return i;
+  if (m.sh_span >= 0) return ((i >> m.sh_span) << m.sh_plane) | (i & (m.plane - 1));
+  if (m.small) {
+    const uint32_t u = (uint32_t)i, sp = (uint32_t)m.span, pl = (uint32_t)m.plane;
+    return (int64_t)((u / sp) * pl + (u % pl));
+  }
+  return (i / m.span) * m.plane + (i % m.plane);
 }
 
 template <typename T, int SRC, bool EMIT>
 __global__ void __launch_bounds__(256)
 laplace_qsample_map_kernel(const T* __restrict__ x, const T* __restrict__ scale, T* __restrict__ out,
                            const T* __restrict__ inj, T* __restrict__ noise_out, float x_mul, uint2 key,
-                           uint64_t offset, int64_t n, int64_t plane, int64_t span, int64_t nvec) {
+                           uint64_t offset, int64_t n, MapIdx mi, int64_t nvec) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   for (int64_t v = tid; v < nvec; v += stride) {
     const int64_t base = v << 3;
     float xv[8], nz[8], sv[8];
     Vec8<T>::load(x + base, xv);
-    Vec8<T>::load(scale + map_index(base, plane, span), sv);
+    Vec8<T>::load(scale + map_index(base, mi), sv);
     if (SRC == SRC_PHILOX) {
       const uint64_t c0 = offset + (uint64_t)(base >> 2);
       const uint4 r0 = philox4x32_10(make_uint4((uint32_t)c0, (uint32_t)(c0 >> 32), 0u, 0u), key);
@@ -277,7 +293,7 @@ laplace_qsample_map_kernel(const T* __restrict__ x, const T* __restrict__ scale,
       if (SRC == SRC_UNIFORM) nzs = laplace_from_uniform(nzs, 1.f);
     }
     if (EMIT) noise_out[t] = from_f32<T>(nzs);
-    const float s = to_f32(scale[map_index(t, plane, span)]);
+    const float s = to_f32(scale[map_index(t, mi)]);
     out[t] = from_f32<T>(__fadd_rn(__fmul_rn(x_mul, to_f32(x[t])), __fmul_rn(nzs, s)));
   }
 }
@@ -285,8 +301,7 @@ laplace_qsample_map_kernel(const T* __restrict__ x, const T* __restrict__ scale,
 template <typename T>
 __global__ void __launch_bounds__(256)
 scaled_residual_kernel(const T* __restrict__ x, const T* __restrict__ eps, const T* __restrict__ scale,
-                       T* __restrict__ out, float out_div, int64_t n, int64_t plane, int64_t span,
-                       int64_t nvec) {
+                       T* __restrict__ out, float out_div, int64_t n, MapIdx mi, int64_t nvec) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   for (int64_t v = tid; v < nvec; v += stride) {
@@ -294,14 +309,14 @@ scaled_residual_kernel(const T* __restrict__ x, const T* __restrict__ eps, const
     float xv[8], ev[8], sv[8];
     Vec8<T>::load(x + base, xv);
     Vec8<T>::load(eps + base, ev);
-    Vec8<T>::load(scale + map_index(base, plane, span), sv);
+    Vec8<T>::load(scale + map_index(base, mi), sv);
 #pragma unroll
     for (int i = 0; i < 8; ++i)
       xv[i] = __fdiv_rn(__fsub_rn(xv[i], __fmul_rn(ev[i], sv[i])), out_div);
     Vec8<T>::store(out + base, xv);
   }
   for (int64_t t = (nvec << 3) + tid; t < n; t += stride) {
-    const float s = to_f32(scale[map_index(t, plane, span)]);
+    const float s = to_f32(scale[map_index(t, mi)]);
     out[t] = from_f32<T>(__fdiv_rn(__fsub_rn(to_f32(x[t]), __fmul_rn(to_f32(eps[t]), s)), out_div));
   }
 }
@@ -309,6 +324,20 @@ scaled_residual_kernel(const T* __restrict__ x, const T* __restrict__ eps, const
 // vector count of the map kernels: 0 when a broadcast plane is not a multiple of the vector width
 static int64_t map_nvec(int64_t n, int64_t plane, int64_t span) {
   return (span != 0 && (plane & 7)) ? 0 : (n >> 3);
+}
+static int log2_exact(int64_t v) {                      // log2(v) if v is a power of two, else -1
+  if (v <= 0 || (v & (v - 1))) return -1;
+  int s = 0;
+  while ((int64_t(1) << s) != v) ++s;
+  return s;
+}
+static MapIdx map_idx(int64_t n, int64_t plane, int64_t span) {
+  MapIdx m;
+  m.plane = plane; m.span = span;
+  m.sh_plane = log2_exact(plane);
+  m.sh_span = (span != 0 && m.sh_plane >= 0) ? log2_exact(span) : -1;
+  m.small = n < (int64_t(1) << 31);
+  return m;
 }
 
 template <typename T>
@@ -322,7 +351,7 @@ static int launch_qsample_map(const void* x, const void* scale, void* out, const
   T* no = (T*)noise_out;
 #define LQM(SRC, EMIT, INJ)                                                                          \
   laplace_qsample_map_kernel<T, SRC, EMIT><<<grid, threads, 0, st>>>(                                \
-      (const T*)x, (const T*)scale, (T*)out, (const T*)(INJ), no, x_mul, key, offset, n, plane, span, nvec)
+      (const T*)x, (const T*)scale, (T*)out, (const T*)(INJ), no, x_mul, key, offset, n, map_idx(n, plane, span), nvec)
   if (noise_in) {
     if (no) LQM(SRC_NOISE, true, noise_in); else LQM(SRC_NOISE, false, noise_in);
   } else if (u_in) {
@@ -340,7 +369,7 @@ static int launch_scaled_residual(const void* x, const void* eps, const void* sc
   const int64_t nvec = map_nvec(n, plane, span), rest = n - (nvec << 3);
   const int grid = grid_for(nvec > rest ? nvec : rest, 256, 8);
   scaled_residual_kernel<T><<<grid, 256, 0, st>>>((const T*)x, (const T*)eps, (const T*)scale, (T*)out,
-                                                  out_div, n, plane, span, nvec);
+                                                  out_div, n, map_idx(n, plane, span), nvec);
   return check_launch();
 }
 

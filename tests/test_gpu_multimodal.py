@@ -9,9 +9,11 @@ from oracle import laplace as olap
 pytestmark = pytest.mark.gpu
 
 # (shape, channels of the scale map): latent shape of the reference, the vector path with a full and a
-# broadcast map, planes that are not a multiple of the vector width (scalar path), one element
+# broadcast map, planes that are not a multiple of the vector width (scalar path), one element,
+# vector path with planes / channel counts that are not powers of two (division instead of shifts)
 CASES = [((1, 4, 32, 32), 1), ((3, 4, 32, 32), 1), ((3, 4, 32, 32), 4), ((8, 4, 128, 128), 1),
-         ((2, 4, 5, 7), 1), ((2, 3, 5, 7), 3), ((1, 1, 1, 1), 1), ((2, 4, 3, 4), 1)]
+         ((2, 4, 5, 7), 1), ((2, 3, 5, 7), 3), ((1, 1, 1, 1), 1), ((2, 4, 3, 4), 1), ((2, 3, 6, 4), 1),
+         ((2, 4, 6, 12), 1)]
 
 
 def _ops():
