@@ -47,6 +47,15 @@ enum {
 enum { LDIFF_STATUS_PRED_RANGE = 1, LDIFF_STATUS_INST_RANGE = 2, LDIFF_STATUS_SW_INF = 4,
        LDIFF_STATUS_XCHG_TIMEOUT = 8, LDIFF_STATUS_LABEL_RANGE = 16 };
 
+/* Scheduling knobs of the whole pass (no effect on results).  A value set here applies to the launches
+ * issued after the call; 0 = off.  Before the first ldiff_tune of a knob its environment variable applies.
+ *  LDIFF_TUNE_ARGMAX_PERSIST_BLOCKS (env LDIFF_ARGMAX_PERSIST): ldiff_lift_argmax runs as that many persistent
+ *    512-thread blocks, each owning one SM's register file, instead of one block per band;
+ *  LDIFF_TUNE_DECODE_TAIL_SMS (env LDIFF_DT_SMS): ldiff_decode_tail_* sizes its one-wave grid for that many SMs
+ *    (the SMs the persistent lift+argmax leaves free) instead of the whole device. */
+enum { LDIFF_TUNE_ARGMAX_PERSIST_BLOCKS = 0, LDIFF_TUNE_DECODE_TAIL_SMS = 1, LDIFF_TUNE_COUNT = 2 };
+int ldiff_tune(int knob, int value);
+
 int ldiff_abi_version(void);
 const char* ldiff_strerror(int code);
 /* number of kernels this library has launched in the calling process */

@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libldiff_sm100.so")
 ABI_VERSION = 1
 
 F32, BF16, U8 = 0, 1, 2
+TUNE_ARGMAX_PERSIST_BLOCKS, TUNE_DECODE_TAIL_SMS = 0, 1
 STATUS_PRED_RANGE, STATUS_INST_RANGE, STATUS_SW_INF, STATUS_XCHG_TIMEOUT, STATUS_LABEL_RANGE = 1, 2, 4, 8, 16
 
 # name -> (restype, argtypes); mirrors include/ldiff.h one to one
@@ -20,6 +21,7 @@ SIGNATURES = {
     "ldiff_abi_version": (c_int, []),
     "ldiff_strerror": (c_char_p, [c_int]),
     "ldiff_launch_count": (c_int64, []),
+    "ldiff_tune": (c_int, [c_int, c_int]),
     "ldiff_laplace_qsample": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
                                       c_uint64, c_uint64, c_int64, c_int, c_void_p]),
     "ldiff_laplace_qsample_map": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,

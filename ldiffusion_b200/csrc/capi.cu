@@ -1,4 +1,6 @@
 // Library-level entry points of libldiff_sm100.so.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace ldiff {
@@ -16,6 +18,22 @@ int sm_count() {
       cached = 148;                                   // B200
   }
   return cached;
+}
+
+// tuning knobs: -1 = not set yet (the environment variable, else the built-in default, is taken on first use)
+static int g_tune[LDIFF_TUNE_COUNT] = {-1, -1};
+static const char* const kTuneEnv[LDIFF_TUNE_COUNT] = {"LDIFF_ARGMAX_PERSIST", "LDIFF_DT_SMS"};
+static const int kTuneDefault[LDIFF_TUNE_COUNT] = {0, 0};
+
+int tune_get(int knob) {
+  int v = __atomic_load_n(&g_tune[knob], __ATOMIC_RELAXED);
+  if (v < 0) {
+    const char* e = getenv(kTuneEnv[knob]);
+    v = e ? atoi(e) : kTuneDefault[knob];
+    if (v < 0) v = 0;
+    __atomic_store_n(&g_tune[knob], v, __ATOMIC_RELAXED);
+  }
+  return v;
 }
 
 // dst plane b (dst + b*dst_stride) = src plane b (src + b*n), n bytes each, 16 bytes per thread
@@ -43,6 +61,12 @@ extern "C" int ldiff_copy_planes_u8(const uint8_t* src, uint8_t* dst, int64_t n,
   ldiff::copy_planes_kernel<<<dim3((unsigned)bx, (unsigned)B), 256, 0, (cudaStream_t)stream>>>(src, dst, n,
                                                                                              dst_stride);
   return ldiff::check_launch();
+}
+
+extern "C" int ldiff_tune(int knob, int value) {
+  if (knob < 0 || knob >= LDIFF_TUNE_COUNT || value < 0) return LDIFF_EINVAL;
+  __atomic_store_n(&ldiff::g_tune[knob], value, __ATOMIC_RELAXED);
+  return LDIFF_OK;
 }
 
 extern "C" int ldiff_abi_version(void) { return LDIFF_ABI_VERSION; }

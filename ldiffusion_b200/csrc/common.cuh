@@ -13,6 +13,9 @@ extern unsigned long long g_launches;          // defined in capi.cu
 
 int sm_count();                                // cached per process (current device)
 
+// ldiff_tune knobs (capi.cu); first use reads the environment (LDIFF_ARGMAX_PERSIST, LDIFF_DT_SMS)
+int tune_get(int knob);
+
 inline int check_launch() {
   __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED);
   return cudaPeekAtLastError() == cudaSuccess ? LDIFF_OK : LDIFF_ELAUNCH;

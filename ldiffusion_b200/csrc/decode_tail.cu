@@ -209,7 +209,9 @@ static int launch_decode_tail(const void* img, uint8_t* rgb, uint8_t* gray, int 
     if (occ == 0 && cudaOccupancyMaxActiveBlocksPerMultiprocessor(                                    \
                         &occ, decode_tail_vec16_kernel<T, R, G, N>, threads, 0) != cudaSuccess)       \
       occ = 4;                                                                                        \
-    int cap = (sm_count() * (occ > 0 ? occ : 4)) / B;                                                 \
+    const int sms = (tune_get(LDIFF_TUNE_DECODE_TAIL_SMS) > 0 && tune_get(LDIFF_TUNE_DECODE_TAIL_SMS) < sm_count())   \
+                        ? tune_get(LDIFF_TUNE_DECODE_TAIL_SMS) : sm_count();                          \
+    int cap = (sms * (occ > 0 ? occ : 4)) / B;                                                        \
     if (cap < 1) cap = 1;                                                                             \
     const int iters = (need + cap - 1) / cap;                                                         \
     const dim3 grid((need + iters - 1) / iters, B);                                                   \

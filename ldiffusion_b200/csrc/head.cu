@@ -146,16 +146,15 @@ __device__ __forceinline__ int tie_acc(const float (&v)[K], float thr, std::inte
 // RANKS: |v' - v_ref| <= 5 * 2^-24 * M (M = the column's largest |logit|; derivation in DESIGN.md a-5),
 // the near-tie gap is widened by 2^-20 * M >= twice that bound, and every pixel inside the gap is
 // resolved by the pinned softmax on the reference's own roundings exactly as before.
-template <int K, int COLS, int MINB, bool DIFF = false>
-__global__ void __launch_bounds__(256, MINB)   // the cold fp64 exp may spill, the hot loop must not
-lift_argmax_kernel(const float* __restrict__ logits, uint8_t* __restrict__ mask, AxisH ay, AxisH ax) {
-  __shared__ float2 s_l[kBand];                          // vertical weights (l0, l1) of the band's rows
-  __shared__ uint32_t s_q[8][kQueue];                    // per-warp queue of near-tie pixels (row, column)
-  __shared__ int s_qn[8];
+// One band of one image for one block: x-block bx, source row iy (the band is every output row whose
+// upper tap is iy, so the whole band shares one source row pair and T/U are gathered exactly once),
+// image b.  NW = warps per block.  s_l: vertical weights (l0, l1) of the band's rows; s_q / s_qn: per-warp
+// queue of near-tie pixels (row, column).
+template <int K, int COLS, bool DIFF, int NW>
+__device__ __forceinline__ void
+lift_argmax_band(const float* __restrict__ logits, uint8_t* __restrict__ mask, const AxisH& ay, const AxisH& ax,
+                 const int bx, const int iy, const int b, float2* s_l, uint32_t (*s_q)[kQueue], int* s_qn) {
   const int warp_in_block = threadIdx.x >> 5;
-  // blockIdx.y = a source row iy; the band is every output row whose upper tap is iy, so the
-  // whole band shares one source row pair and T/U are gathered exactly once
-  const int iy = blockIdx.y;
   auto first_row = [&](int i) {
     if (i <= 0) return 0;
     int y = (int)ceilf(((float)i + 0.5f) / ay.scale - 0.5f);
@@ -167,17 +166,16 @@ lift_argmax_kernel(const float* __restrict__ logits, uint8_t* __restrict__ mask,
   const int Y0 = first_row(iy);
   const int Y1 = (iy + 1 >= ay.in) ? ay.out : first_row(iy + 1);
   if (Y0 >= Y1) return;                                  // (block-uniform)
-  if (threadIdx.x < 8) s_qn[threadIdx.x] = 0;
+  if (threadIdx.x < NW) s_qn[threadIdx.x] = 0;
   if (threadIdx.x < Y1 - Y0) {
     const TapH t = tap(ay, Y0 + threadIdx.x);
     s_l[threadIdx.x] = make_float2(t.l0, t.l1);
   }
   const int i0 = min(iy, ay.in - 1), i1 = min(iy + 1, ay.in - 1);   // the band's source row pair
-  const int b = blockIdx.z;
   const int plane = ay.in * ax.in;
   const float* lb = logits + (int64_t)b * K * plane;
   __syncthreads();
-  const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * COLS;
+  const int x0 = (bx * (int)blockDim.x + (int)threadIdx.x) * COLS;
   const bool active = x0 < ax.out;                       // inactive lanes still help in the epilogue
   uint8_t* out = mask + ((int64_t)b * ay.out + Y0) * ax.out + x0;
 
@@ -320,7 +318,7 @@ lift_argmax_kernel(const float* __restrict__ logits, uint8_t* __restrict__ mask,
   // in one thread); each lane gathers the 4K logits of its pixel with independent loads.
   __syncwarp();
   const int nq = min(s_qn[warp_in_block], kQueue);
-  const int xblock = blockIdx.x * blockDim.x * COLS;
+  const int xblock = bx * (int)blockDim.x * COLS;
   for (int e = (int)(threadIdx.x & 31); e < nq; e += 32) {
     const uint32_t ent = s_q[warp_in_block][e];
     const int r = (int)(ent >> 16), x = xblock + (int)(ent & 0xffffu);
@@ -343,6 +341,35 @@ lift_argmax_kernel(const float* __restrict__ logits, uint8_t* __restrict__ mask,
         if (x0 + c < ax.out)
           mask[((int64_t)b * ay.out + Y0 + rr) * ax.out + x0 + c] = (uint8_t)exact_pixel(
               lb, K, plane, ax.in, i0, i1, s_l[rr].x, s_l[rr].y, tx[c].i0, tx[c].i1, tx[c].l0, tx[c].l1);
+  }
+}
+
+// grid = (x-blocks, source rows, images): one band per block
+template <int K, int COLS, int MINB, bool DIFF = false>
+__global__ void __launch_bounds__(256, MINB)   // the cold fp64 exp may spill, the hot loop must not
+lift_argmax_kernel(const float* __restrict__ logits, uint8_t* __restrict__ mask, AxisH ay, AxisH ax) {
+  __shared__ float2 s_l[kBand];
+  __shared__ uint32_t s_q[8][kQueue];
+  __shared__ int s_qn[8];
+  lift_argmax_band<K, COLS, DIFF, 8>(logits, mask, ay, ax, blockIdx.x, blockIdx.y, blockIdx.z, s_l, s_q, s_qn);
+}
+
+// Persistent form: a FEW blocks of 512 threads x 128 registers — each one owns a whole SM's register
+// file, so the grid occupies exactly gridDim.x SMs — walk all (x-block, source row, image) bands.  Inside
+// the pass this confines the issue-bound lift+argmax to a corner of the chip for the length of the pass
+// instead of letting its register-heavy blocks take turns with the bandwidth-bound kernels on every SM.
+template <int K, bool DIFF>
+__global__ void __launch_bounds__(512, 1)
+lift_argmax_persistent_kernel(const float* __restrict__ logits, uint8_t* __restrict__ mask, AxisH ay, AxisH ax,
+                              int nxb, int B) {
+  __shared__ float2 s_l[kBand];
+  __shared__ uint32_t s_q[16][kQueue];
+  __shared__ int s_qn[16];
+  const int items = nxb * ay.in * B;
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    if (item != (int)blockIdx.x) __syncthreads();        // the previous band's epilogue has read s_l / s_q
+    const int bx = item % nxb, rest = item / nxb;
+    lift_argmax_band<K, 2, DIFF, 16>(logits, mask, ay, ax, bx, rest % ay.in, rest / ay.in, s_l, s_q, s_qn);
   }
 }
 
@@ -608,6 +635,19 @@ extern "C" int ldiff_lift_argmax(const float* logits, uint8_t* mask, int B, int 
     // experiment knob: unused dynamic shared memory that caps how many of these register-heavy CTAs
     // are resident per SM, leaving register file for the bandwidth-bound kernels they run beside
     static const int pad = [] { const char* e = getenv("LDIFF_ARGMAX_SMEM_PAD"); return e ? atoi(e) : 0; }();
+    // persistent form (ldiff_tune / LDIFF_ARGMAX_PERSIST blocks): needs two columns per thread and the DIFF lerp
+    const int persist = tune_get(LDIFF_TUNE_ARGMAX_PERSIST_BLOCKS);
+    if (persist > 0 && K >= 2 && K <= 12 && (W % 2) == 0) {
+      const int nxb = (W / 2 + 511) / 512;
+      const int items = nxb * h * B;
+      const int nblk = persist < items ? persist : items;
+      switch (K) {
+#define LAP(KK) case KK: lift_argmax_persistent_kernel<KK, true><<<nblk, 512, 0, st>>>(logits, mask, ay, ax, nxb, B); break;
+        LAP(2) LAP(3) LAP(4) LAP(5) LAP(6) LAP(7) LAP(8) LAP(9) LAP(10) LAP(11) LAP(12)
+#undef LAP
+      }
+      return check_launch();
+    }
     switch (K) {
 #define LA2(KK) case KK:                                                                               \
       if (variant == 0) {                                                                              \

@@ -101,6 +101,10 @@ class HotPath:
         self.cell_b = torch.zeros(num_classes, device=dev)
         self.status = ops.status_word(dev)
         self.exchange = None                                               # set by attach_exchange (multi-GPU)
+        # experiment (tools/pass_persist.py): hold the decode tails back until the head's logits exist, so a
+        # persistent lift+argmax (ldiff_tune) is resident before the first decode tail occupies every SM
+        self.decode_after_head = os.environ.get("LDIFF_PASS_DECODE_AFTER_HEAD", "0") == "1"
+        self._head_done = torch.cuda.Event()
 
     def attach_exchange(self, exchange, deferred: bool = True):
         """Multi-GPU: fuse the cross-rank sum of the two confusion matrices into the pass
@@ -160,6 +164,9 @@ class HotPath:
             self._chain_lifts(inp)
         with torch.cuda.stream(side[2]), _nvtx("ldiff.tissue"):
             self._chain_tissue(inp)
+        if concurrent and self.decode_after_head:
+            # the persistent lift+argmax must get its SMs before the first decode tail fills the chip
+            side[4].wait_event(self._head_done)
         with torch.cuda.stream(side[3]), _nvtx("ldiff.cell"):
             self._chain_cell(inp)
         with torch.cuda.stream(side[4]), _nvtx("ldiff.decode_tails"):      # the bandwidth-heavy chain
@@ -217,6 +224,8 @@ class HotPath:
 
     def _chain_tissue(self, inp):
         ops._head_logits(inp.head_feat, self.head_w, self.head_b, self.logits)
+        if self.decode_after_head:
+            self._head_done.record(torch.cuda.current_stream(self.device))
         ops._lift_argmax(self.logits, self.mask_tissue)
         self._confusion(self.mask_tissue, inp.gt, 0)
 
