@@ -20,7 +20,10 @@ lut = torch.randint(0, 11, (8, 801), device=dev, dtype=torch.uint8)
 C = torch.zeros(12, 11, dtype=torch.int64, device=dev)
 x = inp.latents
 o = torch.empty_like(x)
-for it in range(3):
+sc = torch.rand(8, 1, 128, 128, device=dev).to(dt)
+cw = (torch.randn(11, 256, device=dev) / 16).to(dt)
+ids = torch.arange(1, 801, dtype=torch.int32, device=dev)
+for it in range(2):
     ops.decode_tail_gray(inp.decoded[it % 2], want_rgb=False, gray_out=planes[:, it])
     ops.decode_tail_gray(inp.decoded[it % 2], rgb_out=rgb, gray_out=planes[:, it])
     ops.bilinear_lift(src, (1024, 1024), out=up)
@@ -31,5 +34,8 @@ for it in range(3):
     ops.confusion_hist(mask.view(-1), inp.gt.view(-1), 11, out=C)
     ops.laplace_qsample(x, 0.9, seed=1, offset=it, out=o)
     ops.plms_step(x, [inp.eps[0], inp.eps[1], inp.eps[0], inp.eps[1]], 4, 1.01, 0.02, 0.9, out=o)
+    ops.laplace_qsample_map(x, sc, seed=1, offset=it, x_mul=0.18215, out=o)
+    ops.scaled_residual(x, inp.eps[0], sc, out_div=0.18215, out=o)
+    ops.cell_classify(inp.inst_feats, cw, None, ids, 801)
 torch.cuda.synchronize()
 print("done")
