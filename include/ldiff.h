@@ -52,8 +52,11 @@ enum { LDIFF_STATUS_PRED_RANGE = 1, LDIFF_STATUS_INST_RANGE = 2, LDIFF_STATUS_SW
  *  LDIFF_TUNE_ARGMAX_PERSIST_BLOCKS (env LDIFF_ARGMAX_PERSIST): ldiff_lift_argmax runs as that many persistent
  *    512-thread blocks, each owning one SM's register file, instead of one block per band;
  *  LDIFF_TUNE_DECODE_TAIL_SMS (env LDIFF_DT_SMS): ldiff_decode_tail_* sizes its one-wave grid for that many SMs
- *    (the SMs the persistent lift+argmax leaves free) instead of the whole device. */
-enum { LDIFF_TUNE_ARGMAX_PERSIST_BLOCKS = 0, LDIFF_TUNE_DECODE_TAIL_SMS = 1, LDIFF_TUNE_COUNT = 2 };
+ *    (the SMs the persistent lift+argmax leaves free) instead of the whole device;
+ *  LDIFF_TUNE_DECODE_TAIL_TMA (env LDIFF_DT_TMA): bf16 decode tails run the bulk-TMA staged persistent kernel
+ *    (not yet measured: a round-2 candidate, off by default). */
+enum { LDIFF_TUNE_ARGMAX_PERSIST_BLOCKS = 0, LDIFF_TUNE_DECODE_TAIL_SMS = 1, LDIFF_TUNE_DECODE_TAIL_TMA = 2,
+       LDIFF_TUNE_COUNT = 3 };
 int ldiff_tune(int knob, int value);
 
 int ldiff_abi_version(void);

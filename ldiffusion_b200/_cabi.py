@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libldiff_sm100.so")
 ABI_VERSION = 1
 
 F32, BF16, U8 = 0, 1, 2
-TUNE_ARGMAX_PERSIST_BLOCKS, TUNE_DECODE_TAIL_SMS = 0, 1
+TUNE_ARGMAX_PERSIST_BLOCKS, TUNE_DECODE_TAIL_SMS, TUNE_DECODE_TAIL_TMA = 0, 1, 2
 STATUS_PRED_RANGE, STATUS_INST_RANGE, STATUS_SW_INF, STATUS_XCHG_TIMEOUT, STATUS_LABEL_RANGE = 1, 2, 4, 8, 16
 
 # name -> (restype, argtypes); mirrors include/ldiff.h one to one

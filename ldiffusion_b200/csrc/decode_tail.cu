@@ -160,6 +160,126 @@ decode_tail_vec16_kernel(const T* __restrict__ img, uint8_t* __restrict__ rgb,
   }
 }
 
+// ----------------------------------------------------------------------------
+// Bulk-TMA staged form (bf16 storage; opt-in through ldiff_tune(LDIFF_TUNE_DECODE_TAIL_TMA) / LDIFF_DT_TMA
+// until it has been measured — round-2 candidate).  Why: the pass experiments of round 1
+// (profiles/r01_pass_persist.txt) show the register-staged kernel above losing bandwidth in proportion to
+// the SMs it is given: its bytes in flight are tied to resident threads (6 blocks x 256 threads x 96 B).
+// Here a persistent CTA keeps kDtStages tiles of 3 x kDtTile pixels in flight through 1-D bulk copies
+// (cp.async.bulk + mbarrier complete_tx; no registers, no address arithmetic per load), and the threads
+// only read shared memory: 72 KB in flight per CTA whatever the occupancy.  Same arithmetic functions as
+// above, so the bytes written are identical by construction.
+// ----------------------------------------------------------------------------
+constexpr int kDtTile = 4096;      // pixels per tile = 256 threads x 16 pixels
+constexpr int kDtStages = 4;       // 4 x 3 x 8 KB = 96 KB of shared memory per CTA (two CTAs per SM)
+
+__device__ __forceinline__ uint32_t dt_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void dt_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(dt_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void dt_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(dt_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void dt_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "DT_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DT_DONE;\n\t"
+      "bra DT_WAIT;\n\t"
+      "DT_DONE:\n\t}" ::"r"(dt_smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void dt_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   dt_smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(dt_smem_u32(bar))
+               : "memory");
+}
+
+// 16 consecutive bf16 pixels of one plane, staged in shared memory -> 16 magic-float bit patterns
+__device__ __forceinline__ void quant16_staged(const __nv_bfloat16* p, uint32_t (&q)[16]) {
+  const uint4 a = *reinterpret_cast<const uint4*>(p);
+  const uint4 b = *(reinterpret_cast<const uint4*>(p) + 1);
+  const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) Quant<__nv_bfloat16>::packed2(w[i], q[2 * i], q[2 * i + 1]);
+}
+
+// grid = persistent CTAs; tile t of the job = image t / tiles_per_img, pixels (t % tiles_per_img) * kDtTile ...
+template <bool RGB, bool GRAY>
+__global__ void __launch_bounds__(256, 2)
+decode_tail_tma_kernel(const __nv_bfloat16* __restrict__ img, uint8_t* __restrict__ rgb,
+                       uint8_t* __restrict__ gray, int64_t hw, int tiles_per_img, int total_tiles,
+                       int64_t gray_batch_stride) {
+  extern __shared__ __align__(128) uint8_t dt_smem[];            // [kDtStages][3][kDtTile] bf16
+  __shared__ __align__(8) uint64_t full[kDtStages];
+  __nv_bfloat16* buf = reinterpret_cast<__nv_bfloat16*>(dt_smem);
+  const int tid = threadIdx.x;
+  constexpr uint32_t kPlaneBytes = kDtTile * sizeof(__nv_bfloat16);
+
+  // k-th tile of this CTA -> stage k % kDtStages (one thread issues; completion lands on full[stage])
+  auto issue = [&](int k) {
+    const int t = blockIdx.x + k * gridDim.x;
+    if (t >= total_tiles) return;
+    const int s = k % kDtStages;
+    const int b = t / tiles_per_img;
+    const int64_t p0 = (int64_t)(t - b * tiles_per_img) * kDtTile;
+    dt_mbar_expect_tx(&full[s], 3 * kPlaneBytes);
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      dt_bulk_g2s(buf + (s * 3 + c) * kDtTile, img + ((int64_t)b * 3 + c) * hw + p0, kPlaneBytes, &full[s]);
+  };
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kDtStages; ++s) dt_mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+#pragma unroll
+    for (int k = 0; k < kDtStages; ++k) issue(k);
+  }
+  for (int k = 0;; ++k) {
+    const int t = blockIdx.x + k * gridDim.x;
+    if (t >= total_tiles) break;                                 // (block-uniform)
+    const int s = k % kDtStages;
+    const int64_t b = t / tiles_per_img;
+    const int64_t p = (int64_t)(t - (int)b * tiles_per_img) * kDtTile + tid * 16;
+    dt_mbar_wait(&full[s], (uint32_t)(k / kDtStages) & 1u);
+    uint32_t q[3][16];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) quant16_staged(buf + (s * 3 + c) * kDtTile + tid * 16, q[c]);
+    if (GRAY) {
+      uint32_t w[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        w[j] = pack4<2>(luma_sum(q[0][4 * j], q[1][4 * j], q[2][4 * j]),
+                        luma_sum(q[0][4 * j + 1], q[1][4 * j + 1], q[2][4 * j + 1]),
+                        luma_sum(q[0][4 * j + 2], q[1][4 * j + 2], q[2][4 * j + 2]),
+                        luma_sum(q[0][4 * j + 3], q[1][4 * j + 3], q[2][4 * j + 3]));
+      __stcs(reinterpret_cast<uint4*>(gray + b * gray_batch_stride + p), make_uint4(w[0], w[1], w[2], w[3]));
+    }
+    if (RGB) {
+      uint32_t w[12];
+#pragma unroll
+      for (int j = 0; j < 12; ++j)
+        w[j] = pack4<0>(q[(4 * j) % 3][(4 * j) / 3], q[(4 * j + 1) % 3][(4 * j + 1) / 3],
+                        q[(4 * j + 2) % 3][(4 * j + 2) / 3], q[(4 * j + 3) % 3][(4 * j + 3) / 3]);
+      uint4* o = reinterpret_cast<uint4*>(rgb + (b * hw + p) * 3);
+      __stcs(o, make_uint4(w[0], w[1], w[2], w[3]));
+      __stcs(o + 1, make_uint4(w[4], w[5], w[6], w[7]));
+      __stcs(o + 2, make_uint4(w[8], w[9], w[10], w[11]));
+    }
+    __syncthreads();                                             // every thread has read stage s
+    if (tid == 0) {
+      // the refill is an async-proxy write over memory just read through the generic proxy
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      issue(k + kDtStages);
+    }
+  }
+}
+
 // any H*W (no alignment assumptions): one pixel per thread
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -195,6 +315,30 @@ static int launch_decode_tail(const void* img, uint8_t* rgb, uint8_t* gray, int 
   const int threads = 256;
   const bool vec_ok = (hw % 16 == 0) && aligned16(img) && aligned16(rgb) && aligned16(gray) &&
                       aligned16(na.out) && (gray_batch_stride % 16 == 0);
+  if (vec_ok && !na.out && sizeof(T) == 2 && (hw % kDtTile) == 0 && tune_get(LDIFF_TUNE_DECODE_TAIL_TMA) > 0 &&
+      (int64_t)B * (hw / kDtTile) <= 0x7fffffff) {
+    const int tiles_per_img = (int)(hw / kDtTile), total = B * tiles_per_img;
+    const size_t smem = (size_t)kDtStages * 3 * kDtTile * sizeof(T);
+    const int cap = 2 * sm_count();
+    const int grid = total < cap ? total : cap;
+    const __nv_bfloat16* p = (const __nv_bfloat16*)img;
+#define DTT(R, G)                                                                                       \
+  do {                                                                                                  \
+    static bool attr = false;                                                                           \
+    if (!attr) {                                                                                        \
+      cudaFuncSetAttribute(decode_tail_tma_kernel<R, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                           (int)smem);                                                                  \
+      attr = true;                                                                                      \
+    }                                                                                                   \
+    decode_tail_tma_kernel<R, G><<<grid, 256, smem, st>>>(p, rgb, gray, hw, tiles_per_img, total,       \
+                                                         gray_batch_stride);                            \
+  } while (0)
+    if (rgb && gray) DTT(true, true);
+    else if (gray) DTT(false, true);
+    else DTT(true, false);
+#undef DTT
+    return check_launch();
+  }
   if (vec_ok) {
     if ((hw >> 4) > 0x7fffffff / 2 || B > 65535) return LDIFF_EUNSUPPORTED;
     const int gpi = (int)(hw >> 4);

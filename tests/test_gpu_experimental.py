@@ -1,0 +1,61 @@
+"""GPU parity of the opt-in kernel forms behind ``ldiff_tune`` (include/ldiff.h).  The persistent
+lift+argmax was measured in round 1 (profiles/r01_pass_persist.txt); the bulk-TMA staged decode tail has
+NOT run on a GPU yet, so this file only runs when asked to (``LDIFF_TEST_EXPERIMENTAL=1``): an unproven
+mbarrier pipeline must not be able to hang the default suite."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import decode_tail as odt
+from oracle import head as ohead
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("LDIFF_TEST_EXPERIMENTAL", "0") != "1",
+                                 reason="experimental kernels: set LDIFF_TEST_EXPERIMENTAL=1")]
+
+
+@pytest.fixture
+def tune():
+    from ldiffusion_b200 import _cabi
+    lib = _cabi.lib()
+    yield lambda knob, value: lib.ldiff_tune(knob, value)
+    for knob in range(3):
+        lib.ldiff_tune(knob, 0)
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("shape", [(1, 3, 64, 64), (2, 3, 128, 96), (8, 3, 1024, 1024), (3, 3, 64, 192)])
+@pytest.mark.parametrize("want_rgb", [False, True])
+def test_decode_tail_tma_bit_exact(tune, shape, want_rgb):
+    """bf16 images whose planes are a multiple of 4096 pixels take the bulk-TMA staged kernel."""
+    from ldiffusion_b200 import _cabi, ops
+    g = torch.Generator().manual_seed(sum(shape))
+    img = torch.empty(shape).uniform_(-1.3, 1.3, generator=g).bfloat16()
+    tune(_cabi.TUNE_DECODE_TAIL_TMA, 0)
+    rgb0, gray0 = ops.decode_tail_gray(img.cuda(), want_rgb=want_rgb)
+    tune(_cabi.TUNE_DECODE_TAIL_TMA, 1)
+    rgb1, gray1 = ops.decode_tail_gray(img.cuda(), want_rgb=want_rgb)
+    torch.cuda.synchronize()
+    assert torch.equal(gray0, gray1)
+    if want_rgb:
+        assert torch.equal(rgb0, rgb1)
+        if shape[-1] * shape[-2] <= 128 * 96:
+            assert np.array_equal(rgb1.cpu().numpy(), odt.decode_tail_chain(img))
+    # slot of a pixel-vector tensor (strided gray planes)
+    planes = torch.zeros(shape[0], 3, shape[2], shape[3], dtype=torch.uint8, device="cuda")
+    ops.decode_tail_gray(img.cuda(), want_rgb=False, gray_out=planes[:, 1])
+    assert torch.equal(planes[:, 1], gray0) and int(planes[:, 0].max()) == 0 and int(planes[:, 2].max()) == 0
+
+
+@pytest.mark.timeout(120)
+def test_lift_argmax_persistent_bit_exact(tune):
+    from ldiffusion_b200 import _cabi, ops
+    g = torch.Generator().manual_seed(3)
+    for K, shape, size in ((11, (2, 32, 32), (1024, 1024)), (6, (1, 16, 16), (512, 512)), (7, (3, 8, 8), (128, 96))):
+        logits = torch.randn((shape[0], K) + shape[1:], generator=g)
+        tune(_cabi.TUNE_ARGMAX_PERSIST_BLOCKS, 52)
+        got = ops.lift_argmax(logits.cuda(), size)
+        tune(_cabi.TUNE_ARGMAX_PERSIST_BLOCKS, 0)
+        assert np.array_equal(got.cpu().numpy(), ohead.lift_argmax_spec(logits.numpy(), size))
