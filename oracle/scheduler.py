@@ -13,7 +13,9 @@ algorithm with the SD-v1.5 ``scheduler_config.json`` values::
 Anchors: the reference's call sites (``segmentor.py:100-104``, ``:438-445``,
 ``:520-527``; ``utils.py:196-202``; ``pixel_latent_vector.py:74-79``;
 ``sample.py:57-64``; ``ldiffusion.py:198,229-234``) and the known-answer
-constants of SURVEY.md §8(a-2), checked in ``tests/test_oracle_scheduler.py``.
+constants of SURVEY.md §8(a-2), checked in ``tests/test_oracle_ops.py`` together with two
+first-principles pins (the published transfer formula in fp64; exactness of the whole loop,
+quirks included, for a perfect noise prediction).
 
 All tensor arithmetic is torch-CPU fp32, op by op, in the published order, so
 the CUDA ``plms_step`` kernel (which uses round-to-nearest intrinsics in the

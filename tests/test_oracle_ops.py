@@ -67,6 +67,44 @@ def test_plms_state_machine_quirks():
     assert len(outs) == 5 and torch.equal(outs[1], x2)
 
 
+@pytest.mark.parametrize("n", [1, 2, 4, 5, 10, 50])
+def test_plms_loop_is_exact_for_a_perfect_noise_prediction(n):
+    """First-principles pin of the restated scheduler (diffusers itself is not installable here): every
+    Adams-Bashforth weight set sums to one and the transfer step is the deterministic (DDIM) update, so
+    with eps == the true noise the whole loop — duplicated second timestep, un-stored second output,
+    stashed first sample, ``final_alpha_cumprod`` at the end — must carry
+    x_t0 = sqrt(a_t0) x0 + sqrt(1 - a_t0) eps to sqrt(a_final) x0 + sqrt(1 - a_final) eps."""
+    s = PNDMOracle()
+    s.set_timesteps(n)
+    g = torch.Generator().manual_seed(n)
+    x0 = torch.randn(256, generator=g, dtype=torch.float64) * 5.5
+    eps = torch.randn(256, generator=g, dtype=torch.float64)
+    a = s.alphas_cumprod.double()
+    t0 = int(s.timesteps[0])
+    x = (a[t0].sqrt() * x0 + (1 - a[t0]).sqrt() * eps).float()
+    for t in s.timesteps:
+        x = s.step(eps.float(), t, s.scale_model_input(x, t))
+    af = s.final_alpha_cumprod.double()
+    want = af.sqrt() * x0 + (1 - af).sqrt() * eps
+    assert float((x.double() - want).abs().max()) < 2e-5
+
+
+def test_transfer_step_equals_the_published_formula():
+    """PNDM (Liu et al., ICLR 2022, eq. 11) in fp64:
+    x_{t-d} = sqrt(a_p / a_t) x_t - (a_p - a_t) / (sqrt(a_t) (sqrt((1 - a_p) a_t) + sqrt((1 - a_t) a_p))) eps."""
+    s = PNDMOracle()
+    s.set_timesteps(10)
+    a = s.alphas_cumprod.double()
+    g = torch.Generator().manual_seed(0)
+    x, e = torch.randn(128, generator=g) * 5.5, torch.randn(128, generator=g)
+    for t, p in ((901, 801), (501, 401), (101, 1), (1, -99), (999, 0)):
+        got = s._get_prev_sample(x, t, p, e).double()
+        a_t, a_p = a[t], (a[p] if p >= 0 else s.final_alpha_cumprod.double())
+        want = (a_p / a_t).sqrt() * x.double() - (a_p - a_t) / (
+            a_t.sqrt() * (((1 - a_p) * a_t).sqrt() + ((1 - a_t) * a_p).sqrt())) * e.double()
+        torch.testing.assert_close(got, want, rtol=2e-6, atol=2e-6)
+
+
 def test_set_timesteps_resets_state():
     s = PNDMOracle(); s.set_timesteps(4)
     s.step(torch.zeros(2), 751, torch.ones(2))

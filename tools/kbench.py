@@ -7,7 +7,7 @@ import os
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from ldiffusion_b200 import ops, LaplacePLMSScheduler
+from ldiffusion_b200 import ops
 
 PEAK = 6546.2
 
@@ -93,7 +93,6 @@ def main():
     lut = torch.randint(0, 11, (800,), device=dev, dtype=torch.uint8)
     us = timeit(lambda i: ops.lut_paint(inst, lut), 1)
     res["lut_paint"] = (us, 8 * 1024 * 1024 * 5 / us / 1e3, 8 * 1024 * 1024 * 5 / us / 1e3 / PEAK)
-    import numpy as np
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
     from test_gpu_head_metrics import _blob_labels
     for nimg in (8, 64):
