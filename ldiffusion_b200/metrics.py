@@ -200,6 +200,50 @@ def global_dice_from_counts(tp, fp, fn):
     return per_class, np.nanmean(per_class)
 
 
+def nnunet_label_metrics_from_confusion(C: np.ndarray, labels, ignore_label=None) -> dict:
+    """nnU-Net's per-file metrics (``evaluation/evaluate_predictions.py:77-120``: ``compute_tp_fp_fn_tn`` +
+    ``compute_metrics``) for plain integer labels, from the ``(K+1) x K`` confusion matrix (rows = reference
+    label, row K = every reference value outside ``[0, K)``; columns = predicted label).
+
+    ``ignore_label``: reference pixels with that value are left out of every count (``:97,79-82``); it is
+    either a label below K or the only out-of-range value of the reference map (nnU-Net's convention: the
+    ignore label is the highest one), in which case it is row K.  Returns ``{label: {"Dice", "IoU", "FP",
+    "TP", "FN", "TN", "n_pred", "n_ref"}}`` with the reference's conventions (Dice = IoU = nan when
+    tp + fp + fn == 0)."""
+    C = np.asarray(C, dtype=np.int64)
+    K = C.shape[1]
+    used = np.ones(K + 1, dtype=bool)
+    if ignore_label is not None:
+        used[min(int(ignore_label), K)] = False
+    Cu = C[used]
+    total = int(Cu.sum())
+    out = {}
+    for r in labels:
+        r = int(r)
+        if not 0 <= r < K:
+            raise ValueError(f"label {r} outside [0, {K})")
+        tp = int(C[r, r]) if used[r] else 0
+        fp = int(Cu[:, r].sum()) - tp
+        fn = (int(C[r].sum()) - tp) if used[r] else 0
+        tn = total - tp - fp - fn
+        m = {}
+        if tp + fp + fn == 0:
+            m["Dice"], m["IoU"] = np.nan, np.nan
+        else:
+            m["Dice"], m["IoU"] = 2 * tp / (2 * tp + fp + fn), tp / (tp + fp + fn)
+        m.update(FP=fp, TP=tp, FN=fn, TN=tn, n_pred=fp + tp, n_ref=fn + tp)
+        out[r] = m
+    return out
+
+
+def nnunet_compute_metrics(seg_ref: torch.Tensor, seg_pred: torch.Tensor, labels, ignore_label=None) -> dict:
+    """``compute_metrics`` of nnU-Net's evaluator on two label maps already on the device: one histogram
+    launch instead of four boolean-mask reductions per label (``evaluate_predictions.py:97-119``)."""
+    K = max(int(r) for r in labels) + 1
+    C = confusion_matrix(seg_pred, seg_ref, K)
+    return nnunet_label_metrics_from_confusion(_to_host(C), labels, ignore_label)
+
+
 def per_image_confusion(preds: torch.Tensor, gts: torch.Tensor, num_classes: int) -> torch.Tensor:
     """uint8 [N,H,W] x2 -> int64 [N,(K+1),K] in one launch, no syncs."""
     return ops.confusion_hist_batched(preds, gts, int(num_classes))

@@ -50,3 +50,19 @@ def load():
         sys.stdout = old
         devnull.close()
     return ref_utils, ref_evaluate
+
+
+def load_functions(path, names):
+    """Compile only the named top-level functions of a reference module whose imports cannot be satisfied
+    here (e.g. nnU-Net's evaluator pulls in batchgenerators and SimpleITK) — the functions' own source, run
+    as is, with numpy and the typing names they use in scope."""
+    import ast
+    from typing import List, Tuple, Union
+
+    import numpy as np
+    tree = ast.parse(open(path).read())
+    ns = {"np": np, "List": List, "Tuple": Tuple, "Union": Union}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in names:
+            exec(compile(ast.Module([node], []), path, "exec"), ns)
+    return [ns[n] for n in names]

@@ -133,6 +133,24 @@ def nnunet_golden():
     print("nnunet counts saved")
 
 
+def nnunet_eval_golden():
+    """Second pin of the confusion tier: nnU-Net's evaluator (evaluation/evaluate_predictions.py:67-119)."""
+    path = os.path.join(_refshim.REF_ROOT, "model", "nnunetv2", "evaluation", "evaluate_predictions.py")
+    to_mask, counts = _refshim.load_functions(path, ["region_or_label_to_mask", "compute_tp_fp_fn_tn"])
+    rng = np.random.default_rng(77)
+    K = 6
+    ref = rng.integers(0, K + 1, (3, 40, 52)).astype(np.uint8)        # value K = the ignore label
+    pred = rng.integers(0, K, (3, 40, 52)).astype(np.uint8)
+    pred[ref == 2] = 2                                                # a perfectly segmented class
+    ref[ref == 4] = 0; pred[pred == 4] = 0                            # a class absent from both
+    out = {}
+    for tag, ignore in (("plain", None), ("ignore", K), ("ignore_inner", 3)):
+        ignore_mask = (ref == ignore) if ignore is not None else None
+        out[tag] = np.array([counts(to_mask(ref, r), to_mask(pred, r), ignore_mask) for r in range(1, K)], dtype=np.int64)
+    np.savez_compressed(os.path.join(HERE, "nnunet_eval.npz"), ref=ref, pred=pred, K=K, **out)
+    print("nnunet eval saved", out["plain"][0], out["ignore"][0])
+
+
 def sliding_golden():
     """N2: the vendored nnU-Net sliding-window helpers (sliding_window_prediction.py:10-56); the
     module's unused acvl_utils import is stubbed."""
@@ -161,4 +179,5 @@ if __name__ == "__main__":
     metrics_golden()
     chain_golden()
     nnunet_golden()
+    nnunet_eval_golden()
     sliding_golden()

@@ -233,3 +233,21 @@ def test_multimodal_augment_host_logic(monkeypatch):
     assert len(got) == 3 and got[0].shape == (256, 256, 3) and got[0].dtype == np.float32
     for a, b in zip(got, want):                          # batched convolutions vs B = 1: not bit-identical
         np.testing.assert_allclose(a, b, rtol=1e-4, atol=1e-5)
+
+
+def test_nnunet_compute_metrics_host_logic(monkeypatch):
+    """metrics.nnunet_compute_metrics = one confusion histogram + the evaluator's formulas; the histogram is
+    emulated by the oracle here (its GPU parity: tests/test_gpu_head_metrics.py)."""
+    from ldiffusion_b200 import metrics as pmet
+    monkeypatch.setattr(pmet, "confusion_matrix",
+                        lambda pred, ref, K: torch.from_numpy(omet.confusion_matrix(pred.numpy(), ref.numpy(), K)))
+    rng = np.random.default_rng(4)
+    ref = torch.from_numpy(rng.integers(0, 5, (2, 20, 30)).astype(np.uint8))
+    pred = torch.from_numpy(rng.integers(0, 4, (2, 20, 30)).astype(np.uint8))
+    got = pmet.nnunet_compute_metrics(ref, pred, [1, 2, 3], ignore_label=4)
+    keep = ref != 4
+    for r in (1, 2, 3):
+        tp = int(((ref == r) & (pred == r) & keep).sum()); fp = int(((ref != r) & (pred == r) & keep).sum())
+        fn = int(((ref == r) & (pred != r) & keep).sum())
+        assert (got[r]["TP"], got[r]["FP"], got[r]["FN"]) == (tp, fp, fn)
+        assert got[r]["TN"] == int(keep.sum()) - tp - fp - fn and got[r]["Dice"] == 2 * tp / (2 * tp + fp + fn)
