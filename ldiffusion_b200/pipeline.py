@@ -104,6 +104,9 @@ class HotPath:
         # experiment (tools/pass_persist.py): hold the decode tails back until the head's logits exist, so a
         # persistent lift+argmax (ldiff_tune) is resident before the first decode tail occupies every SM
         self.decode_after_head = os.environ.get("LDIFF_PASS_DECODE_AFTER_HEAD", "0") == "1"
+        # experiment (unmeasured): each classifier chain zeroes its own matrix instead of one memset on the
+        # caller's stream that all five chains wait for
+        self.zero_in_chains = os.environ.get("LDIFF_PASS_ZERO_IN_CHAINS", "0") == "1"
         self._head_done = torch.cuda.Event()
 
     def attach_exchange(self, exchange, deferred: bool = True):
@@ -146,7 +149,8 @@ class HotPath:
         queueing behind them (and the caller's stream priority does not matter)."""
         cur = torch.cuda.current_stream(self.device)
         n = self.n
-        self.C.zero_()
+        if not self.zero_in_chains:
+            self.C.zero_()                                                 # a memset every chain waits for
         if concurrent:
             side = self._side_streams()
             for s in side:
@@ -223,6 +227,8 @@ class HotPath:
         ops.bilinear_lift(self.rgb_small, (self.H, self.W), out=self.rgb_up)
 
     def _chain_tissue(self, inp):
+        if self.zero_in_chains:
+            self.C[0].zero_()
         ops._head_logits(inp.head_feat, self.head_w, self.head_b, self.logits)
         if self.decode_after_head:
             self._head_done.record(torch.cuda.current_stream(self.device))
@@ -230,6 +236,8 @@ class HotPath:
         self._confusion(self.mask_tissue, inp.gt, 0)
 
     def _chain_cell(self, inp):
+        if self.zero_in_chains:
+            self.C[1].zero_()
         ops._cell_classify(inp.inst_feats, self.cell_w, self.cell_b, self.inst_ids, self.lut, None, self.status)
         ops.lut_paint(inp.inst_map, self.lut, out=self.mask_cell)
         self._confusion(self.mask_cell, inp.gt, 1)
