@@ -161,7 +161,7 @@ decode_tail_vec16_kernel(const T* __restrict__ img, uint8_t* __restrict__ rgb,
 }
 
 // ----------------------------------------------------------------------------
-// Bulk-TMA staged form (bf16 storage; opt-in through ldiff_tune(LDIFF_TUNE_DECODE_TAIL_TMA) / LDIFF_DT_TMA
+// Bulk-TMA staged form (opt-in through ldiff_tune(LDIFF_TUNE_DECODE_TAIL_TMA) / LDIFF_DT_TMA
 // until it has been measured — round-2 candidate).  Why: the pass experiments of round 1
 // (profiles/r01_pass_persist.txt) show the register-staged kernel above losing bandwidth in proportion to
 // the SMs it is given: its bytes in flight are tied to resident threads (6 blocks x 256 threads x 96 B).
@@ -171,7 +171,10 @@ decode_tail_vec16_kernel(const T* __restrict__ img, uint8_t* __restrict__ rgb,
 // above, so the bytes written are identical by construction.
 // ----------------------------------------------------------------------------
 constexpr int kDtTile = 4096;      // pixels per tile = 256 threads x 16 pixels
-constexpr int kDtStages = 4;       // 4 x 3 x 8 KB = 96 KB of shared memory per CTA (two CTAs per SM)
+// stages in flight: bf16 4 x 3 x 8 KB = 96 KB per CTA, two CTAs per SM; fp32 4 x 3 x 16 KB = 192 KB, one CTA per SM
+template <typename T> struct DtPipe;
+template <> struct DtPipe<__nv_bfloat16> { static constexpr int kStages = 4, kCtasPerSm = 2; };
+template <> struct DtPipe<float> { static constexpr int kStages = 4, kCtasPerSm = 1; };
 
 __device__ __forceinline__ uint32_t dt_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void dt_mbar_init(uint64_t* bar, uint32_t count) {
@@ -206,17 +209,29 @@ __device__ __forceinline__ void quant16_staged(const __nv_bfloat16* p, uint32_t 
   for (int i = 0; i < 8; ++i) Quant<__nv_bfloat16>::packed2(w[i], q[2 * i], q[2 * i + 1]);
 }
 
+__device__ __forceinline__ void quant16_staged(const float* p, uint32_t (&q)[16]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 v = *(reinterpret_cast<const float4*>(p) + j);
+    q[4 * j] = Quant<float>::bits(v.x);
+    q[4 * j + 1] = Quant<float>::bits(v.y);
+    q[4 * j + 2] = Quant<float>::bits(v.z);
+    q[4 * j + 3] = Quant<float>::bits(v.w);
+  }
+}
+
 // grid = persistent CTAs; tile t of the job = image t / tiles_per_img, pixels (t % tiles_per_img) * kDtTile ...
-template <bool RGB, bool GRAY>
-__global__ void __launch_bounds__(256, 2)
-decode_tail_tma_kernel(const __nv_bfloat16* __restrict__ img, uint8_t* __restrict__ rgb,
+template <typename T, bool RGB, bool GRAY>
+__global__ void __launch_bounds__(256, DtPipe<T>::kCtasPerSm)
+decode_tail_tma_kernel(const T* __restrict__ img, uint8_t* __restrict__ rgb,
                        uint8_t* __restrict__ gray, int64_t hw, int tiles_per_img, int total_tiles,
                        int64_t gray_batch_stride) {
-  extern __shared__ __align__(128) uint8_t dt_smem[];            // [kDtStages][3][kDtTile] bf16
+  constexpr int kDtStages = DtPipe<T>::kStages;
+  extern __shared__ __align__(128) uint8_t dt_smem[];            // [kDtStages][3][kDtTile] T
   __shared__ __align__(8) uint64_t full[kDtStages];
-  __nv_bfloat16* buf = reinterpret_cast<__nv_bfloat16*>(dt_smem);
+  T* buf = reinterpret_cast<T*>(dt_smem);
   const int tid = threadIdx.x;
-  constexpr uint32_t kPlaneBytes = kDtTile * sizeof(__nv_bfloat16);
+  constexpr uint32_t kPlaneBytes = kDtTile * sizeof(T);
 
   // k-th tile of this CTA -> stage k % kDtStages (one thread issues; completion lands on full[stage])
   auto issue = [&](int k) {
@@ -315,23 +330,23 @@ static int launch_decode_tail(const void* img, uint8_t* rgb, uint8_t* gray, int 
   const int threads = 256;
   const bool vec_ok = (hw % 16 == 0) && aligned16(img) && aligned16(rgb) && aligned16(gray) &&
                       aligned16(na.out) && (gray_batch_stride % 16 == 0);
-  if (vec_ok && !na.out && sizeof(T) == 2 && (hw % kDtTile) == 0 && tune_get(LDIFF_TUNE_DECODE_TAIL_TMA) > 0 &&
+  if (vec_ok && !na.out && (hw % kDtTile) == 0 && tune_get(LDIFF_TUNE_DECODE_TAIL_TMA) > 0 &&
       (int64_t)B * (hw / kDtTile) <= 0x7fffffff) {
     const int tiles_per_img = (int)(hw / kDtTile), total = B * tiles_per_img;
-    const size_t smem = (size_t)kDtStages * 3 * kDtTile * sizeof(T);
-    const int cap = 2 * sm_count();
+    const size_t smem = (size_t)DtPipe<T>::kStages * 3 * kDtTile * sizeof(T);
+    const int cap = DtPipe<T>::kCtasPerSm * sm_count();
     const int grid = total < cap ? total : cap;
-    const __nv_bfloat16* p = (const __nv_bfloat16*)img;
+    const T* p = (const T*)img;
 #define DTT(R, G)                                                                                       \
   do {                                                                                                  \
     static bool attr = false;                                                                           \
     if (!attr) {                                                                                        \
-      cudaFuncSetAttribute(decode_tail_tma_kernel<R, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+      cudaFuncSetAttribute(decode_tail_tma_kernel<T, R, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                            (int)smem);                                                                  \
       attr = true;                                                                                      \
     }                                                                                                   \
-    decode_tail_tma_kernel<R, G><<<grid, 256, smem, st>>>(p, rgb, gray, hw, tiles_per_img, total,       \
-                                                         gray_batch_stride);                            \
+    decode_tail_tma_kernel<T, R, G><<<grid, 256, smem, st>>>(p, rgb, gray, hw, tiles_per_img, total,    \
+                                                            gray_batch_stride);                         \
   } while (0)
     if (rgb && gray) DTT(true, true);
     else if (gray) DTT(false, true);

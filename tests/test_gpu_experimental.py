@@ -28,11 +28,12 @@ def tune():
 @pytest.mark.timeout(120)
 @pytest.mark.parametrize("shape", [(1, 3, 64, 64), (2, 3, 128, 96), (8, 3, 1024, 1024), (3, 3, 64, 192)])
 @pytest.mark.parametrize("want_rgb", [False, True])
-def test_decode_tail_tma_bit_exact(tune, shape, want_rgb):
-    """bf16 images whose planes are a multiple of 4096 pixels take the bulk-TMA staged kernel."""
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_decode_tail_tma_bit_exact(tune, shape, want_rgb, dtype):
+    """Images whose planes are a multiple of 4096 pixels take the bulk-TMA staged kernel."""
     from ldiffusion_b200 import _cabi, ops
     g = torch.Generator().manual_seed(sum(shape))
-    img = torch.empty(shape).uniform_(-1.3, 1.3, generator=g).bfloat16()
+    img = torch.empty(shape).uniform_(-1.3, 1.3, generator=g).to(dtype)
     tune(_cabi.TUNE_DECODE_TAIL_TMA, 0)
     rgb0, gray0 = ops.decode_tail_gray(img.cuda(), want_rgb=want_rgb)
     tune(_cabi.TUNE_DECODE_TAIL_TMA, 1)
