@@ -251,3 +251,13 @@ def test_nnunet_compute_metrics_host_logic(monkeypatch):
         fn = int(((ref == r) & (pred != r) & keep).sum())
         assert (got[r]["TP"], got[r]["FP"], got[r]["FN"]) == (tp, fp, fn)
         assert got[r]["TN"] == int(keep.sum()) - tp - fp - fn and got[r]["Dice"] == 2 * tp / (2 * tp + fp + fn)
+
+
+def test_evaluate_command_line_flags():
+    """python -m ldiffusion_b200.evaluate takes the flags of the reference's evaluate.py:129-139."""
+    from ldiffusion_b200 import evaluate as ev
+    a = ev.parse_args(["--image-dir", "p", "--label-dir", "l", "--num-classes", "7"])
+    assert (a.image_dir, a.label_dir, a.num_classes, a.save_dir) == ("p", "l", 7, "./LDiffusion/eval/eval_report")
+    with pytest.raises(SystemExit):
+        ev.parse_args(["--image-dir", "p"])
+    assert ev.evaluate is not None and ev.pixel_accuracy is not None and ev.frequency_weighted_iou is not None
