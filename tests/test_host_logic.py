@@ -253,11 +253,20 @@ def test_nnunet_compute_metrics_host_logic(monkeypatch):
         assert got[r]["TN"] == int(keep.sum()) - tp - fp - fn and got[r]["Dice"] == 2 * tp / (2 * tp + fp + fn)
 
 
-def test_evaluate_command_line_flags():
-    """python -m ldiffusion_b200.evaluate takes the flags of the reference's evaluate.py:129-139."""
-    from ldiffusion_b200 import evaluate as ev
+def test_evaluate_command_line_flags(monkeypatch):
+    """python -m ldiffusion_b200.evaluate takes the flags of the reference's evaluate.py:129-139, and importing
+    the submodule does not break ``ldiffusion_b200.evaluate(...)`` (the module forwards calls to the function)."""
+    import importlib
+    import ldiffusion_b200 as L
+    from ldiffusion_b200 import metrics as pmet
+    assert L.evaluate is pmet.evaluate
+    ev = importlib.import_module("ldiffusion_b200.evaluate")
     a = ev.parse_args(["--image-dir", "p", "--label-dir", "l", "--num-classes", "7"])
     assert (a.image_dir, a.label_dir, a.num_classes, a.save_dir) == ("p", "l", 7, "./LDiffusion/eval/eval_report")
     with pytest.raises(SystemExit):
         ev.parse_args(["--image-dir", "p"])
-    assert ev.evaluate is not None and ev.pixel_accuracy is not None and ev.frequency_weighted_iou is not None
+    assert ev.evaluate is pmet.evaluate and ev.pixel_accuracy is pmet.pixel_accuracy
+    calls = []
+    monkeypatch.setattr(ev, "evaluate", lambda *a, **k: calls.append((a, k)) or "report")
+    assert L.evaluate("pred", "gt", 7, save_dir="out") == "report"          # L.evaluate is the module now
+    assert calls == [(("pred", "gt", 7), {"save_dir": "out"})]
