@@ -152,6 +152,14 @@ int ldiff_bilinear_lift_multi(const void* const* host_srcs, int n_src, int src_d
                               int dst_dtype, int Ctot, int dst_channel, int H, int W, int B, int gray,
                               void* stream);
 
+/* adjoint of ldiff_bilinear_lift for the training caller (ldiffusion.py:240-252; round-2 widening, reached only
+ * through autograd): grad_src[b,c,y,x] += w_c * ly * lx * grad_out[b, dst_channel (+c), oy, ox] with the
+ * forward's taps (h x w = the SOURCE size, H x W = the lifted size); fp32; grad_src (element strides as the
+ * forward's source) must be zeroed by the caller and is accumulated into with atomics. */
+int ldiff_bilinear_lift_backward(const float* grad_out, int Ctot, int dst_channel, int H, int W,
+                                 float* grad_src, int C, int h, int w, int64_t src_batch_stride,
+                                 int64_t src_channel_stride, int B, int gray, void* stream);
+
 /* ---- a-5  classifier head + argmax ---------------------------------------
  * tissue form, replaces conductor.py:127 (1x1 conv 256->K), :135 (bilinear lift
  * to the input size) and segmentor.py:536 (argmax(softmax)) without ever

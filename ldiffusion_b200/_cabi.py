@@ -38,6 +38,8 @@ SIGNATURES = {
                                     c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "ldiff_bilinear_lift_multi": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int64, c_int64, c_void_p,
                                           c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "ldiff_bilinear_lift_backward": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,
+                                             c_int64, c_int64, c_int, c_int, c_void_p]),
     "ldiff_head_logits": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                   c_int, c_void_p]),
     "ldiff_lift_argmax": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,

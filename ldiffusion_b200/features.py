@@ -84,6 +84,13 @@ def feature_concat(decoded_steps: Sequence[torch.Tensor], size=(64, 64), out_dty
     return out
 
 
+def feature_concat_autograd(decoded_steps: Sequence[torch.Tensor], size=(64, 64)) -> torch.Tensor:
+    """``feature_concat`` for the training caller (ldiffusion.py:240-252): the same kernels in the forward, their
+    adjoint in the backward, so the InfoNCE loss on the features reaches the decoder outputs (fp32 [B,n,h,w];
+    the concat itself is torch.cat here because autograd needs separate nodes)."""
+    return torch.cat([ops.bilinear_lift_autograd(d, size, gray=True) for d in decoded_steps], dim=1)
+
+
 def label_down(label: torch.Tensor, size=(64, 64)) -> torch.Tensor:
     """ldiffusion.py:224-226: uint8 [B,1,H,W] -> float -> bilinear -> uint8 (truncation)."""
     if label.dtype != torch.uint8:

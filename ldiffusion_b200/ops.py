@@ -167,6 +167,15 @@ def _bilinear_lift_multi(srcs: Sequence[Tensor], dst: Tensor, dst_channel: int, 
                                                 1 if gray else 0, _stream(s0)))
 
 
+def _bilinear_lift_backward(grad_out: Tensor, dst_channel: int, grad_src: Tensor, gray: bool) -> None:
+    _cuda(grad_out, grad_src)
+    B, Ctot, H, W = grad_out.shape
+    _, C, h, w = grad_src.shape
+    check(_cabi.lib().ldiff_bilinear_lift_backward(_ptr(grad_out), Ctot, dst_channel, H, W, _ptr(grad_src), C, h, w,
+                                                   grad_src.stride(0), grad_src.stride(1), B, 1 if gray else 0,
+                                                   _stream(grad_out)))
+
+
 def _head_logits(feat: Tensor, weight: Tensor, bias: Optional[Tensor], logits: Tensor) -> None:
     _cuda(feat, weight, bias, logits)
     B, Cin = feat.shape[:2]
@@ -303,6 +312,7 @@ torch.library.custom_op("ldiff::decode_tail_model_input",
                         mutates_args=("rgb", "gray", "model_input"))(_decode_tail_model_input)
 torch.library.custom_op("ldiff::bilinear_lift", mutates_args=("dst",))(_bilinear_lift)
 torch.library.custom_op("ldiff::bilinear_lift_multi", mutates_args=("dst",))(_bilinear_lift_multi)
+torch.library.custom_op("ldiff::bilinear_lift_backward", mutates_args=("grad_src",))(_bilinear_lift_backward)
 torch.library.custom_op("ldiff::head_logits", mutates_args=("logits",))(_head_logits)
 torch.library.custom_op("ldiff::lift_argmax", mutates_args=("mask",))(_lift_argmax)
 torch.library.custom_op("ldiff::cell_classify", mutates_args=("lut", "logits_out", "status"))(_cell_classify)
@@ -470,6 +480,42 @@ def bilinear_lift(src: Tensor, size, *, out: Optional[Tensor] = None, out_channe
         raise ValueError("out must be [B,Ctot,H,W]")
     _bilinear_lift(src, out, out_channel, gray)
     return out
+
+
+def bilinear_lift_backward(grad_out: Tensor, src_shape, *, out_channel: int = 0, gray: bool = False) -> Tensor:
+    """Adjoint of ``bilinear_lift`` (fp32): gradient w.r.t. a ``src_shape`` = [B,C,h,w] source of the lift whose
+    result sits in channels ``out_channel ...`` of ``grad_out`` [B,Ctot,H,W].  Round-2 widening (training
+    caller, ldiffusion.py:240-252); not measured yet."""
+    if grad_out.dtype != torch.float32 or grad_out.dim() != 4:
+        raise TypeError("grad_out must be fp32 [B,Ctot,H,W]")
+    _cuda(grad_out)
+    _dense(grad_out, "grad_out")
+    B, C, h, w = src_shape
+    if grad_out.shape[0] != B or (gray and C != 3):
+        raise ValueError("grad_out / src_shape mismatch")
+    grad_src = torch.zeros((B, C, h, w), dtype=torch.float32, device=grad_out.device)
+    if grad_src.numel() and grad_out.numel():
+        _bilinear_lift_backward(grad_out, int(out_channel), grad_src, bool(gray))
+    return grad_src
+
+
+class _LiftFn(torch.autograd.Function):
+    """bilinear_lift (+ gray) with a backward: the lift kernels run under no_grad everywhere else."""
+
+    @staticmethod
+    def forward(ctx, src, size, gray):
+        ctx.src_shape, ctx.gray, ctx.src_dtype = tuple(src.shape), bool(gray), src.dtype
+        return bilinear_lift(src.detach().contiguous(), size, gray=gray, out_dtype=torch.float32)
+
+    @staticmethod
+    def backward(ctx, grad):
+        g = bilinear_lift_backward(grad.float().contiguous(), ctx.src_shape, gray=ctx.gray)
+        return g.to(ctx.src_dtype), None, None
+
+
+def bilinear_lift_autograd(src: Tensor, size, *, gray: bool = False) -> Tensor:
+    """Differentiable ``bilinear_lift`` (fp32 result): forward = the lift kernel, backward = its adjoint kernel."""
+    return _LiftFn.apply(src, tuple(size), gray)
 
 
 def bilinear_lift_multi(srcs: Sequence[Tensor], size, *, out: Optional[Tensor] = None, out_channel: int = 0,

@@ -112,3 +112,40 @@ def feature_concat_spec(decoded_steps, size=(64, 64)):
 def label_down_spec(label_u8, size=(64, 64)):
     """float -> uint8 conversion truncates toward zero (values are in [0,255])."""
     return lift_spec(np.asarray(label_u8).astype(np.float32), size).astype(np.uint8)
+
+
+def feature_concat_grad_chain(decoded_steps, grad_out, size=(64, 64)):
+    """torch-CPU autograd through the literal chain of ldiffusion.py:240-247 (interpolate -> weighted gray ->
+    cat): gradients w.r.t. every decoded step for an upstream ``grad_out`` [B,n,h,w]."""
+    import torch
+    import torch.nn.functional as F
+    xs = [d.detach().clone().float().requires_grad_(True) for d in decoded_steps]
+    chans = []
+    for x in xs:
+        r = F.interpolate(x, size=size, mode="bilinear", align_corners=False)
+        chans.append((0.2989 * r[:, 0] + 0.5870 * r[:, 1] + 0.1140 * r[:, 2]).unsqueeze(1))
+    torch.cat(chans, dim=1).backward(grad_out)
+    return [x.grad for x in xs]
+
+
+def lift_backward_spec(grad_out, src_shape, gray=False):
+    """What ``ldiff_bilinear_lift_backward`` scatters, restated with numpy: the forward's taps
+    (``source_index``), weight ``ly * lx`` per tap, ``GRAY_W[c]`` per channel in gray mode, fp32 products,
+    accumulation in output-pixel order (the kernel's atomics may add in another order where footprints
+    overlap).  grad_out: [B, (1 if gray else C), H, W] -> [B, C, h, w]."""
+    g = _f32(grad_out)
+    B, C, h, w = src_shape
+    H, W = g.shape[2:]
+    yi0, yi1, yl0, yl1 = source_index(H, h)
+    xi0, xi1, xl0, xl1 = source_index(W, w)
+    out = np.zeros((B, C, h, w), np.float32)
+    wy = [(yi0, yl0), (yi1, yl1)]
+    wx = [(xi0, xl0), (xi1, xl1)]
+    for c in range(C):
+        gc = g[:, 0] * np.float32(GRAY_W[c]) if gray else g[:, c]
+        for iy, ly in wy:
+            for ix, lx in wx:
+                wgt = (ly[:, None] * lx[None, :]).astype(np.float32)          # [H, W]
+                contrib = (wgt[None] * gc).astype(np.float32)                  # [B, H, W]
+                np.add.at(out[:, c], (slice(None), iy[:, None], ix[None, :]), contrib)
+    return out

@@ -58,6 +58,12 @@ def test_argument_errors_are_reported_without_a_gpu(built_lib):
     assert lib.ldiff_decode_tail_gray(16, None, 16, 1, 4, 4, 8, 0, None) == EINVAL                     # stride < H*W
     assert lib.ldiff_bilinear_lift(16, 0, 2, 4, 4, 32, 16, 16, 0, 1, 0, 8, 8, 1, 1, None) == EINVAL    # gray needs C==3
     assert lib.ldiff_bilinear_lift(16, 2, 1, 4, 4, 16, 16, 16, 1, 1, 0, 8, 8, 1, 0, None) == EUNSUP    # u8 -> bf16
+    lb = lib.ldiff_bilinear_lift_backward
+    assert lb(16, 1, 0, 8, 8, 16, 2, 16, 16, 512, 256, 1, 1, None) == EINVAL                           # gray needs C == 3
+    assert lb(16, 1, 1, 8, 8, 16, 3, 16, 16, 768, 256, 1, 1, None) == EINVAL                           # channel outside grad_out
+    assert lb(16, 3, 0, 8, 8, 16, 3, 16, 16, 768, 100, 1, 0, None) == EINVAL                           # channel stride < h*w
+    assert lb(16, 3, 0, 8, 8, 16, 3, 16, 16, 768, 256, 0, 0, None) == 0                                # empty batch
+    assert lib.ldiff_tune(7, 1) == EINVAL and lib.ldiff_tune(0, -1) == EINVAL and lib.ldiff_tune(0, 0) == 0
     assert lib.ldiff_confusion_hist(16, 16, None, 16, 64, 0, 16, None) == EINVAL                       # K < 1
     assert lib.ldiff_confusion_hist(16, 16, None, 16, 64, 200, 16, None) == EUNSUP                     # K > 128
     assert lib.ldiff_lift_argmax(16, 16, 1, 300, 4, 4, 8, 8, None) == EINVAL

@@ -60,3 +60,33 @@ def test_lift_argmax_persistent_bit_exact(tune):
         got = ops.lift_argmax(logits.cuda(), size)
         tune(_cabi.TUNE_ARGMAX_PERSIST_BLOCKS, 0)
         assert np.array_equal(got.cpu().numpy(), ohead.lift_argmax_spec(logits.numpy(), size))
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("shape,size", [((2, 3, 1024, 1024), (64, 64)), ((1, 3, 50, 40), (20, 16)), ((1, 3, 16, 16), (40, 24)),
+                                        ((2, 3, 64, 64), (64, 64))])
+def test_lift_backward_matches_spec_and_autograd(shape, size):
+    """The adjoint kernel against its numpy spec (bit-exact where footprints are disjoint) and, end to end, the
+    gradient of feature_concat_autograd against torch's autograd through ldiffusion.py:240-247."""
+    from oracle import bilinear as obil
+    from ldiffusion_b200 import features, ops
+    g = torch.Generator().manual_seed(sum(shape))
+    go = torch.randn(shape[0], 1, *size, generator=g)
+    got = ops.bilinear_lift_backward(go.cuda(), shape, gray=True).cpu().numpy()
+    want = obil.lift_backward_spec(go.numpy(), shape, gray=True)
+    disjoint = shape[2] % size[0] == 0 and shape[3] % size[1] == 0 and shape[2] // size[0] >= 2
+    if disjoint or shape[2:] == size:
+        assert np.array_equal(got, want)
+    else:
+        np.testing.assert_allclose(got, want, rtol=0, atol=5e-7 * float(np.abs(want).max()))
+    rgb = torch.randn(shape[0], 3, *size, generator=g)
+    np.testing.assert_allclose(ops.bilinear_lift_backward(rgb.cuda(), shape).cpu().numpy(),
+                               obil.lift_backward_spec(rgb.numpy(), shape), rtol=0, atol=5e-7 * float(rgb.abs().max()) * 4)
+    steps = [torch.randn(shape, generator=g) for _ in range(2)]
+    dev = [s_.cuda().requires_grad_(True) for s_ in steps]
+    feats = features.feature_concat_autograd(dev, size)
+    up = torch.randn(feats.shape, generator=g)
+    feats.backward(up.cuda())
+    ref = obil.feature_concat_grad_chain(steps, up, size)
+    for d, r in zip(dev, ref):
+        np.testing.assert_allclose(d.grad.cpu().numpy(), r.numpy(), rtol=0, atol=5e-7 * float(r.abs().max()))

@@ -270,3 +270,31 @@ def test_evaluate_command_line_flags(monkeypatch):
     monkeypatch.setattr(ev, "evaluate", lambda *a, **k: calls.append((a, k)) or "report")
     assert L.evaluate("pred", "gt", 7, save_dir="out") == "report"          # L.evaluate is the module now
     assert calls == [(("pred", "gt", 7), {"save_dir": "out"})]
+
+
+def test_feature_concat_autograd_wiring(monkeypatch):
+    """features.feature_concat_autograd: forward = the lift kernel, backward = its adjoint kernel, both emulated
+    here by the oracle (chain forward, numpy spec backward) — the gradient that reaches every decoded step must
+    be torch's own autograd through ldiffusion.py:240-247."""
+    from oracle import bilinear as obil
+    from ldiffusion_b200 import features, ops
+
+    def fake_lift(src, size, *, gray=False, out_dtype=None, **kw):
+        y = obil.lift_chain(src.float(), size)
+        return obil.gray_weighted_chain(y) if gray else y
+
+    def fake_backward(grad_out, src_shape, *, out_channel=0, gray=False):
+        return torch.from_numpy(obil.lift_backward_spec(grad_out.numpy(), src_shape, gray=gray))
+
+    monkeypatch.setattr(ops, "bilinear_lift", fake_lift)
+    monkeypatch.setattr(ops, "bilinear_lift_backward", fake_backward)
+    g = torch.Generator().manual_seed(12)
+    steps = [torch.randn(2, 3, 64, 64, generator=g, requires_grad=True) for _ in range(3)]
+    feats = features.feature_concat_autograd(steps, (16, 16))
+    assert feats.shape == (2, 3, 16, 16) and feats.requires_grad
+    assert torch.equal(feats.detach(), obil.feature_concat_chain([s.detach() for s in steps], (16, 16)))
+    go = torch.randn(feats.shape, generator=g)
+    feats.backward(go)
+    want = obil.feature_concat_grad_chain(steps, go, (16, 16))
+    for s_, w_ in zip(steps, want):
+        assert torch.equal(s_.grad, w_)

@@ -235,3 +235,28 @@ def test_pixel_vectors_layout():
     assert v.shape == (6, 5, 4)
     for (i, j), vec in d.items():
         assert v[i, j].tolist() == [int(a) for a in vec]
+
+
+@pytest.mark.parametrize("shape,size", [((2, 3, 64, 64), (16, 16)), ((1, 3, 50, 40), (20, 16)), ((1, 3, 8, 8), (8, 8)),
+                                        ((1, 3, 16, 16), (40, 24)), ((1, 3, 256, 256), (16, 16))])
+def test_lift_backward_spec_equals_torch_autograd(shape, size):
+    """The adjoint the backward kernel scatters (oracle/bilinear.py::lift_backward_spec) against torch's own
+    autograd through ldiffusion.py:240-247: bit-identical where footprints are disjoint (down-sampling by an
+    integer factor, the path's case), within 2 ulp of the largest gradient elsewhere (summation order)."""
+    g = torch.Generator().manual_seed(sum(shape) + sum(size))
+    steps = [torch.randn(shape, generator=g) for _ in range(2)]
+    go = torch.randn(shape[0], 2, *size, generator=g)
+    want = obil.feature_concat_grad_chain(steps, go, size)
+    disjoint = shape[2] % size[0] == 0 and shape[3] % size[1] == 0 and shape[2] // size[0] >= 2 and shape[3] // size[1] >= 2
+    for i in range(2):
+        got = obil.lift_backward_spec(go[:, i:i + 1].numpy(), shape, gray=True)
+        if disjoint or shape[2:] == size:
+            assert np.array_equal(got, want[i].numpy())
+        else:
+            np.testing.assert_allclose(got, want[i].numpy(), rtol=0, atol=2.4e-7 * float(want[i].abs().max()))
+    x = steps[0].clone().requires_grad_(True)
+    y = torch.nn.functional.interpolate(x, size=size, mode="bilinear", align_corners=False)
+    gy = torch.randn(y.shape, generator=g)
+    y.backward(gy)
+    np.testing.assert_allclose(obil.lift_backward_spec(gy.numpy(), shape), x.grad.numpy(), rtol=0,
+                               atol=2.4e-7 * float(x.grad.abs().max()))
