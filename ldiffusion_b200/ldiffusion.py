@@ -3,9 +3,11 @@
 In scope: ``inference`` (dispatch to the Segmentor hot loops) and the tensor part of
 one warm-up step (``ldiffusion.py:224-251``: label down-sample, Laplace noising per
 timestep, decode -> bilinear -> gray -> concat, final RGB up-sample), exposed as
-``laplace_feature_step``.  Out of scope: the DeepSpeed ZeRO-3 engine, AdamW, the
-InfoNCE/VGG loss, checkpointing — ``train`` therefore needs an injected
-``train_step`` callable and otherwise raises.
+``laplace_feature_step``; and, as an unmeasured round-2 widening, the same step with
+gradients (``warmup_step`` / ``train_ldiffusion``: lift adjoint + InfoNCE kernels, plain
+AdamW).  Out of scope: the DeepSpeed ZeRO-3 engine, the VGG content loss, checkpointing,
+data loading — ``train`` therefore needs an injected ``train_step`` callable and
+otherwise raises.
 """
 import os
 
@@ -73,6 +75,89 @@ class LDiffusionModel:
         rgb64 = features.ops.bilinear_lift(last, (64, 64))                           # :240 (the RGB that is kept)
         rgb = features.rgb_up(rgb64, (1024, 1024))                                   # :251
         return rgb, gray, label64
+
+    def warmup_step(self, image, label, pipeline, unet, vae, proj, optimizer, num_inference_steps,
+                    seed: int = 0, step_index: int = 0, size=(64, 64), noise=None, pairs=None):
+        """One batch of the Laplace warm-up, ldiffusion.py:209-255, WITH gradients, on the product kernels
+        (round-2 widening; unmeasured).  Per timestep: Laplace noising of the clean latents (one launch, no
+        grad), UNet, VAE decode (both out of scope, with grad), bilinear -> gray feature (lift kernel forward,
+        adjoint kernel backward); then the pixel-contrastive InfoNCE term on the concatenated features
+        (``loss.pixel_contrastive_loss``; the VGG content term of ``loss.py:19-42`` is out of scope), backward,
+        gradient clipping at 1.0 and the optimizer step (plain AdamW in place of the DeepSpeed engine,
+        ldiffusion.py:165-193).  image [B,3,h,w] float, label uint8 [B,1,H,W].  Returns the detached loss."""
+        from . import ops
+        from .loss import pixel_contrastive_loss
+        dev = self.device
+        image = image.to(dev, torch.float32)
+        ids = torch.tensor(pipeline.tokenizer(["A pathological slide"] * image.shape[0])["input_ids"],
+                           dtype=torch.long, device=dev)                                  # :211-214
+        with torch.no_grad():
+            text = pipeline.text_encoder(ids)["last_hidden_state"].to(torch.float32)      # :215-216
+            label64 = features.label_down(label.to(dev), size)                            # :223-226
+            latents = vae.encode(image).latent_dist.mean.to(torch.float32).contiguous()   # :227-228
+        text = proj(text)                                                                 # :219
+        sched = pipeline.scheduler
+        sched.set_timesteps(num_inference_steps, device=dev)                              # :229
+        blocks = (latents.numel() + 3) // 4
+        n = len(sched.timesteps)
+        grays = []
+        for i, t in enumerate(sched.timesteps):
+            with torch.no_grad():
+                x = sched.scale_model_input(latents, t)                                   # :233
+                noisy = sched.add_laplace_noise(x, sched._host_timesteps[i], seed=seed,
+                                                offset=(step_index * n + i) * blocks,
+                                                noise=None if noise is None else noise[i])   # :234-237
+            denoised = unet(noisy, t, text).sample                                        # :238
+            decoded = vae.decode(denoised.to(torch.float32)).sample                       # :240
+            grays.append(ops.bilinear_lift_autograd(decoded, size, gray=True))            # :240-242
+        gray = torch.cat(grays, dim=1)                                                    # :244-247
+        loss = pixel_contrastive_loss(gray, label64, pairs=pairs, seed=seed, offset=step_index)   # :252
+        optimizer.zero_grad(set_to_none=True)
+        loss.backward()                                                                   # :254
+        params = [p for g in optimizer.param_groups for p in g["params"] if p.grad is not None]
+        if params:
+            torch.nn.utils.clip_grad_norm_(params, 1.0)                                   # "gradient_clipping": 1.0
+        optimizer.step()                                                                  # :255
+        return loss.detach()
+
+    def train_ldiffusion(self, args, train_loader, val_loader=None, pipeline=None, log=None):
+        """ldiffusion.py:121-295 without DeepSpeed: AdamW(lr 1e-5, betas (0.9, 0.999), eps 1e-8, weight decay
+        0.01) over the UNet and the text projection, ``warmup_step`` per batch, the epoch-mean loss (summed
+        over ranks when torch.distributed is initialised, :56-64) appended to ``log`` and returned as a list.
+        ``train_loader`` yields (image, _, label) like the reference's; checkpoint writing is out of scope."""
+        import torch.distributed as dist
+        if pipeline is None:
+            from .standin import StandInPipeline
+            pipeline = StandInPipeline(self.device) if self._pipeline_loader is None else \
+                self._pipeline_loader(None, getattr(args, "diffusion_path", self.diffusion_path))[0]
+        self.pipeline, self.vae = pipeline, pipeline.vae
+        unet = pipeline.unet
+        hid, cad = pipeline.text_encoder.config.hidden_size, unet.config.cross_attention_dim
+        if self.linear_layer is None or self.linear_layer.in_features != hid or self.linear_layer.out_features != cad:
+            self.linear_layer = torch.nn.Linear(hid, cad)                                 # :141-150
+        self.linear_layer = self.linear_layer.to(self.device, torch.float32)
+        opt = torch.optim.AdamW(list(unet.parameters()) + list(self.linear_layer.parameters()), lr=1e-5,
+                                betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01)          # :167-175
+        n_steps = min(int(args.num_inference_steps / 5), len(pipeline.scheduler.alphas_cumprod))   # :198
+        n_steps = max(n_steps, 1)
+        history, step = [], 0
+        for epoch in range(int(getattr(args, "num_epochs", 10))):                         # :122,202
+            unet.train()
+            total = torch.zeros((), device=self.device)
+            batches = 0
+            for image, _, label in train_loader:                                          # :209
+                total += self.warmup_step(image, label, pipeline, unet, self.vae, self.linear_layer, opt, n_steps,
+                                          seed=int(getattr(args, "seed", 0)), step_index=step)
+                step += 1
+                batches += 1
+            mean = total / max(batches, 1)
+            if dist.is_available() and dist.is_initialized():                             # _reduce_mean :56-64
+                dist.all_reduce(mean)
+                mean /= dist.get_world_size()
+            history.append(float(mean))
+            if log is not None:
+                log.append((epoch + 1, history[-1]))
+        return history
 
     def train(self, args, component="all", ldiffusion_weight=None, train_step=None):
         """ldiffusion.py:297-315.  Training orchestration (DeepSpeed ZeRO-3, losses,

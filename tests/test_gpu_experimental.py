@@ -90,3 +90,26 @@ def test_lift_backward_matches_spec_and_autograd(shape, size):
     ref = obil.feature_concat_grad_chain(steps, up, size)
     for d, r in zip(dev, ref):
         np.testing.assert_allclose(d.grad.cpu().numpy(), r.numpy(), rtol=0, atol=5e-7 * float(r.abs().max()))
+
+
+@pytest.mark.timeout(300)
+def test_warmup_step_runs_on_the_product_kernels():
+    """ldiffusion.py:209-255 with gradients: Laplace noising, lift + adjoint, InfoNCE forward/backward, AdamW."""
+    import ldiffusion_b200 as L
+    from ldiffusion_b200.standin import StandInPipeline
+    model = L.LDiffusionModel("unused", "tissue")
+    pipe = StandInPipeline("cuda", seed=5)
+    g = torch.Generator().manual_seed(1)
+    image = torch.rand(2, 3, 512, 512, generator=g)
+    label = torch.zeros(2, 1, 1024, 1024, dtype=torch.uint8)
+    label[:, :, :512] = 1
+    label[:, :, :, 768:] = 2
+    proj = torch.nn.Linear(768, 768).cuda()
+    params = list(pipe.unet.parameters()) + list(proj.parameters())
+    opt = torch.optim.AdamW(params, lr=1e-3)
+    before = [p.detach().clone() for p in params]
+    losses = [float(model.warmup_step(image, label, pipe, pipe.unet, pipe.vae, proj, opt, 2, seed=3, step_index=i))
+              for i in range(3)]
+    assert all(np.isfinite(v) and v > 0 for v in losses)
+    assert any(not torch.equal(a, b.detach()) for a, b in zip(before, params))
+    L.ops.check_status("cuda")

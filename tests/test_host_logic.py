@@ -298,3 +298,64 @@ def test_feature_concat_autograd_wiring(monkeypatch):
     want = obil.feature_concat_grad_chain(steps, go, (16, 16))
     for s_, w_ in zip(steps, want):
         assert torch.equal(s_.grad, w_)
+
+
+def test_warmup_step_host_logic(monkeypatch):
+    """LDiffusionModel.warmup_step / train_ldiffusion (ldiffusion.py:121-295 without DeepSpeed) with every
+    ldiff operator emulated by its oracle: gradients reach the UNet and the text projection through the
+    feature lift and the InfoNCE term, the parameters move, and the loss equals the reference loop's."""
+    import types
+    from oracle import bilinear as obil
+    from oracle.loss import contrastive_loss_chain
+    from ldiffusion_b200 import loss as ploss, ops
+    from ldiffusion_b200.ldiffusion import LDiffusionModel
+    from ldiffusion_b200.standin import StandInPipeline
+
+    def fake_lift(src, size, *, gray=False, out_dtype=None, **kw):
+        y = obil.lift_chain(src.float(), tuple(size))
+        if src.dtype == torch.uint8:
+            return y.to(torch.uint8)
+        return obil.gray_weighted_chain(y) if gray else y
+
+    monkeypatch.setattr(ops, "bilinear_lift", fake_lift)
+    monkeypatch.setattr(ops, "bilinear_lift_backward", lambda g, shape, *, out_channel=0, gray=False:
+                        torch.from_numpy(obil.lift_backward_spec(g.numpy(), shape, gray=gray)))
+    monkeypatch.setattr(ops, "laplace_qsample", lambda x, b, *, noise=None, **kw: x + noise)
+    seen = {}
+
+    def fake_loss(feats, labels, pairs=None, seed=0, offset=0, **kw):
+        seen["feats"], seen["labels"] = feats.detach().clone(), labels.clone()
+        pairs = ploss.sample_contrastive_pairs(labels, 64, torch.Generator().manual_seed(offset))
+        seen["pairs"] = pairs
+        return contrastive_loss_chain(feats, pairs)
+
+    monkeypatch.setattr(ploss, "pixel_contrastive_loss", fake_loss)
+    torch.manual_seed(0)
+    pipe = StandInPipeline("cpu", seed=5)
+    model = object.__new__(LDiffusionModel)                      # the constructor insists on a CUDA device
+    model.device, model.linear_layer, model._pipeline_loader, model.diffusion_path = torch.device("cpu"), None, None, "x"
+    g = torch.Generator().manual_seed(1)
+    image = torch.rand(2, 3, 64, 64, generator=g)
+    label = torch.zeros(2, 1, 128, 128, dtype=torch.uint8)
+    label[:, :, :64] = 1
+    label[:, :, :, 96:] = 2
+    proj = torch.nn.Linear(768, 768)
+    params = list(pipe.unet.parameters()) + list(proj.parameters())
+    opt = torch.optim.AdamW(params, lr=1e-3)
+    before = [p.detach().clone() for p in params]
+    pipe.scheduler.set_timesteps(2)
+    noise = [torch.randn(2, 4, 8, 8, generator=g) for _ in pipe.scheduler.timesteps]
+    loss = model.warmup_step(image, label, pipe, pipe.unet, pipe.vae, proj, opt, 2, noise=noise, size=(16, 16))
+    assert loss.ndim == 0 and float(loss) > 0 and seen["feats"].shape == (2, 3, 16, 16)
+    assert torch.equal(seen["labels"], obil.lift_chain(label.float(), (16, 16)).to(torch.uint8))
+    assert float(loss) == pytest.approx(float(contrastive_loss_chain(seen["feats"], seen["pairs"])), rel=1e-6)
+    moved = [not torch.equal(a, b.detach()) for a, b in zip(before, params)]
+    assert all(moved[:len(list(pipe.unet.parameters()))]) and any(moved[-2:])        # UNet and projection updated
+    # the epoch driver: AdamW as configured at ldiffusion.py:167-175, one mean loss per epoch
+    monkeypatch.setattr(LDiffusionModel, "warmup_step",
+                        lambda self, image, label, *a, **k: torch.tensor(float(k["step_index"] + 1)))
+    args = types.SimpleNamespace(num_inference_steps=10, num_epochs=2, diffusion_path="x")
+    log = []
+    hist = model.train_ldiffusion(args, [(image, None, label)] * 3, pipeline=pipe, log=log)
+    assert hist == [2.0, 5.0] and log == [(1, 2.0), (2, 5.0)]
+    assert model.linear_layer.in_features == 768 and model.linear_layer.out_features == 768
