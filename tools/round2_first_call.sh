@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
 o=gpurun_out/r2_first
-( LDIFF_TEST_EXPERIMENTAL=1 timeout 120 python -m pytest tests/test_gpu_experimental.py -q -m gpu ) > ${o}_experimental_tests.log 2>&1
+( LDIFF_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_experimental.py -q -m gpu ) > ${o}_experimental_tests.log 2>&1
 python tools/kbench.py > ${o}_kbench_default.txt 2>&1
 LDIFF_DT_TMA=1 timeout 120 python tools/kbench.py > ${o}_kbench_tma.txt 2>&1
 for cfg in "" "LDIFF_DT_TMA=1" "LDIFF_PASS_ZERO_IN_CHAINS=1" "LDIFF_DT_TMA=1 LDIFF_PASS_ZERO_IN_CHAINS=1"; do
