@@ -332,7 +332,7 @@ def run_ours(args):
     host_out = [hp.alloc_host_results() for _ in range(2)]
     d2h = sum(t.numel() * t.element_size() for t in host_out[0].values())
     after = (lambda: dist.all_reduce(hp.C)) if nccl_ar else None
-    e2e_steps = max(4, min(args.steps, 12))
+    e2e_steps = max(4, min(args.steps, 32))          # long enough that the pipeline's fill and drain are < 2 % of it
     with torch.cuda.stream(stream):
         hp.run_host([host] * 3, host_out, after_run=after)
         barrier()
