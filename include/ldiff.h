@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define LDIFF_ABI_VERSION 1
+#define LDIFF_ABI_VERSION 2
 
 enum { LDIFF_F32 = 0, LDIFF_BF16 = 1, LDIFF_U8 = 2 };
 
@@ -47,15 +47,15 @@ enum {
 enum { LDIFF_STATUS_PRED_RANGE = 1, LDIFF_STATUS_INST_RANGE = 2, LDIFF_STATUS_SW_INF = 4,
        LDIFF_STATUS_XCHG_TIMEOUT = 8, LDIFF_STATUS_LABEL_RANGE = 16 };
 
-/* Scheduling knobs of the whole pass (no effect on results).  A value set here applies to the launches
- * issued after the call; 0 = off.  Before the first ldiff_tune of a knob its environment variable applies.
- *  LDIFF_TUNE_ARGMAX_PERSIST_BLOCKS (env LDIFF_ARGMAX_PERSIST): ldiff_lift_argmax runs as that many persistent
- *    512-thread blocks, each owning one SM's register file, instead of one block per band;
- *  LDIFF_TUNE_DECODE_TAIL_SMS (env LDIFF_DT_SMS): ldiff_decode_tail_* sizes its one-wave grid for that many SMs
- *    (the SMs the persistent lift+argmax leaves free) instead of the whole device;
- *  LDIFF_TUNE_DECODE_TAIL_TMA (env LDIFF_DT_TMA): bf16 decode tails run the bulk-TMA staged persistent kernel
- *    (not yet measured: a round-2 candidate, off by default). */
-enum { LDIFF_TUNE_ARGMAX_PERSIST_BLOCKS = 0, LDIFF_TUNE_DECODE_TAIL_SMS = 1, LDIFF_TUNE_DECODE_TAIL_TMA = 2,
+/* Scheduling / variant knobs (no effect on results).  A value set here applies to the launches issued
+ * after the call.  Before the first ldiff_tune of a knob its environment variable, else the default, applies.
+ *  LDIFF_TUNE_ARGMAX_VARIANT (env LDIFF_ARGMAX_VARIANT, default 0): ldiff_lift_argmax runs 0 = the envelope
+ *    kernel, 4 / 5 = round 1's per-pixel evaluation kernel with 2 / 1 columns per thread (A/B timing);
+ *  LDIFF_TUNE_DECODE_TAIL_SMS (env LDIFF_DT_SMS, default 0 = all): the register-staged decode tail sizes its
+ *    one-wave grid for that many SMs;
+ *  LDIFF_TUNE_DECODE_TAIL_TMA (env LDIFF_DT_TMA, default 1): 0 = register-staged decode tail, 1..4 = the
+ *    bulk-TMA staged persistent kernel with (stages x CTAs/SM) = (4x2) / (3x3) / (2x4) / (2x3) for bf16. */
+enum { LDIFF_TUNE_ARGMAX_VARIANT = 0, LDIFF_TUNE_DECODE_TAIL_SMS = 1, LDIFF_TUNE_DECODE_TAIL_TMA = 2,
        LDIFF_TUNE_COUNT = 3 };
 int ldiff_tune(int knob, int value);
 
@@ -114,6 +114,17 @@ int ldiff_plms_step(const void* sample, const void* e0, const void* e1, const vo
                     const void* e3, int mode, float sample_coeff, float alpha_diff, float denom,
                     void* prev_sample, int64_t n, int dtype, void* stream);
 
+/* a-2 + a-1 fused ("step_then_noise"): ONE launch that performs the reverse update of
+ * ldiff_plms_step on (sample, e0..e3) AND the forward noising of ldiff_laplace_qsample on `clean`
+ * (noisy = clean + Laplace(0, b)); the reference does both on latent-sized tensors inside the same
+ * loop iteration (segmentor.py:100-104 + ldiffusion.py:233-237).  Arguments as in the two entry
+ * points above; every output bit equals what the two separate launches produce. */
+int ldiff_plms_step_noise(const void* sample, const void* e0, const void* e1, const void* e2,
+                          const void* e3, int mode, float sample_coeff, float alpha_diff, float denom,
+                          void* prev_sample, const void* clean, void* noisy, const void* noise_in,
+                          const void* u_in, float b, uint64_t seed, uint64_t offset, int64_t n,
+                          int dtype, void* stream);
+
 /* ---- a-3  decode tail -> uint8 RGB + PIL gray ----------------------------
  * replaces diffusers decode_latents' tail + numpy_to_pil + PIL convert("L") +
  * the per-pixel stacking loop (pixel_latent_vector.py:80-93,
@@ -131,6 +142,21 @@ int ldiff_decode_tail_gray(const void* img, uint8_t* rgb_hwc, uint8_t* gray, int
 int ldiff_decode_tail_model_input(const void* img, uint8_t* rgb_hwc, uint8_t* gray, float* model_input,
                                   const float* host_mean3, const float* host_std3, int B, int H, int W,
                                   int64_t gray_batch_stride, int dtype, void* stream);
+
+/* the same pass with the per-step consumers of the decoder output fused in — what the tail already
+ * streams is not fetched again by separate launches.  Requires H % 16 == 0, W % 16 == 0, gray != NULL; every
+ * other pointer is optional (NULL = off), at least one must be given:
+ *   feat        channel feat_channel of [B, feat_ctot, H/16, W/16] (feat_dtype = dtype or LDIFF_F32) =
+ *               weighted gray of F.interpolate(img, (H/16, W/16), bilinear): the per-step body of
+ *               ldiffusion.py:240-247 (lift + gray + torch.cat), bit-identical to ldiff_bilinear_lift(gray=1);
+ *   small_rgb   [B,3,H/16,W/16] (image dtype): that lift before the gray (the source of ldiffusion.py:251);
+ *   label_plane the uint8 [B,H,W] ground truth `label` copied to label_plane + b*label_plane_stride (the
+ *               label slot of the pixel vectors, pixel_latent_vector.py:92 — replaces ldiff_copy_planes_u8);
+ *   label_small uint8 [B,1,H/16,W/16] = trunc(bilinear(label)) (ldiffusion.py:224-226). */
+int ldiff_decode_tail_fused(const void* img, uint8_t* rgb_hwc, uint8_t* gray, int B, int H, int W,
+                            int64_t gray_batch_stride, int dtype, void* feat, int feat_dtype, int feat_ctot,
+                            int feat_channel, void* small_rgb, const uint8_t* label, uint8_t* label_plane,
+                            int64_t label_plane_stride, uint8_t* label_small, void* stream);
 
 /* ---- a-4  bilinear lift + gray + concat ----------------------------------
  * replaces F.interpolate(mode='bilinear', align_corners=False) (+ weighted gray
@@ -165,12 +191,23 @@ int ldiff_bilinear_lift_backward(const float* grad_out, int Ctot, int dst_channe
  * to the input size) and segmentor.py:536 (argmax(softmax)) without ever
  * materialising full-resolution logits. */
 /* feat [B,Cin,h*w] planar fp32/bf16, weight [K,Cin] same dtype, bias fp32 [K]
- * (or NULL) -> logits fp32 [B,K,h*w].  bf16 runs on tcgen05 tensor cores. */
+ * (or NULL) -> logits fp32 [B,K,h*w].  bf16 runs on tcgen05 tensor cores.
+ * clear_i64 / n_clear (optional, NULL / 0): int64 counters this kernel zeroes as a side job — the
+ * confusion matrix that ldiff_lift_argmax_hist, enqueued behind it on the same stream, accumulates
+ * into — so that a pass needs no memset. */
 int ldiff_head_logits(const void* feat, const void* weight, const float* bias, float* logits,
-                      int B, int Cin, int K, int hw, int dtype, void* stream);
+                      int B, int Cin, int K, int hw, int dtype, int64_t* clear_i64, int n_clear,
+                      void* stream);
 /* logits fp32 [B,K,h,w] -> uint8 mask [B,H,W] */
 int ldiff_lift_argmax(const float* logits, uint8_t* mask, int B, int K, int h, int w, int H, int W,
                       void* stream);
+/* the same with the a-6 histogram fused in: C[(K+1),K] += counts of (gt, mask) over the whole batch while
+ * the mask bytes are still in registers (gt uint8 [B,H,W]; semantics of ldiff_confusion_hist, no gt LUT).
+ * xchg != NULL: the kernel's last block also pushes the finished matrix into every rank's peer window, as
+ * ldiff_confusion_hist_push does (channel = the window's channel).  K <= 15 and H >= 4h (the envelope
+ * kernel's domain); otherwise LDIFF_EUNSUPPORTED: use ldiff_lift_argmax + ldiff_confusion_hist. */
+int ldiff_lift_argmax_hist(const float* logits, uint8_t* mask, const uint8_t* gt, int64_t* C, int B, int K,
+                           int h, int w, int H, int W, void* xchg, int channel, int* status, void* stream);
 /* cell form, replaces conductor.py:218-221: per-instance Linear(Cin,K) ->
  * softmax[:,1:] -> top-1 (+1); writes lut[b*lut_stride + inst_ids[i]] = class.
  * inst_feats [B,n_per_image,Cin] row-major fp32/bf16 (Cin % 8 == 0); inst_ids int32
@@ -178,12 +215,18 @@ int ldiff_lift_argmax(const float* logits, uint8_t* mask, int B, int K, int h, i
 int ldiff_cell_classify(const void* inst_feats, const void* weight, const float* bias,
                         const int32_t* inst_ids, uint8_t* lut, int lut_size, int64_t lut_stride,
                         float* logits_out, int n_per_image, int B, int Cin, int K, int dtype,
-                        int* status, void* stream);
+                        int64_t* clear_i64, int n_clear /* as ldiff_head_logits */, int* status, void* stream);
 /* replaces the painting loop conductor.py:224-231 (+ segmentor.py:536):
  * mask[b,p] = lut[b*lut_stride + inst[b,p]]; ids outside [0,lut_size) -> 0 and
  * LDIFF_STATUS_INST_RANGE. */
 int ldiff_lut_paint(const int32_t* inst, const uint8_t* lut, uint8_t* mask, int64_t n_per_image,
                     int B, int lut_size, int64_t lut_stride, int* status, void* stream);
+/* painting + the a-6 histogram in one pass (6 B/pixel instead of 5 + 2): C[(K+1),K] += counts of
+ * (gt, mask) over the whole batch; xchg / channel as in ldiff_lift_argmax_hist.  K <= 15,
+ * n_per_image % 16 == 0, 16-byte aligned planes; otherwise use ldiff_lut_paint + ldiff_confusion_hist. */
+int ldiff_lut_paint_hist(const int32_t* inst, const uint8_t* lut, uint8_t* mask, const uint8_t* gt,
+                         int64_t* C, int64_t n_per_image, int B, int lut_size, int64_t lut_stride, int K,
+                         void* xchg, int channel, int* status, void* stream);
 /* first-maximum argmax over the channel axis of [B,K,HW] (the argmax taken
  * inside utils.py:56, :85, evaluate.py:12, :30 on one-hot / logit inputs). */
 int ldiff_argmax_channels(const void* x, uint8_t* out, int B, int K, int64_t hw, int dtype,
@@ -217,8 +260,10 @@ int ldiff_confusion_hist_batched(const uint8_t* pred, const uint8_t* gt, const u
  *   ldiff_xchg_connect_ipc   handles = world * 64 bytes in rank order (own entry ignored)
  *   ldiff_xchg_connect_local same-process windows (several "ranks" on one GPU: tests)
  *   ldiff_confusion_hist_push  ldiff_confusion_hist whose last block stores the finished matrix C
- *                            into row `rank`, channel `channel` of EVERY rank's window and raises
- *                            that row's flag (st.release.sys after a system fence)
+ *                            into row `rank`, channel `channel` of EVERY rank's window: plain 8-byte
+ *                            st.relaxed.sys stores, each word = half a counter + the step number (data
+ *                            and "has landed" in one store; no system fence, no separate flag).  The
+ *                            fused producers ldiff_lut_paint_hist / ldiff_lift_argmax_hist carry the same tail
  *   ldiff_xchg_reduce        one block: the j-th reduce of a rank waits for the j-th push of
  *                            every rank and channel, then writes the sum of the world rows to
  *                            out [channels][n_i64]

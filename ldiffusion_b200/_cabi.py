@@ -10,10 +10,10 @@ from ctypes import c_char_p, c_float, c_int, c_int64, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libldiff_sm100.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 F32, BF16, U8 = 0, 1, 2
-TUNE_ARGMAX_PERSIST_BLOCKS, TUNE_DECODE_TAIL_SMS, TUNE_DECODE_TAIL_TMA = 0, 1, 2
+TUNE_ARGMAX_VARIANT, TUNE_DECODE_TAIL_SMS, TUNE_DECODE_TAIL_TMA = 0, 1, 2
 STATUS_PRED_RANGE, STATUS_INST_RANGE, STATUS_SW_INF, STATUS_XCHG_TIMEOUT, STATUS_LABEL_RANGE = 1, 2, 4, 8, 16
 
 # name -> (restype, argtypes); mirrors include/ldiff.h one to one
@@ -30,10 +30,16 @@ SIGNATURES = {
                                       c_int, c_int, c_void_p]),
     "ldiff_plms_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float,
                                 c_float, c_float, c_void_p, c_int64, c_int, c_void_p]),
+    "ldiff_plms_step_noise": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float,
+                                      c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_float, c_uint64, c_uint64, c_int64, c_int, c_void_p]),
     "ldiff_decode_tail_gray": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64,
                                        c_int, c_void_p]),
     "ldiff_decode_tail_model_input": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                               c_int, c_int, c_int64, c_int, c_void_p]),
+    "ldiff_decode_tail_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int, c_void_p,
+                                        c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
+                                        c_void_p]),
     "ldiff_bilinear_lift": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int64, c_int64, c_void_p,
                                     c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "ldiff_bilinear_lift_multi": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int64, c_int64, c_void_p,
@@ -41,11 +47,15 @@ SIGNATURES = {
     "ldiff_bilinear_lift_backward": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,
                                              c_int64, c_int64, c_int, c_int, c_void_p]),
     "ldiff_head_logits": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
-                                  c_int, c_void_p]),
+                                  c_int, c_void_p, c_int, c_void_p]),
+    "ldiff_lift_argmax_hist": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                       c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    "ldiff_lut_paint_hist": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int,
+                                     c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "ldiff_lift_argmax": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                   c_void_p]),
     "ldiff_cell_classify": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p,
-                                    c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+                                    c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "ldiff_copy_planes_u8": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int64, c_void_p]),
     "ldiff_lut_paint": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int64,
                                 c_void_p, c_void_p]),

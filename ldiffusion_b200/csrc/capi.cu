@@ -7,23 +7,28 @@ namespace ldiff {
 
 unsigned long long g_launches = 0;
 
+int current_device() {
+  int dev = -1;
+  return cudaGetDevice(&dev) == cudaSuccess ? dev : -1;
+}
+
+// SM count of the CURRENT device; one cached slot per device ordinal (a process may drive several GPUs)
 int sm_count() {
-  static int cached = 0;
-  if (cached == 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-      cached = n;
-    else
-      cached = 148;                                   // B200
+  static int cached[kMaxDevices] = {};
+  const int dev = current_device();
+  if (dev < 0 || dev >= kMaxDevices) return 148;      // B200
+  int n = __atomic_load_n(&cached[dev], __ATOMIC_RELAXED);
+  if (n == 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    __atomic_store_n(&cached[dev], n, __ATOMIC_RELAXED);
   }
-  return cached;
+  return n;
 }
 
 // tuning knobs: -1 = not set yet (the environment variable, else the built-in default, is taken on first use)
 static int g_tune[LDIFF_TUNE_COUNT] = {-1, -1, -1};
-static const char* const kTuneEnv[LDIFF_TUNE_COUNT] = {"LDIFF_ARGMAX_PERSIST", "LDIFF_DT_SMS", "LDIFF_DT_TMA"};
-static const int kTuneDefault[LDIFF_TUNE_COUNT] = {0, 0, 0};
+static const char* const kTuneEnv[LDIFF_TUNE_COUNT] = {"LDIFF_ARGMAX_VARIANT", "LDIFF_DT_SMS", "LDIFF_DT_TMA"};
+static const int kTuneDefault[LDIFF_TUNE_COUNT] = {0, 0, 1};
 
 int tune_get(int knob) {
   int v = __atomic_load_n(&g_tune[knob], __ATOMIC_RELAXED);

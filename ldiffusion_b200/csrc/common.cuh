@@ -11,7 +11,9 @@ namespace ldiff {
 // ---- launch bookkeeping ----------------------------------------------------
 extern unsigned long long g_launches;          // defined in capi.cu
 
-int sm_count();                                // cached per process (current device)
+constexpr int kMaxDevices = 64;
+int current_device();                          // cudaGetDevice, -1 on error
+int sm_count();                                // SM count of the CURRENT device (cached per device)
 
 // ldiff_tune knobs (capi.cu); first use reads the environment (LDIFF_ARGMAX_PERSIST, LDIFF_DT_SMS)
 int tune_get(int knob);
@@ -71,6 +73,13 @@ template <> struct Vec8<__nv_bfloat16> {
     __stcs(reinterpret_cast<uint4*>(p), make_uint4(w[0], w[1], w[2], w[3]));
   }
 };
+
+// Optional side job of a chain's FIRST kernel: zero the int64 counters (a confusion matrix) that a later
+// kernel of the same stream accumulates into, so a pass needs no memset node that every chain waits for.
+__device__ __forceinline__ void clear_counters(unsigned long long* __restrict__ p, int n) {
+  if (p != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
+    for (int i = threadIdx.x; i < n; i += blockDim.x) p[i] = 0ull;
+}
 
 __device__ __forceinline__ float to_f32(float x) { return x; }
 __device__ __forceinline__ float to_f32(__nv_bfloat16 x) { return __bfloat162float(x); }

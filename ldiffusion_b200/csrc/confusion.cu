@@ -16,51 +16,10 @@
 #include <cstdlib>
 #include <cstring>
 
-#include "common.cuh"
+#include "hist.cuh"
 
 namespace ldiff {
 
-// bytes of w that are >= k (k <= 128) get 0x80, others 0
-__device__ __forceinline__ uint32_t bytes_ge(uint32_t w, uint32_t k) {
-  return (((w & 0x7f7f7f7fu) + (0x80u - k) * 0x01010101u) | w) & 0x80808080u;
-}
-
-// ---- peer exchange window (multi-GPU): one per rank, mapped into every peer over NVLink -------------
-// The only cross-rank step of the path is the SUM of the int64 matrices.  Instead of a separate
-// collective, the LAST block of the histogram kernel stores the finished matrix straight into every
-// peer's window (plain 8-byte stores over NVLink peer mappings); a one-block kernel on each rank then
-// waits for the W rows and adds them.  Every 8-byte word carries half a counter and the step number
-// (data and "it has landed" travel in one atomic store, as in NCCL's LL protocol), so the pusher
-// needs no system fence and no separate flag: its tail is one dependent read of the matrix and a
-// burst of fire-and-forget stores.  Rows are overwritten, never accumulated, so nothing is zeroed
-// between steps; kXSlots ring slots keep a row alive until every rank has read it (ordering
-// contract in ldiff.h).
-constexpr int kXSlots = 4, kXMaxWorld = 16, kXMaxChan = 4, kXHeaderBytes = 256;
-struct XchgHeader {
-  unsigned long long step[kXMaxChan];                          // pushes completed by THIS rank, per channel
-  unsigned long long reduced;                                  // reduces completed by THIS rank
-  unsigned int ticket[kXMaxChan];                              // last-block election of the histogram grid
-};
-static_assert(sizeof(XchgHeader) <= kXHeaderBytes, "header does not fit");
-struct XchgPush {                                              // by-value kernel argument; win == nullptr: off
-  XchgHeader* win;
-  int world, rank, channels, channel, n;
-  unsigned long long peers[kXMaxWorld];                        // window base of every rank, as mapped here
-};
-// row of (slot, source rank, channel): 2*n words, word 2*bin = lo32 | tag<<32, word 2*bin+1 = hi32 | tag<<32
-__device__ __forceinline__ unsigned long long* xchg_row(unsigned long long base, int slot, int src, int chan,
-                                                        int world, int channels, int n) {
-  return reinterpret_cast<unsigned long long*>(base + kXHeaderBytes) +
-         ((int64_t)(slot * world + src) * channels + chan) * (2 * n);
-}
-__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -75,13 +34,12 @@ confusion_hist_body(const uint8_t* __restrict__ pred, const uint8_t* __restrict_
   extern __shared__ uint32_t hist[];                 // [nbins][R]
   __shared__ uint8_t lut[256];
   const int nbins = (K + 1) * K;
-  for (int i = threadIdx.x; i < nbins * R; i += blockDim.x) hist[i] = 0;
+  BlockHist<R, SMALLK> h;
+  h.init(hist, K);
   if (HAS_LUT)
     for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = gt_lut[i];
-  // (push) this launch's step number: only the previous launch's last block ever changes the counter,
-  // so it is read here, long before the tail needs it, instead of on the tail's dependent chain
   __shared__ unsigned long long s_step;
-  if (PUSH && threadIdx.x == 0) s_step = __ldcg(&px.win->step[px.channel]) + 1;
+  if (PUSH && threadIdx.x == 0) s_step = xchg_step_of_launch(px);
   __syncthreads();
 
   // grid.y = image (batched form: one matrix per image)
@@ -89,35 +47,12 @@ confusion_hist_body(const uint8_t* __restrict__ pred, const uint8_t* __restrict_
   gt += (int64_t)blockIdx.y * n;
   C += (int64_t)blockIdx.y * nbins;
 
-  uint32_t* my = hist + (threadIdx.x & (R - 1));     // this lane's replica column
-  uint32_t bad = 0;
-  const uint32_t k4 = (uint32_t)K * 0x01010101u;
-
-  auto pixel = [&](uint32_t p, uint32_t g) {         // generic path
-    if (HAS_LUT) g = lut[g];
-    g = min(g, (uint32_t)K);
-    if (p >= (uint32_t)K) { bad = 1; p = 0; }
-    atomicAdd(my + (g * K + p) * R, 1u);
-  };
+  auto pixel = [&](uint32_t p, uint32_t g) { h.pixel(p, HAS_LUT ? (uint32_t)lut[g] : g); };
   auto word = [&](uint32_t pw, uint32_t gw) {
-    if (SMALLK) {
-      if (HAS_LUT)
-        gw = (uint32_t)lut[gw & 0xff] | ((uint32_t)lut[(gw >> 8) & 0xff] << 8) |
-             ((uint32_t)lut[(gw >> 16) & 0xff] << 16) | ((uint32_t)lut[gw >> 24] << 24);
-      const uint32_t gm = (bytes_ge(gw, K) >> 7) * 0xffu;          // 0xff where gt >= K
-      const uint32_t gc = (gw & ~gm) | (k4 & gm);
-      const uint32_t po = bytes_ge(pw, K);
-      bad |= po;
-      const uint32_t pc = pw & ~((po >> 7) * 0xffu);
-      const uint32_t bins = gc * (uint32_t)K + pc;                  // four byte-sized bin indices
-      atomicAdd(my + (bins & 0xffu) * R, 1u);
-      atomicAdd(my + ((bins >> 8) & 0xffu) * R, 1u);
-      atomicAdd(my + ((bins >> 16) & 0xffu) * R, 1u);
-      atomicAdd(my + (bins >> 24) * R, 1u);
-    } else {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) pixel((pw >> (8 * k)) & 0xffu, (gw >> (8 * k)) & 0xffu);
-    }
+    if (HAS_LUT)
+      gw = (uint32_t)lut[gw & 0xff] | ((uint32_t)lut[(gw >> 8) & 0xff] << 8) |
+           ((uint32_t)lut[(gw >> 16) & 0xff] << 16) | ((uint32_t)lut[gw >> 24] << 24);
+    h.word(pw, gw);
   };
 
   // [0,head) scalar until both streams are 16-byte aligned (all of it if they are
@@ -138,42 +73,10 @@ confusion_hist_body(const uint8_t* __restrict__ pred, const uint8_t* __restrict_
     word(a.x, b.x); word(a.y, b.y); word(a.z, b.z); word(a.w, b.w);
   }
   for (int64_t i = head + (nvec << 4) + gtid; i < n; i += stride) pixel(pred[i], gt[i]);
-  if (bad) atomicOr(status, LDIFF_STATUS_PRED_RANGE);
   __syncthreads();
-
-  for (int bin = threadIdx.x; bin < nbins; bin += blockDim.x) {
-    unsigned long long s = 0;
-#pragma unroll 8
-    for (int r = 0; r < R; ++r) s += hist[bin * R + ((r + threadIdx.x) & (R - 1))];
-    if (s) atomicAdd(C + bin, s);
-  }
-  if (!PUSH) return;
-
+  h.flush(hist, C, status);
   // ---- fused exchange: the last block to finish owns the complete matrix and pushes it to every rank
-  __shared__ int s_last;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0)
-    s_last = atomicAdd(&px.win->ticket[px.channel], 1u) == gridDim.x * gridDim.y - 1;
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  const unsigned long long step = s_step;
-  const unsigned long long tag = (step & 0xffffffffull) << 32;
-  const int slot = (int)(step % kXSlots);
-  for (int bin = threadIdx.x; bin < px.n; bin += blockDim.x) {
-    const unsigned long long v = __ldcg(C + bin);
-    const unsigned long long w0 = (v & 0xffffffffull) | tag, w1 = (v >> 32) | tag;
-    for (int q = 0; q < px.world; ++q) {
-      unsigned long long* row = xchg_row(px.peers[q], slot, px.rank, px.channel, px.world, px.channels, px.n);
-      st_relaxed_sys(row + 2 * bin, w0);
-      st_relaxed_sys(row + 2 * bin + 1, w1);
-    }
-  }
-  if (threadIdx.x == 0) {
-    px.win->step[px.channel] = step;
-    px.win->ticket[px.channel] = 0;                  // re-armed for the next launch (stream-ordered)
-  }
+  if (PUSH) xchg_push_tail(C, px, s_step, gridDim.x * gridDim.y);
 }
 
 template <int R, bool SMALLK, bool HAS_LUT>
@@ -192,6 +95,59 @@ confusion_hist_push_kernel(const uint8_t* __restrict__ pred, const uint8_t* __re
                            const uint8_t* __restrict__ gt_lut, unsigned long long* __restrict__ C,
                            int64_t n, int K, int* __restrict__ status, XchgPush px) {
   confusion_hist_body<R, SMALLK, HAS_LUT, true>(pred, gt, gt_lut, C, n, K, status, px);
+}
+
+// ----------------------------------------------------------------------------
+// a-5 (cell form) + a-6 in one pass: mask[b,p] = lut[b][inst[b,p]] (conductor.py:224-231 + segmentor.py:536)
+// AND C[gt[b,p]][mask[b,p]] += 1 while the mask byte is still in a register — the stand-alone histogram
+// would read the 1 B/pixel mask back and needs its own launch.  6 B/pixel: 4 (instance id) + 1 (gt) in,
+// 1 (mask) out.  K <= 15 (byte-sized bins); one matrix for the whole batch (grid.y = image picks the LUT).
+template <bool PUSH>
+__global__ void __launch_bounds__(512, 2)
+lut_paint_hist_kernel(const int32_t* __restrict__ inst, const uint8_t* __restrict__ lut, uint8_t* __restrict__ mask,
+                      const uint8_t* __restrict__ gt, unsigned long long* __restrict__ C, int64_t n, int lut_size,
+                      int64_t lut_stride, int K, int* __restrict__ status, XchgPush px) {
+  extern __shared__ uint32_t hist[];                 // [nbins][32]
+  BlockHist<32, true> h;
+  h.init(hist, K);
+  __shared__ unsigned long long s_step;
+  if (PUSH && threadIdx.x == 0) s_step = xchg_step_of_launch(px);
+  __syncthreads();
+  const int b = blockIdx.y;
+  const uint8_t* l = lut + b * lut_stride;           // (global LUT through L1: beats a shared-memory copy at 800 entries)
+  const int32_t* in = inst + b * n;
+  const uint8_t* g = gt + b * n;
+  uint8_t* out = mask + b * n;
+  int badid = 0;
+  auto look4 = [&](int4 q) -> uint32_t {
+    const uint32_t a = (uint32_t)q.x, bb = (uint32_t)q.y, c = (uint32_t)q.z, d = (uint32_t)q.w;
+    if (max(max(a, bb), max(c, d)) < (uint32_t)lut_size)          // common case: all four in range
+      return (uint32_t)l[a] | ((uint32_t)l[bb] << 8) | ((uint32_t)l[c] << 16) | ((uint32_t)l[d] << 24);
+    badid = 1;
+    uint32_t w = 0;
+    if (a < (uint32_t)lut_size) w |= l[a];
+    if (bb < (uint32_t)lut_size) w |= (uint32_t)l[bb] << 8;
+    if (c < (uint32_t)lut_size) w |= (uint32_t)l[c] << 16;
+    if (d < (uint32_t)lut_size) w |= (uint32_t)l[d] << 24;
+    return w;
+  };
+  const int64_t nvec = n >> 4;                       // (host: n % 16 == 0, 16-byte aligned planes)
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
+    const int4* p = reinterpret_cast<const int4*>(in) + 4 * v;
+    int4 q[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) q[j] = __ldcs(p + j);
+    const uint4 gw = __ldcs(reinterpret_cast<const uint4*>(g) + v);
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) w[j] = look4(q[j]);
+    __stcs(reinterpret_cast<uint4*>(out) + v, make_uint4(w[0], w[1], w[2], w[3]));
+    h.word(w[0], gw.x); h.word(w[1], gw.y); h.word(w[2], gw.z); h.word(w[3], gw.w);
+  }
+  if (badid) atomicOr(status, LDIFF_STATUS_INST_RANGE);
+  __syncthreads();
+  h.flush(hist, C, status);
+  if (PUSH) xchg_push_tail(C, px, s_step, gridDim.x * gridDim.y);
 }
 
 // One block per rank.  The j-th reduce of a rank adds the rows of every rank's j-th push: each thread
@@ -418,16 +374,52 @@ extern "C" int ldiff_xchg_destroy(void* handle) {
   return LDIFF_OK;
 }
 
+int ldiff::xchg_push_args(void* handle, int channel, int n_i64, XchgPush* px) {
+  Xchg* x = static_cast<Xchg*>(handle);
+  if (!x || channel < 0 || channel >= x->channels || x->n != n_i64) return LDIFF_EINVAL;
+  if (!x->peers[x->rank]) return LDIFF_EINVAL;       // not connected yet
+  *px = XchgPush{reinterpret_cast<XchgHeader*>(x->base), x->world, x->rank, x->channels, channel, x->n, {0}};
+  for (int q = 0; q < x->world; ++q) px->peers[q] = x->peers[q];
+  return LDIFF_OK;
+}
+
+extern "C" int ldiff_lut_paint_hist(const int32_t* inst, const uint8_t* lut, uint8_t* mask, const uint8_t* gt,
+                                    int64_t* C, int64_t n_per_image, int B, int lut_size, int64_t lut_stride,
+                                    int K, void* xchg, int channel, int* status, void* stream) {
+  if (!inst || !lut || !mask || !gt || !C || !status || n_per_image < 0 || B < 0 || lut_size < 1 || K < 1)
+    return LDIFF_EINVAL;
+  if (K > 15 || B > 65535) return LDIFF_EUNSUPPORTED;  // byte-sized bins; larger K: ldiff_lut_paint + ldiff_confusion_hist
+  XchgPush px{};
+  if (xchg) {
+    const int rc = xchg_push_args(xchg, channel, (K + 1) * K, &px);
+    if (rc != LDIFF_OK) return rc;
+  }
+  if (n_per_image == 0 || B == 0) return xchg ? LDIFF_EINVAL : LDIFF_OK;   // a push needs a launch
+  if (!aligned16(inst) || !aligned16(mask) || !aligned16(gt) || (n_per_image % 16)) return LDIFF_EALIGN;
+  const int threads = 512;
+  const size_t smem = (size_t)(K + 1) * K * 32 * 4;
+  int64_t bx = ((n_per_image >> 4) + threads - 1) / threads;
+  const int64_t cap = ((int64_t)sm_count() * 2 + B - 1) / B;     // 2 blocks of 512 threads per SM over the batch
+  if (bx > cap) bx = cap > 0 ? cap : 1;
+  const dim3 grid((unsigned)bx, (unsigned)B);
+  unsigned long long* Cu = reinterpret_cast<unsigned long long*>(C);
+  if (xchg)
+    lut_paint_hist_kernel<true><<<grid, threads, smem, (cudaStream_t)stream>>>(inst, lut, mask, gt, Cu, n_per_image,
+                                                                             lut_size, lut_stride, K, status, px);
+  else
+    lut_paint_hist_kernel<false><<<grid, threads, smem, (cudaStream_t)stream>>>(inst, lut, mask, gt, Cu, n_per_image,
+                                                                              lut_size, lut_stride, K, status, px);
+  return check_launch();
+}
+
 extern "C" int ldiff_confusion_hist_push(const uint8_t* pred, const uint8_t* gt, const uint8_t* gt_lut,
                                          int64_t* C, int64_t n, int K, void* xchg, int channel,
                                          int* status, void* stream) {
   if (!pred || !gt || !C || !status || !xchg || n < 1 || K < 1) return LDIFF_EINVAL;
   if (K > 128) return LDIFF_EUNSUPPORTED;
-  Xchg* x = static_cast<Xchg*>(xchg);
-  if (channel < 0 || channel >= x->channels || x->n != (K + 1) * K) return LDIFF_EINVAL;
-  if (!x->peers[x->rank]) return LDIFF_EINVAL;       // not connected yet
-  XchgPush px{reinterpret_cast<XchgHeader*>(x->base), x->world, x->rank, x->channels, channel, x->n, {0}};
-  for (int q = 0; q < x->world; ++q) px.peers[q] = x->peers[q];
+  XchgPush px{};
+  const int rc = xchg_push_args(xchg, channel, (K + 1) * K, &px);
+  if (rc != LDIFF_OK) return rc;
   return launch_confusion(pred, gt, gt_lut, C, n, 1, K, status, (cudaStream_t)stream, px);
 }
 

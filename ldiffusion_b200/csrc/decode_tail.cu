@@ -99,11 +99,71 @@ struct NormArgs {            // optional fused model-input output (N1 of SURVEY 
   float mean[3], stdv[3];
 };
 
-template <typename T, bool RGB, bool GRAY, bool NORM>
+// Optional outputs fused into the tail (device pointers, null = off).  Valid for H % 16 == 0 and
+// W % 16 == 0, where the reference's 16x bilinear down-sample (align_corners=False) is exactly the
+// 2x2 footprint at rows / columns 16d+7, 16d+8 with weights 0.5: src = fma(16, d + 0.5, -0.5) = 16d + 7.5.
+// The thread that owns columns 16g .. 16g+15 of row 16e+7 re-reads its two footprint pixels and the two
+// below them (scalar loads, L1/L2 hits: 1/16 of the warps, 4 loads per channel) and evaluates the pinned
+// lerp chain of bilinear.cu — the tail already streams every byte those gathers used to fetch again.
+struct TailExtras {
+  void* feat;                  // a-4 feature (ldiffusion.py:240-247): weighted gray of the lift -> channel feat_ch
+  int feat_ctot, feat_ch;      //   of [B, feat_ctot, H/16, W/16]; storage = the image dtype, or fp32 (feat_f32)
+  int feat_f32;
+  void* small_rgb;             // [B,3,H/16,W/16] image dtype: the lift itself (source of ldiffusion.py:251)
+  const uint8_t* label;        // uint8 [B,H,W] ground truth ...
+  uint8_t* label_plane;        // ... copied into the label slot of the pixel vectors (pixel_latent_vector.py:92)
+  int64_t label_plane_stride;
+  uint8_t* label_small;        // ... and uint8 [B,1,H/16,W/16] = trunc(bilinear(label)) (ldiffusion.py:224-226)
+  int W, fh, gpr, gpr_shift;   // row width, H/16, 16-pixel groups per row (= W/16), log2(gpr) or -1
+};
+
+__device__ __forceinline__ float half_lerp(float a, float b) {        // lerp_h(0.5, a, 0.5, b) of bilinear.cu
+  return __fmaf_rn(0.5f, a, __fmul_rn(0.5f, b));
+}
+
+template <typename T>
+__device__ __forceinline__ void tail_extras(const T* __restrict__ img, const TailExtras& ex, int64_t b, int64_t hw,
+                                            int gidx) {
+  const int64_t p = (int64_t)gidx << 4;
+  if (ex.label_plane)
+    __stcs(reinterpret_cast<uint4*>(ex.label_plane + b * ex.label_plane_stride + p),
+           __ldg(reinterpret_cast<const uint4*>(ex.label + b * hw + p)));
+  const int y = ex.gpr_shift >= 0 ? (gidx >> ex.gpr_shift) : (gidx / ex.gpr);
+  if ((y & 15) != 7) return;
+  const int g = gidx - y * ex.gpr;
+  const int64_t o = ((int64_t)(y >> 4)) * ex.gpr + g;                 // output pixel (y/16, g) of a plane
+  const int64_t fplane = (int64_t)ex.fh * ex.gpr;
+  if (ex.feat || ex.small_rgb) {
+    float v[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const T* r0 = img + (b * 3 + c) * hw + p + 7;
+      const T* r1 = r0 + ex.W;
+      v[c] = half_lerp(half_lerp(to_f32(__ldg(r0)), to_f32(__ldg(r0 + 1))),
+                       half_lerp(to_f32(__ldg(r1)), to_f32(__ldg(r1 + 1))));
+      if (ex.small_rgb) static_cast<T*>(ex.small_rgb)[(b * 3 + c) * fplane + o] = from_f32<T>(v[c]);
+    }
+    if (ex.feat) {
+      const float gr = __fadd_rn(__fadd_rn(__fmul_rn(0.2989f, v[0]), __fmul_rn(0.5870f, v[1])), __fmul_rn(0.1140f, v[2]));
+      const int64_t fo = (b * ex.feat_ctot + ex.feat_ch) * fplane + o;
+      if (ex.feat_f32) static_cast<float*>(ex.feat)[fo] = gr;
+      else static_cast<T*>(ex.feat)[fo] = from_f32<T>(gr);
+    }
+  }
+  if (ex.label_small) {
+    const uint8_t* r0 = ex.label + b * hw + p + 7;
+    const uint8_t* r1 = r0 + ex.W;
+    const float v = half_lerp(half_lerp((float)__ldg(r0), (float)__ldg(r0 + 1)),
+                              half_lerp((float)__ldg(r1), (float)__ldg(r1 + 1)));
+    ex.label_small[b * fplane + o] = from_f32<uint8_t>(v);
+  }
+}
+
+template <typename T, bool RGB, bool GRAY, bool NORM, bool EXTRA = false>
 __global__ void __launch_bounds__(256)
 decode_tail_vec16_kernel(const T* __restrict__ img, uint8_t* __restrict__ rgb,
                          uint8_t* __restrict__ gray, int64_t hw, int groups_per_img,
-                         int64_t gray_batch_stride, NormArgs na) {
+                         int64_t gray_batch_stride, NormArgs na, TailExtras ex = TailExtras{}) {
   // a channel value has 256 possible inputs: the two IEEE divisions are tabulated once per block
   __shared__ float s_norm[NORM ? 3 * 256 : 1];
   if (NORM) {
@@ -119,6 +179,7 @@ decode_tail_vec16_kernel(const T* __restrict__ img, uint8_t* __restrict__ rgb,
   for (int gidx = blockIdx.x * blockDim.x + threadIdx.x; gidx < groups_per_img; gidx += stride) {
     const int64_t p = (int64_t)gidx << 4;
     const T* base = img + b * 3 * hw + p;
+    if (EXTRA) tail_extras<T>(img, ex, b, hw, gidx);
     uint32_t q[3][16];                                 // float bits 0x4B400000 | value
 #pragma unroll
     for (int c = 0; c < 3; ++c) quant16(base + c * hw, q[c]);
@@ -172,9 +233,7 @@ decode_tail_vec16_kernel(const T* __restrict__ img, uint8_t* __restrict__ rgb,
 // ----------------------------------------------------------------------------
 constexpr int kDtTile = 4096;      // pixels per tile = 256 threads x 16 pixels
 // stages in flight: bf16 4 x 3 x 8 KB = 96 KB per CTA, two CTAs per SM; fp32 4 x 3 x 16 KB = 192 KB, one CTA per SM
-template <typename T> struct DtPipe;
-template <> struct DtPipe<__nv_bfloat16> { static constexpr int kStages = 4, kCtasPerSm = 2; };
-template <> struct DtPipe<float> { static constexpr int kStages = 4, kCtasPerSm = 1; };
+// (pipeline shape = template parameters STAGES x CTAS of the kernel; LDIFF_TUNE_DECODE_TAIL_TMA picks one)
 
 __device__ __forceinline__ uint32_t dt_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void dt_mbar_init(uint64_t* bar, uint32_t count) {
@@ -221,12 +280,12 @@ __device__ __forceinline__ void quant16_staged(const float* p, uint32_t (&q)[16]
 }
 
 // grid = persistent CTAs; tile t of the job = image t / tiles_per_img, pixels (t % tiles_per_img) * kDtTile ...
-template <typename T, bool RGB, bool GRAY>
-__global__ void __launch_bounds__(256, DtPipe<T>::kCtasPerSm)
+template <typename T, bool RGB, bool GRAY, bool EXTRA, int STAGES, int CTAS>
+__global__ void __launch_bounds__(256, CTAS)
 decode_tail_tma_kernel(const T* __restrict__ img, uint8_t* __restrict__ rgb,
                        uint8_t* __restrict__ gray, int64_t hw, int tiles_per_img, int total_tiles,
-                       int64_t gray_batch_stride) {
-  constexpr int kDtStages = DtPipe<T>::kStages;
+                       int64_t gray_batch_stride, TailExtras ex) {
+  constexpr int kDtStages = STAGES;
   extern __shared__ __align__(128) uint8_t dt_smem[];            // [kDtStages][3][kDtTile] T
   __shared__ __align__(8) uint64_t full[kDtStages];
   T* buf = reinterpret_cast<T*>(dt_smem);
@@ -261,6 +320,7 @@ decode_tail_tma_kernel(const T* __restrict__ img, uint8_t* __restrict__ rgb,
     const int s = k % kDtStages;
     const int64_t b = t / tiles_per_img;
     const int64_t p = (int64_t)(t - (int)b * tiles_per_img) * kDtTile + tid * 16;
+    if (EXTRA) tail_extras<T>(img, ex, b, hw, (int)(p >> 4));      // (global loads: overlap the wait)
     dt_mbar_wait(&full[s], (uint32_t)(k / kDtStages) & 1u);
     uint32_t q[3][16];
 #pragma unroll
@@ -323,34 +383,74 @@ decode_tail_scalar_kernel(const T* __restrict__ img, uint8_t* __restrict__ rgb,
   }
 }
 
+// per-device attribute bookkeeping: cudaFuncSetAttribute applies to the CURRENT device only
+template <typename F>
+static void ensure_smem_attr(F kernel, int bytes, bool (&done)[kMaxDevices]) {
+  const int dev = current_device();
+  if (dev < 0 || dev >= kMaxDevices) { cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); return; }
+  if (!done[dev]) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    done[dev] = true;
+  }
+}
+
+template <typename T, bool RGB, bool GRAY, bool EXTRA, int STAGES, int CTAS>
+static void launch_tma_one(const T* p, uint8_t* rgb, uint8_t* gray, int64_t hw, int tiles_per_img, int total,
+                           int64_t gray_batch_stride, const TailExtras& ex, cudaStream_t st) {
+  static bool attr[kMaxDevices] = {};
+  const size_t smem = (size_t)STAGES * 3 * kDtTile * sizeof(T);
+  auto k = decode_tail_tma_kernel<T, RGB, GRAY, EXTRA, STAGES, CTAS>;
+  ensure_smem_attr(k, (int)smem, attr);
+  const int cap = CTAS * sm_count();
+  const int grid = total < cap ? total : cap;
+  k<<<grid, 256, smem, st>>>(p, rgb, gray, hw, tiles_per_img, total, gray_batch_stride, ex);
+}
+
+// pipeline shapes (stages x CTAs per SM) selectable through LDIFF_TUNE_DECODE_TAIL_TMA: smem in flight per SM is
+// stages * CTAs * 3 planes * 4096 px * sizeof(T)
+template <typename T> struct TmaShapes;
+template <> struct TmaShapes<__nv_bfloat16> {
+  template <bool RGB, bool GRAY, bool EXTRA>
+  static void launch(int variant, const __nv_bfloat16* p, uint8_t* rgb, uint8_t* gray, int64_t hw, int tpi, int total,
+                     int64_t gbs, const TailExtras& ex, cudaStream_t st) {
+    typedef __nv_bfloat16 T;
+    switch (variant) {
+      case 2: launch_tma_one<T, RGB, GRAY, EXTRA, 3, 3>(p, rgb, gray, hw, tpi, total, gbs, ex, st); break;   // 216 KB
+      case 3: launch_tma_one<T, RGB, GRAY, EXTRA, 2, 4>(p, rgb, gray, hw, tpi, total, gbs, ex, st); break;   // 192 KB
+      case 4: launch_tma_one<T, RGB, GRAY, EXTRA, 2, 3>(p, rgb, gray, hw, tpi, total, gbs, ex, st); break;   // 144 KB
+      default: launch_tma_one<T, RGB, GRAY, EXTRA, 4, 2>(p, rgb, gray, hw, tpi, total, gbs, ex, st); break;  // 192 KB
+    }
+  }
+};
+template <> struct TmaShapes<float> {
+  template <bool RGB, bool GRAY, bool EXTRA>
+  static void launch(int variant, const float* p, uint8_t* rgb, uint8_t* gray, int64_t hw, int tpi, int total,
+                     int64_t gbs, const TailExtras& ex, cudaStream_t st) {
+    if (variant == 2 || variant == 3) launch_tma_one<float, RGB, GRAY, EXTRA, 2, 2>(p, rgb, gray, hw, tpi, total, gbs, ex, st);
+    else launch_tma_one<float, RGB, GRAY, EXTRA, 4, 1>(p, rgb, gray, hw, tpi, total, gbs, ex, st);
+  }
+};
+
 template <typename T>
 static int launch_decode_tail(const void* img, uint8_t* rgb, uint8_t* gray, int B, int H, int W,
-                              int64_t gray_batch_stride, NormArgs na, cudaStream_t st) {
+                              int64_t gray_batch_stride, NormArgs na, const TailExtras* exp, cudaStream_t st) {
   const int64_t hw = (int64_t)H * W;
   const int threads = 256;
   const bool vec_ok = (hw % 16 == 0) && aligned16(img) && aligned16(rgb) && aligned16(gray) &&
                       aligned16(na.out) && (gray_batch_stride % 16 == 0);
-  if (vec_ok && !na.out && (hw % kDtTile) == 0 && tune_get(LDIFF_TUNE_DECODE_TAIL_TMA) > 0 &&
-      (int64_t)B * (hw / kDtTile) <= 0x7fffffff) {
+  const bool extra = exp != nullptr;
+  if (extra && (!vec_ok || na.out || !gray)) return LDIFF_EUNSUPPORTED;      // (entry point checked the geometry)
+  const TailExtras ex = extra ? *exp : TailExtras{};
+  const int tma = tune_get(LDIFF_TUNE_DECODE_TAIL_TMA);
+  if (vec_ok && !na.out && (hw % kDtTile) == 0 && tma > 0 && (int64_t)B * (hw / kDtTile) <= 0x7fffffff) {
     const int tiles_per_img = (int)(hw / kDtTile), total = B * tiles_per_img;
-    const size_t smem = (size_t)DtPipe<T>::kStages * 3 * kDtTile * sizeof(T);
-    const int cap = DtPipe<T>::kCtasPerSm * sm_count();
-    const int grid = total < cap ? total : cap;
     const T* p = (const T*)img;
-#define DTT(R, G)                                                                                       \
-  do {                                                                                                  \
-    static bool attr = false;                                                                           \
-    if (!attr) {                                                                                        \
-      cudaFuncSetAttribute(decode_tail_tma_kernel<T, R, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                           (int)smem);                                                                  \
-      attr = true;                                                                                      \
-    }                                                                                                   \
-    decode_tail_tma_kernel<T, R, G><<<grid, 256, smem, st>>>(p, rgb, gray, hw, tiles_per_img, total,    \
-                                                            gray_batch_stride);                         \
-  } while (0)
-    if (rgb && gray) DTT(true, true);
-    else if (gray) DTT(false, true);
-    else DTT(true, false);
+#define DTT(R, G, E) TmaShapes<T>::template launch<R, G, E>(tma, p, rgb, gray, hw, tiles_per_img, total, \
+                                                            gray_batch_stride, ex, st)
+    if (extra) { if (rgb) DTT(true, true, true); else DTT(false, true, true); }
+    else if (rgb && gray) DTT(true, true, false);
+    else if (gray) DTT(false, true, false);
+    else DTT(true, false, false);
 #undef DTT
     return check_launch();
   }
@@ -362,11 +462,11 @@ static int launch_decode_tail(const void* img, uint8_t* rgb, uint8_t* gray, int 
     const int need = (gpi + threads - 1) / threads;
     const T* p = (const T*)img;
     // resident blocks per SM of THIS instantiation (register-limited: 4 for fp32, 6-7 for bf16)
-#define DT(R, G, N)                                                                                   \
+#define DT(R, G, N, E)                                                                                \
   do {                                                                                                \
     static int occ = 0;                                                                               \
     if (occ == 0 && cudaOccupancyMaxActiveBlocksPerMultiprocessor(                                    \
-                        &occ, decode_tail_vec16_kernel<T, R, G, N>, threads, 0) != cudaSuccess)       \
+                        &occ, decode_tail_vec16_kernel<T, R, G, N, E>, threads, 0) != cudaSuccess)    \
       occ = 4;                                                                                        \
     const int sms = (tune_get(LDIFF_TUNE_DECODE_TAIL_SMS) > 0 && tune_get(LDIFF_TUNE_DECODE_TAIL_SMS) < sm_count())   \
                         ? tune_get(LDIFF_TUNE_DECODE_TAIL_SMS) : sm_count();                          \
@@ -374,18 +474,21 @@ static int launch_decode_tail(const void* img, uint8_t* rgb, uint8_t* gray, int 
     if (cap < 1) cap = 1;                                                                             \
     const int iters = (need + cap - 1) / cap;                                                         \
     const dim3 grid((need + iters - 1) / iters, B);                                                   \
-    decode_tail_vec16_kernel<T, R, G, N><<<grid, threads, 0, st>>>(p, rgb, gray, hw, gpi,             \
-                                                                   gray_batch_stride, na);           \
+    decode_tail_vec16_kernel<T, R, G, N, E><<<grid, threads, 0, st>>>(p, rgb, gray, hw, gpi,          \
+                                                                      gray_batch_stride, na, ex);     \
   } while (0)
-    if (na.out) {
-      if (rgb && gray) DT(true, true, true);
-      else if (gray) DT(false, true, true);
-      else if (rgb) DT(true, false, true);
-      else DT(false, false, true);
+    if (extra) {
+      if (rgb) DT(true, true, false, true);
+      else DT(false, true, false, true);
+    } else if (na.out) {
+      if (rgb && gray) DT(true, true, true, false);
+      else if (gray) DT(false, true, true, false);
+      else if (rgb) DT(true, false, true, false);
+      else DT(false, false, true, false);
     } else {
-      if (rgb && gray) DT(true, true, false);
-      else if (gray) DT(false, true, false);
-      else DT(true, false, false);
+      if (rgb && gray) DT(true, true, false, false);
+      else if (gray) DT(false, true, false, false);
+      else DT(true, false, false, false);
     }
 #undef DT
   } else {
@@ -402,7 +505,7 @@ using namespace ldiff;
 
 static int decode_tail_entry(const void* img, uint8_t* rgb_hwc, uint8_t* gray, float* model_input,
                              const float* mean3, const float* std3, int B, int H, int W,
-                             int64_t gray_batch_stride, int dtype, void* stream) {
+                             int64_t gray_batch_stride, int dtype, const TailExtras* ex, void* stream) {
   if (!img || (!rgb_hwc && !gray && !model_input) || B < 0 || H < 0 || W < 0) return LDIFF_EINVAL;
   if (gray && gray_batch_stride < (int64_t)H * W) return LDIFF_EINVAL;
   if (model_input && (!mean3 || !std3)) return LDIFF_EINVAL;
@@ -415,16 +518,16 @@ static int decode_tail_entry(const void* img, uint8_t* rgb_hwc, uint8_t* gray, f
   }
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == LDIFF_F32)
-    return launch_decode_tail<float>(img, rgb_hwc, gray, B, H, W, gray_batch_stride, na, st);
+    return launch_decode_tail<float>(img, rgb_hwc, gray, B, H, W, gray_batch_stride, na, ex, st);
   if (dtype == LDIFF_BF16)
-    return launch_decode_tail<__nv_bfloat16>(img, rgb_hwc, gray, B, H, W, gray_batch_stride, na, st);
+    return launch_decode_tail<__nv_bfloat16>(img, rgb_hwc, gray, B, H, W, gray_batch_stride, na, ex, st);
   return LDIFF_EUNSUPPORTED;
 }
 
 extern "C" int ldiff_decode_tail_gray(const void* img, uint8_t* rgb_hwc, uint8_t* gray, int B, int H,
                                       int W, int64_t gray_batch_stride, int dtype, void* stream) {
   return decode_tail_entry(img, rgb_hwc, gray, nullptr, nullptr, nullptr, B, H, W, gray_batch_stride,
-                           dtype, stream);
+                           dtype, nullptr, stream);
 }
 
 extern "C" int ldiff_decode_tail_model_input(const void* img, uint8_t* rgb_hwc, uint8_t* gray,
@@ -433,5 +536,31 @@ extern "C" int ldiff_decode_tail_model_input(const void* img, uint8_t* rgb_hwc, 
                                              int64_t gray_batch_stride, int dtype, void* stream) {
   if (!model_input) return LDIFF_EINVAL;
   return decode_tail_entry(img, rgb_hwc, gray, model_input, host_mean3, host_std3, B, H, W,
-                           gray_batch_stride, dtype, stream);
+                           gray_batch_stride, dtype, nullptr, stream);
+}
+
+extern "C" int ldiff_decode_tail_fused(const void* img, uint8_t* rgb_hwc, uint8_t* gray, int B, int H, int W,
+                                       int64_t gray_batch_stride, int dtype, void* feat, int feat_dtype,
+                                       int feat_ctot, int feat_channel, void* small_rgb, const uint8_t* label,
+                                       uint8_t* label_plane, int64_t label_plane_stride, uint8_t* label_small,
+                                       void* stream) {
+  if (!img || !gray || B < 0 || H < 0 || W < 0) return LDIFF_EINVAL;
+  if (!feat && !small_rgb && !label_plane && !label_small) return LDIFF_EINVAL;       // use ldiff_decode_tail_gray
+  if ((label_plane || label_small) && !label) return LDIFF_EINVAL;
+  if (feat && (feat_channel < 0 || feat_channel >= feat_ctot)) return LDIFF_EINVAL;
+  if (feat && feat_dtype != dtype && feat_dtype != LDIFF_F32) return LDIFF_EUNSUPPORTED;
+  if (label_plane && label_plane_stride < (int64_t)H * W) return LDIFF_EINVAL;
+  if (B == 0 || H == 0 || W == 0) return LDIFF_OK;
+  if ((H % 16) || (W % 16)) return LDIFF_EUNSUPPORTED;  // the 16x down-sample is the 2x2 footprint only then
+  if (!aligned16(label) || !aligned16(label_plane) || (label_plane && (label_plane_stride % 16))) return LDIFF_EALIGN;
+  TailExtras ex;
+  ex.feat = feat; ex.feat_ctot = feat_ctot; ex.feat_ch = feat_channel;
+  ex.feat_f32 = (feat && feat_dtype == LDIFF_F32 && dtype != LDIFF_F32) ? 1 : 0;
+  ex.small_rgb = small_rgb; ex.label = label; ex.label_plane = label_plane;
+  ex.label_plane_stride = label_plane_stride; ex.label_small = label_small;
+  ex.W = W; ex.fh = H / 16; ex.gpr = W / 16; ex.gpr_shift = -1;
+  for (int sft = 0; sft < 31; ++sft)
+    if ((1 << sft) == ex.gpr) ex.gpr_shift = sft;
+  return decode_tail_entry(img, rgb_hwc, gray, nullptr, nullptr, nullptr, B, H, W, gray_batch_stride, dtype, &ex,
+                           stream);
 }

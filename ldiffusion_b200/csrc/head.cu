@@ -13,103 +13,11 @@
 // <= kTieGap re-evaluate the pinned softmax (exp in fp64 rounded to fp32,
 // sequential fp32 sum, fp32 division, first maximum).
 #include <cstdlib>
-#include <utility>
 
-#include "common.cuh"
+#include "head_common.cuh"
+#include "hist.cuh"
 
 namespace ldiff {
-
-struct AxisH { float scale; int in, out; };
-struct TapH { int i0, i1; float l0, l1; };
-
-__device__ __forceinline__ TapH tap(const AxisH& a, int dst) {
-  TapH t;
-  if (a.in == a.out) { t.i0 = t.i1 = dst; t.l0 = 1.f; t.l1 = 0.f; return t; }
-  float src = fmaxf(__fmaf_rn(a.scale, (float)dst + 0.5f, -0.5f), 0.f);
-  t.i0 = min((int)floorf(src), a.in - 1);
-  t.i1 = min(t.i0 + 1, a.in - 1);
-  t.l1 = fminf(fmaxf(__fsub_rn(src, (float)t.i0), 0.f), 1.f);
-  t.l0 = __fsub_rn(1.f, t.l1);
-  return t;
-}
-
-__device__ __forceinline__ float lerp2(float w0, float a, float w1, float b) {
-  return __fmaf_rn(w0, a, __fmul_rn(w1, b));
-}
-
-constexpr float kTieGap = 1e-5f;
-
-// pinned softmax + first-max argmax over v[lo..K)
-template <int KT>
-__device__ __noinline__ int softmax_argmax_exact(const float (&v)[KT], int K, int lo) {
-  float m = v[0];
-  for (int k = 1; k < K; ++k) m = fmaxf(m, v[k]);
-  float e[KT];
-  float s = 0.f;
-  for (int k = 0; k < K; ++k) {
-    e[k] = (float)exp((double)__fsub_rn(v[k], m));
-    s = __fadd_rn(s, e[k]);
-  }
-  int best = lo;
-  float pb = __fdiv_rn(e[lo], s);
-  for (int k = lo + 1; k < K; ++k) {
-    const float p = __fdiv_rn(e[k], s);
-    if (p > pb) { pb = p; best = k; }
-  }
-  return best;
-}
-
-// Cold path taken INSIDE the row loop: the K lifted logits of one pixel by value (the
-// struct travels through the ABI's parameter space, so the hot loop keeps its
-// register allocation), no memory traffic, ~1k instructions.
-template <int K>
-struct Vals { float v[K]; };
-
-template <int K>
-__device__ __noinline__ int exact_from_values(Vals<K> x) {
-  float m = x.v[0];
-#pragma unroll 1
-  for (int k = 1; k < K; ++k) m = fmaxf(m, x.v[k]);
-  float e[K];
-  float s = 0.f;
-#pragma unroll 1
-  for (int k = 0; k < K; ++k) {
-    e[k] = (float)exp((double)__fsub_rn(x.v[k], m));
-    s = __fadd_rn(s, e[k]);
-  }
-  int best = 0;
-  float pb = __fdiv_rn(e[0], s);
-#pragma unroll 1
-  for (int k = 1; k < K; ++k) {
-    const float p = __fdiv_rn(e[k], s);
-    if (p > pb) { pb = p; best = k; }
-  }
-  return best;
-}
-
-// Cold path of the generic kernel: one pixel resolved from scratch with the pinned softmax.  Kept out of
-// line and fed scalars only so that it costs the hot loops no registers.
-__device__ __noinline__ int exact_pixel(const float* __restrict__ lb, int K, int plane, int in_w,
-                                        int yi0, int yi1, float yl0, float yl1, int xi0, int xi1,
-                                        float xl0, float xl1) {
-  auto value = [&](int k) {
-    const float* r0 = lb + k * plane + yi0 * in_w;
-    const float* r1 = lb + k * plane + yi1 * in_w;
-    return lerp2(yl0, lerp2(xl0, __ldg(r0 + xi0), xl1, __ldg(r0 + xi1)), yl1,
-                 lerp2(xl0, __ldg(r1 + xi0), xl1, __ldg(r1 + xi1)));
-  };
-  float m = value(0);
-  for (int k = 1; k < K; ++k) m = fmaxf(m, value(k));
-  float s = 0.f;
-  for (int k = 0; k < K; ++k) s = __fadd_rn(s, (float)exp((double)__fsub_rn(value(k), m)));
-  float pb = -1.f;
-  int idx = 0;
-  for (int k = 0; k < K; ++k) {
-    const float pk = __fdiv_rn((float)exp((double)__fsub_rn(value(k), m)), s);
-    if (pk > pb) { pb = pk; idx = k; }
-  }
-  return idx;
-}
 
 // ----------------------------------------------------------------------------
 // logits fp32 [B,K,h,w] -> mask uint8 [B,H,W], K known at compile time.
@@ -125,8 +33,6 @@ __device__ __noinline__ int exact_pixel(const float* __restrict__ lb, int K, int
 // warp's lanes (resolving in place costs 60 registers; resolving serially in the
 // owning thread made a vertical run of 16 near-ties cost 60 us).  The kernel is issue-bound (ALU), not HBM-bound: it
 // reads 0.36 MB of logits and writes 1 byte per pixel.
-constexpr int kBand = 128;                             // longest band (output rows per source row)
-constexpr int kQueue = 128;
 
 // acc += (v >= thr) ? C : 0 as exactly FSETP + one predicated integer add
 template <int C>
@@ -354,25 +260,6 @@ lift_argmax_kernel(const float* __restrict__ logits, uint8_t* __restrict__ mask,
   lift_argmax_band<K, COLS, DIFF, 8>(logits, mask, ay, ax, blockIdx.x, blockIdx.y, blockIdx.z, s_l, s_q, s_qn);
 }
 
-// Persistent form: a FEW blocks of 512 threads x 128 registers — each one owns a whole SM's register
-// file, so the grid occupies exactly gridDim.x SMs — walk all (x-block, source row, image) bands.  Inside
-// the pass this confines the issue-bound lift+argmax to a corner of the chip for the length of the pass
-// instead of letting its register-heavy blocks take turns with the bandwidth-bound kernels on every SM.
-template <int K, bool DIFF>
-__global__ void __launch_bounds__(512, 1)
-lift_argmax_persistent_kernel(const float* __restrict__ logits, uint8_t* __restrict__ mask, AxisH ay, AxisH ax,
-                              int nxb, int B) {
-  __shared__ float2 s_l[kBand];
-  __shared__ uint32_t s_q[16][kQueue];
-  __shared__ int s_qn[16];
-  const int items = nxb * ay.in * B;
-  for (int item = blockIdx.x; item < items; item += gridDim.x) {
-    if (item != (int)blockIdx.x) __syncthreads();        // the previous band's epilogue has read s_l / s_q
-    const int bx = item % nxb, rest = item / nxb;
-    lift_argmax_band<K, 2, DIFF, 16>(logits, mask, ay, ax, bx, rest % ay.in, rest / ay.in, s_l, s_q, s_qn);
-  }
-}
-
 // any K <= 255: one thread per output pixel, nothing cached (cold path)
 __global__ void __launch_bounds__(256)
 lift_argmax_generic_kernel(const float* __restrict__ logits, uint8_t* __restrict__ mask, int K,
@@ -414,7 +301,8 @@ template <typename T, int KT>
 __global__ void __launch_bounds__(128)
 head_logits_simt_kernel(const T* __restrict__ feat, const T* __restrict__ weight,
                         const float* __restrict__ bias, float* __restrict__ logits, int Cin, int K,
-                        int hw) {
+                        int hw, unsigned long long* __restrict__ clear, int n_clear) {
+  clear_counters(clear, n_clear);
   extern __shared__ float wsm[];                      // [Cin][KT]
   for (int i = threadIdx.x; i < Cin * KT; i += blockDim.x) {
     const int c = i / KT, k = i - c * KT;
@@ -479,7 +367,8 @@ cell_classify_kernel(const T* __restrict__ feats, const T* __restrict__ weight,
                      const float* __restrict__ bias, const int32_t* __restrict__ ids,
                      uint8_t* __restrict__ lut, int lut_size, int64_t lut_stride,
                      float* __restrict__ logits_out, int n_per_image, int n_total, int Cin, int K,
-                     int* __restrict__ status) {
+                     int* __restrict__ status, unsigned long long* __restrict__ clear, int n_clear) {
+  clear_counters(clear, n_clear);
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -609,7 +498,10 @@ argmax_channels_kernel(const T* __restrict__ x, uint8_t* __restrict__ out, int K
 }
 
 int launch_head_logits_tc(const void* feat, const void* weight, const float* bias, float* logits,
-                          int B, int Cin, int K, int hw, cudaStream_t st);   // head_tc.cu
+                          int B, int Cin, int K, int hw, int64_t* clear, int n_clear, cudaStream_t st);   // head_tc.cu
+bool lift_argmax_env_ok(int K, int h, int H);                                   // lift_argmax_env.cu
+int launch_lift_argmax_env(const float* logits, uint8_t* mask, const uint8_t* gt, int64_t* C, int B, int K, int h,
+                           int w, int H, int W, int* status, const XchgPush* px, cudaStream_t st);
 
 }  // namespace ldiff
 
@@ -622,49 +514,20 @@ extern "C" int ldiff_lift_argmax(const float* logits, uint8_t* mask, int B, int 
   if (B == 0) return LDIFF_OK;
   cudaStream_t st = (cudaStream_t)stream;
   AxisH ay{(float)h / (float)H, h, H}, ax{(float)w / (float)W, w, W};
-  if (K <= 15 && H >= 4 * h && (H + h - 1) / h + 2 <= kBand && h <= 65535) {
-    // two columns per thread while T/U (4K registers) fit the 80-register budget, else one
-    // variant: 0 = 2 columns/thread, 2 CTAs/SM; 1 = 1 column, 3 CTAs/SM; 2 = 1 column, 4 CTAs/SM; 3 = 1 column, 2 CTAs/SM;
-    // 4 / 5 = variants 0 / 1 with the one-fma lerp (DIFF).  Measured at 32x lift, K=11, alone: 31.7 / 32.0 us
-    // for 0 / 1, 30.6 / 29.2 us for 4 / 5; inside the whole pass 136.3 / 137.6 / 135.0 / 135.7 us for 0 / 1 / 4 / 5.
-    static const int knob = [] { const char* e = getenv("LDIFF_ARGMAX_VARIANT"); return e ? atoi(e) : -1; }();
-    int variant = knob >= 0 ? knob : 4;
-    if (K > 12 || (W % 2) != 0) variant = variant == 0 ? 1 : (variant == 4 ? 5 : variant);
-    const int cols = (variant == 0 || variant == 4) ? 2 : 1;
-    dim3 grid((W / cols + 255) / 256, h, B);
-    // experiment knob: unused dynamic shared memory that caps how many of these register-heavy CTAs
-    // are resident per SM, leaving register file for the bandwidth-bound kernels they run beside
-    static const int pad = [] { const char* e = getenv("LDIFF_ARGMAX_SMEM_PAD"); return e ? atoi(e) : 0; }();
-    // persistent form (ldiff_tune / LDIFF_ARGMAX_PERSIST blocks): needs two columns per thread and the DIFF lerp
-    const int persist = tune_get(LDIFF_TUNE_ARGMAX_PERSIST_BLOCKS);
-    if (persist > 0 && K >= 2 && K <= 12 && (W % 2) == 0) {
-      const int nxb = (W / 2 + 511) / 512;
-      const int items = nxb * h * B;
-      const int nblk = persist < items ? persist : items;
-      switch (K) {
-#define LAP(KK) case KK: lift_argmax_persistent_kernel<KK, true><<<nblk, 512, 0, st>>>(logits, mask, ay, ax, nxb, B); break;
-        LAP(2) LAP(3) LAP(4) LAP(5) LAP(6) LAP(7) LAP(8) LAP(9) LAP(10) LAP(11) LAP(12)
-#undef LAP
-      }
-      return check_launch();
-    }
+  // variant: 0 (default) = envelope kernel; 4 / 5 = the per-pixel evaluation kernel of round 1 with 2 / 1
+  // columns per thread (kept for A/B timing: tools/kbench_argmax.py)
+  const int variant = tune_get(LDIFF_TUNE_ARGMAX_VARIANT);
+  if (variant == 0 && H >= 4 * h && lift_argmax_env_ok(K, h, H))
+    return launch_lift_argmax_env(logits, mask, nullptr, nullptr, B, K, h, w, H, W, nullptr, nullptr, st);
+  if (K <= 15 && H >= 4 * h && max_band_rows(h, H) <= kBand && h <= 65535) {
+    const bool two = variant != 5 && K <= 12 && (W % 2) == 0;
+    dim3 grid((W / (two ? 2 : 1) + 255) / 256, h, B);
     switch (K) {
 #define LA2(KK) case KK:                                                                               \
-      if (variant == 0) {                                                                              \
-        if (pad > 48 * 1024)                                                                           \
-          cudaFuncSetAttribute(lift_argmax_kernel<KK, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad); \
-        lift_argmax_kernel<KK, 2, 2><<<grid, 256, pad, st>>>(logits, mask, ay, ax);                    \
-      }                                                                                                \
-      else if (variant == 4) lift_argmax_kernel<KK, 2, 2, true><<<grid, 256, 0, st>>>(logits, mask, ay, ax); \
-      else if (variant == 5) lift_argmax_kernel<KK, 1, 3, true><<<grid, 256, 0, st>>>(logits, mask, ay, ax); \
-      else if (variant == 1) lift_argmax_kernel<KK, 1, 3><<<grid, 256, 0, st>>>(logits, mask, ay, ax);  \
-      else if (variant == 3) lift_argmax_kernel<KK, 1, 2><<<grid, 256, 0, st>>>(logits, mask, ay, ax);  \
-      else lift_argmax_kernel<KK, 1, 4><<<grid, 256, 0, st>>>(logits, mask, ay, ax);                    \
+      if (two) lift_argmax_kernel<KK, 2, 2, true><<<grid, 256, 0, st>>>(logits, mask, ay, ax);         \
+      else lift_argmax_kernel<KK, 1, 3, true><<<grid, 256, 0, st>>>(logits, mask, ay, ax);             \
       break;
-#define LA1(KK) case KK:                                                                               \
-      if (variant == 5) lift_argmax_kernel<KK, 1, 3, true><<<grid, 256, 0, st>>>(logits, mask, ay, ax); \
-      else lift_argmax_kernel<KK, 1, 3><<<grid, 256, 0, st>>>(logits, mask, ay, ax);                    \
-      break;
+#define LA1(KK) case KK: lift_argmax_kernel<KK, 1, 3, true><<<grid, 256, 0, st>>>(logits, mask, ay, ax); break;
       LA2(1) LA2(2) LA2(3) LA2(4) LA2(5) LA2(6) LA2(7) LA2(8) LA2(9) LA2(10) LA2(11) LA2(12)
       LA1(13) LA1(14) LA1(15)
 #undef LA2
@@ -677,21 +540,39 @@ extern "C" int ldiff_lift_argmax(const float* logits, uint8_t* mask, int B, int 
   return check_launch();
 }
 
+extern "C" int ldiff_lift_argmax_hist(const float* logits, uint8_t* mask, const uint8_t* gt, int64_t* C, int B,
+                                      int K, int h, int w, int H, int W, void* xchg, int channel, int* status,
+                                      void* stream) {
+  if (!logits || !mask || !gt || !C || !status || B < 0 || K < 1 || h < 1 || w < 1 || H < 1 || W < 1)
+    return LDIFF_EINVAL;
+  if (!(H >= 4 * h && lift_argmax_env_ok(K, h, H))) return LDIFF_EUNSUPPORTED;   // ldiff_lift_argmax + ldiff_confusion_hist
+  XchgPush px{};
+  if (xchg) {
+    const int rc = xchg_push_args(xchg, channel, (K + 1) * K, &px);
+    if (rc != LDIFF_OK) return rc;
+  }
+  if (B == 0) return xchg ? LDIFF_EINVAL : LDIFF_OK;       // a push needs a launch
+  return launch_lift_argmax_env(logits, mask, gt, C, B, K, h, w, H, W, status, xchg ? &px : nullptr,
+                                (cudaStream_t)stream);
+}
+
 extern "C" int ldiff_head_logits(const void* feat, const void* weight, const float* bias,
                                  float* logits, int B, int Cin, int K, int hw, int dtype,
-                                 void* stream) {
-  if (!feat || !weight || !logits || B < 0 || Cin < 1 || K < 1 || hw < 1) return LDIFF_EINVAL;
+                                 int64_t* clear_i64, int n_clear, void* stream) {
+  if (!feat || !weight || !logits || B < 0 || Cin < 1 || K < 1 || hw < 1 || n_clear < 0 || (n_clear && !clear_i64))
+    return LDIFF_EINVAL;
   if (K > 32) return LDIFF_EUNSUPPORTED;
-  if (B == 0) return LDIFF_OK;
+  if (B == 0) return n_clear ? LDIFF_EINVAL : LDIFF_OK;    // a clear needs a launch
   cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long* clear = reinterpret_cast<unsigned long long*>(clear_i64);
   if (dtype == LDIFF_BF16) {
-    const int rc = launch_head_logits_tc(feat, weight, bias, logits, B, Cin, K, hw, st);
+    const int rc = launch_head_logits_tc(feat, weight, bias, logits, B, Cin, K, hw, clear_i64, n_clear, st);
     if (rc != LDIFF_EUNSUPPORTED) return rc;          // shapes the tensor-core tile cannot take
   }
   dim3 grid((hw + 127) / 128, B);
 #define HL(T, KT)                                                                              \
   head_logits_simt_kernel<T, KT><<<grid, 128, (size_t)Cin * KT * sizeof(float), st>>>(         \
-      (const T*)feat, (const T*)weight, bias, logits, Cin, K, hw)
+      (const T*)feat, (const T*)weight, bias, logits, Cin, K, hw, clear, n_clear)
   if ((size_t)Cin * 32 * sizeof(float) > 48 * 1024) return LDIFF_EUNSUPPORTED;
   if (dtype == LDIFF_F32) { if (K <= 16) HL(float, 16); else HL(float, 32); }
   else if (dtype == LDIFF_BF16) { if (K <= 16) HL(__nv_bfloat16, 16); else HL(__nv_bfloat16, 32); }
@@ -703,12 +584,14 @@ extern "C" int ldiff_head_logits(const void* feat, const void* weight, const flo
 extern "C" int ldiff_cell_classify(const void* inst_feats, const void* weight, const float* bias,
                                    const int32_t* inst_ids, uint8_t* lut, int lut_size,
                                    int64_t lut_stride, float* logits_out, int n_per_image, int B,
-                                   int Cin, int K, int dtype, int* status, void* stream) {
+                                   int Cin, int K, int dtype, int64_t* clear_i64, int n_clear, int* status,
+                                   void* stream) {
   if (!inst_feats || !weight || !inst_ids || !lut || !status || n_per_image < 0 || B < 0 || Cin < 1 ||
-      K < 1 || lut_size < 1)
+      K < 1 || lut_size < 1 || n_clear < 0 || (n_clear && !clear_i64))
     return LDIFF_EINVAL;
   if (K > 32 || (Cin % 8) != 0) return LDIFF_EUNSUPPORTED;
-  if (n_per_image == 0 || B == 0) return LDIFF_OK;
+  if (n_per_image == 0 || B == 0) return n_clear ? LDIFF_EINVAL : LDIFF_OK;   // a clear needs a launch
+  unsigned long long* clear = reinterpret_cast<unsigned long long*>(clear_i64);
   if (!aligned16(inst_feats) || !aligned16(weight)) return LDIFF_EALIGN;
   cudaStream_t st = (cudaStream_t)stream;
   const int n_total = n_per_image * B;
@@ -718,7 +601,7 @@ extern "C" int ldiff_cell_classify(const void* inst_feats, const void* weight, c
 #define CC(T, KT)                                                                                   \
   cell_classify_kernel<T, KT><<<grid, 128, 0, st>>>((const T*)inst_feats, (const T*)weight, bias,   \
                                                     inst_ids, lut, lut_size, lut_stride, logits_out, \
-                                                    n_per_image, n_total, Cin, K, status)
+                                                    n_per_image, n_total, Cin, K, status, clear, n_clear)
   if (dtype == LDIFF_F32) { if (K <= 16) CC(float, 16); else CC(float, 32); }
   else if (dtype == LDIFF_BF16) { if (K <= 16) CC(__nv_bfloat16, 16); else CC(__nv_bfloat16, 32); }
   else return LDIFF_EUNSUPPORTED;

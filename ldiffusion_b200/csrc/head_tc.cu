@@ -79,8 +79,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // grid = (hw / 128, B); dynamic smem = 1024 (alignment slack) + nkb * (16 KB + 2 KB)
 __global__ void __launch_bounds__(kThreads, 1)
 head_logits_tc_kernel(const __nv_bfloat16* __restrict__ feat, const __nv_bfloat16* __restrict__ weight,
-                      const float* __restrict__ bias, float* __restrict__ logits, int Cin, int K, int hw) {
+                      const float* __restrict__ bias, float* __restrict__ logits, int Cin, int K, int hw,
+                      unsigned long long* __restrict__ clear, int n_clear) {
   extern __shared__ uint8_t smem_raw[];
+  clear_counters(clear, n_clear);
   __shared__ __align__(8) uint64_t mma_bar;
   __shared__ uint32_t tmem_base_slot;
 
@@ -185,21 +187,23 @@ head_logits_tc_kernel(const __nv_bfloat16* __restrict__ feat, const __nv_bfloat1
 }  // namespace tc
 
 int launch_head_logits_tc(const void* feat, const void* weight, const float* bias, float* logits,
-                          int B, int Cin, int K, int hw, cudaStream_t st) {
+                          int B, int Cin, int K, int hw, int64_t* clear, int n_clear, cudaStream_t st) {
   using namespace tc;
   if (K > kTileN || (hw % kTileM) != 0 || (Cin % kBlockK) != 0 || B > 65535) return LDIFF_EUNSUPPORTED;
   if (!aligned16(weight) || (reinterpret_cast<uintptr_t>(feat) & 1)) return LDIFF_EUNSUPPORTED;
   const int nkb = Cin / kBlockK;
   const size_t smem = 1024 + (size_t)nkb * (kTileM + kTileN) * 128;
   if (smem > 200 * 1024) return LDIFF_EUNSUPPORTED;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDevices] = {};              // the attribute belongs to the CURRENT device
+  const int dev = current_device();
+  if (dev < 0 || dev >= kMaxDevices || !attr_set[dev]) {
     cudaFuncSetAttribute(head_logits_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_set = true;
+    if (dev >= 0 && dev < kMaxDevices) attr_set[dev] = true;
   }
   dim3 grid(hw / kTileM, B);
   head_logits_tc_kernel<<<grid, kThreads, smem, st>>>((const __nv_bfloat16*)feat,
-                                                       (const __nv_bfloat16*)weight, bias, logits, Cin, K, hw);
+                                                       (const __nv_bfloat16*)weight, bias, logits, Cin, K, hw,
+                                                       reinterpret_cast<unsigned long long*>(clear), n_clear);
   return check_launch();
 }
 

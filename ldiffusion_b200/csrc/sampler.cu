@@ -77,6 +77,40 @@ __device__ __forceinline__ float laplace_from_uniform(float u, float b) {
 
 enum { SRC_PHILOX = 0, SRC_UNIFORM = 1, SRC_NOISE = 2 };
 
+// noise of the 8 elements [base, base + 8) / of element t (shared by the stand-alone kernel and the
+// fused step+noise kernel, so both produce the same bits)
+template <typename T, int SRC>
+__device__ __forceinline__ void laplace_noise8(const T* __restrict__ inj, int64_t base, float b, uint2 key,
+                                               uint64_t offset, float (&nz)[8]) {
+  if (SRC == SRC_PHILOX) {
+    const uint64_t c0 = offset + (uint64_t)(base >> 2);
+    const uint4 r0 = philox4x32_10(make_uint4((uint32_t)c0, (uint32_t)(c0 >> 32), 0u, 0u), key);
+    const uint64_t c1 = c0 + 1;
+    const uint4 r1 = philox4x32_10(make_uint4((uint32_t)c1, (uint32_t)(c1 >> 32), 0u, 0u), key);
+    const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) nz[i] = laplace_from_uniform_fast<FastLaplace<T>::kSeries>(uniform_pm1(w[i]), b);
+  } else {
+    Vec8<T>::load(inj + base, nz);
+    if (SRC == SRC_UNIFORM) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) nz[i] = laplace_from_uniform(nz[i], b);
+    }
+  }
+}
+template <typename T, int SRC>
+__device__ __forceinline__ float laplace_noise1(const T* __restrict__ inj, int64_t t, float b, uint2 key,
+                                                uint64_t offset) {
+  if (SRC == SRC_PHILOX) {
+    const uint64_t c = offset + (uint64_t)(t >> 2);
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0u, 0u), key);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+    return laplace_from_uniform_fast<FastLaplace<T>::kSeries>(uniform_pm1(w[t & 3]), b);
+  }
+  const float nzs = to_f32(inj[t]);
+  return SRC == SRC_UNIFORM ? laplace_from_uniform(nzs, b) : nzs;
+}
+
 template <typename T, int SRC, bool EMIT>
 __global__ void __launch_bounds__(256)
 laplace_qsample_kernel(const T* __restrict__ x, T* __restrict__ out, const T* __restrict__ inj,
@@ -87,21 +121,7 @@ laplace_qsample_kernel(const T* __restrict__ x, T* __restrict__ out, const T* __
     const int64_t base = v << 3;
     float xv[8], nz[8];
     Vec8<T>::load(x + base, xv);
-    if (SRC == SRC_PHILOX) {
-      const uint64_t c0 = offset + (uint64_t)(base >> 2);
-      const uint4 r0 = philox4x32_10(make_uint4((uint32_t)c0, (uint32_t)(c0 >> 32), 0u, 0u), key);
-      const uint64_t c1 = c0 + 1;
-      const uint4 r1 = philox4x32_10(make_uint4((uint32_t)c1, (uint32_t)(c1 >> 32), 0u, 0u), key);
-      const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-      for (int i = 0; i < 8; ++i) nz[i] = laplace_from_uniform_fast<FastLaplace<T>::kSeries>(uniform_pm1(w[i]), b);
-    } else {
-      Vec8<T>::load(inj + base, nz);
-      if (SRC == SRC_UNIFORM) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) nz[i] = laplace_from_uniform(nz[i], b);
-      }
-    }
+    laplace_noise8<T, SRC>(inj, base, b, key, offset, nz);
     if (EMIT) Vec8<T>::store(noise_out + base, nz);
 #pragma unroll
     for (int i = 0; i < 8; ++i) xv[i] = __fadd_rn(xv[i], nz[i]);
@@ -110,16 +130,7 @@ laplace_qsample_kernel(const T* __restrict__ x, T* __restrict__ out, const T* __
   // scalar tail (n % 8 elements), one thread each
   const int64_t t = (nvec << 3) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t < n) {
-    float nzs;
-    if (SRC == SRC_PHILOX) {
-      const uint64_t c = offset + (uint64_t)(t >> 2);
-      const uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0u, 0u), key);
-      const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-      nzs = laplace_from_uniform_fast<FastLaplace<T>::kSeries>(uniform_pm1(w[t & 3]), b);
-    } else {
-      nzs = to_f32(inj[t]);
-      if (SRC == SRC_UNIFORM) nzs = laplace_from_uniform(nzs, b);
-    }
+    const float nzs = laplace_noise1<T, SRC>(inj, t, b, key, offset);
     if (EMIT) noise_out[t] = from_f32<T>(nzs);
     out[t] = from_f32<T>(__fadd_rn(to_f32(x[t]), nzs));
   }
@@ -214,6 +225,84 @@ static int launch_plms(const void* x, const void* e0, const void* e1, const void
     default: PS(4); break;
   }
 #undef PS
+  return check_launch();
+}
+
+
+// ---------------------------------------------------------------------------
+// a-2 + a-1 in ONE launch ("step_then_noise"): the reference runs the reverse update
+// (segmentor.py:100-104) and the Laplace forward noising (ldiffusion.py:233-237) on latent-sized
+// tensors inside the same loop iteration; both are elementwise over the same index space, and at the
+// config shape (2 MiB) each stand-alone launch is pure latency.  Per 8 elements:
+//   prev  = sc * x - (dA * eh) / denom            (exactly plms_step_kernel's chain)
+//   noisy = clean + Laplace(0, b)                  (exactly laplace_qsample_kernel's chain)
+// Same helper functions as the two kernels above, so every output bit is the same.
+// ---------------------------------------------------------------------------
+template <typename T, int MODE, int SRC>
+__global__ void __launch_bounds__(256)
+plms_step_noise_kernel(const T* __restrict__ x, const T* __restrict__ e0, const T* __restrict__ e1,
+                       const T* __restrict__ e2, const T* __restrict__ e3, float sc, float dA, float denom,
+                       T* __restrict__ prev, const T* __restrict__ clean, const T* __restrict__ inj,
+                       T* __restrict__ noisy, float b, uint2 key, uint64_t offset, int64_t n) {
+  const int64_t nvec = n >> 3;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+    const int64_t base = v << 3;
+    float xv[8], a[8], bb[8], c[8], d[8], cl[8], nz[8];
+    Vec8<T>::load(x + base, xv);
+    Vec8<T>::load(e0 + base, a);
+    if (MODE >= 1) Vec8<T>::load(e1 + base, bb);
+    if (MODE >= 3) Vec8<T>::load(e2 + base, c);
+    if (MODE >= 4) Vec8<T>::load(e3 + base, d);
+    Vec8<T>::load(clean + base, cl);
+    laplace_noise8<T, SRC>(inj, base, b, key, offset, nz);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float eh = plms_eps<MODE>(a[i], MODE >= 1 ? bb[i] : 0.f, MODE >= 3 ? c[i] : 0.f,
+                                      MODE >= 4 ? d[i] : 0.f);
+      xv[i] = __fsub_rn(__fmul_rn(sc, xv[i]), __fdiv_rn(__fmul_rn(dA, eh), denom));
+      cl[i] = __fadd_rn(cl[i], nz[i]);
+    }
+    Vec8<T>::store(prev + base, xv);
+    Vec8<T>::store(noisy + base, cl);
+  }
+  const int64_t t = (nvec << 3) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) {
+    const float eh = plms_eps<MODE>(to_f32(e0[t]), MODE >= 1 ? to_f32(e1[t]) : 0.f,
+                                    MODE >= 3 ? to_f32(e2[t]) : 0.f, MODE >= 4 ? to_f32(e3[t]) : 0.f);
+    prev[t] = from_f32<T>(__fsub_rn(__fmul_rn(sc, to_f32(x[t])), __fdiv_rn(__fmul_rn(dA, eh), denom)));
+    noisy[t] = from_f32<T>(__fadd_rn(to_f32(clean[t]), laplace_noise1<T, SRC>(inj, t, b, key, offset)));
+  }
+}
+
+template <typename T>
+static int launch_plms_noise(const void* x, const void* e0, const void* e1, const void* e2, const void* e3,
+                             int mode, float sc, float dA, float denom, void* prev, const void* clean,
+                             const void* noise_in, const void* u_in, void* noisy, float b, uint64_t seed,
+                             uint64_t offset, int64_t n, cudaStream_t st) {
+  const int threads = 256;
+  const int64_t items = (n >> 3) > (n & 7) ? (n >> 3) : (n & 7);
+  const int grid = grid_for(items, threads, 8);
+  const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+#define PSN(M, SRC, INJ)                                                                               \
+  plms_step_noise_kernel<T, M, SRC><<<grid, threads, 0, st>>>(                                         \
+      (const T*)x, (const T*)e0, (const T*)e1, (const T*)e2, (const T*)e3, sc, dA, denom, (T*)prev,    \
+      (const T*)clean, (const T*)(INJ), (T*)noisy, b, key, offset, n)
+#define PSM(M)                                          \
+  do {                                                  \
+    if (noise_in) PSN(M, SRC_NOISE, noise_in);          \
+    else if (u_in) PSN(M, SRC_UNIFORM, u_in);           \
+    else PSN(M, SRC_PHILOX, nullptr);                   \
+  } while (0)
+  switch (mode) {
+    case 0: PSM(0); break;
+    case 1: PSM(1); break;
+    case 2: PSM(2); break;
+    case 3: PSM(3); break;
+    default: PSM(4); break;
+  }
+#undef PSM
+#undef PSN
   return check_launch();
 }
 
@@ -418,6 +507,28 @@ extern "C" int ldiff_plms_step(const void* sample, const void* e0, const void* e
   if (dtype == LDIFF_BF16)
     return launch_plms<__nv_bfloat16>(sample, e0, e1, e2, e3, mode, sample_coeff, alpha_diff, denom,
                                       prev_sample, n, st);
+  return LDIFF_EUNSUPPORTED;
+}
+
+extern "C" int ldiff_plms_step_noise(const void* sample, const void* e0, const void* e1, const void* e2,
+                                     const void* e3, int mode, float sample_coeff, float alpha_diff,
+                                     float denom, void* prev_sample, const void* clean, void* noisy,
+                                     const void* noise_in, const void* u_in, float b, uint64_t seed,
+                                     uint64_t offset, int64_t n, int dtype, void* stream) {
+  if (!sample || !e0 || !prev_sample || !clean || !noisy || n < 0 || mode < 0 || mode > 4 || (noise_in && u_in))
+    return LDIFF_EINVAL;
+  if ((mode >= 1 && !e1) || (mode >= 3 && !e2) || (mode >= 4 && !e3)) return LDIFF_EINVAL;
+  if (n == 0) return LDIFF_OK;
+  if (!aligned16(sample) || !aligned16(e0) || !aligned16(e1) || !aligned16(e2) || !aligned16(e3) ||
+      !aligned16(prev_sample) || !aligned16(clean) || !aligned16(noisy) || !aligned16(noise_in) || !aligned16(u_in))
+    return LDIFF_EALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == LDIFF_F32)
+    return launch_plms_noise<float>(sample, e0, e1, e2, e3, mode, sample_coeff, alpha_diff, denom, prev_sample,
+                                    clean, noise_in, u_in, noisy, b, seed, offset, n, st);
+  if (dtype == LDIFF_BF16)
+    return launch_plms_noise<__nv_bfloat16>(sample, e0, e1, e2, e3, mode, sample_coeff, alpha_diff, denom,
+                                            prev_sample, clean, noise_in, u_in, noisy, b, seed, offset, n, st);
   return LDIFF_EUNSUPPORTED;
 }
 

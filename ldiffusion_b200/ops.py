@@ -126,12 +126,34 @@ def _plms_step(sample: Tensor, eps: Sequence[Tensor], mode: int, sample_coeff: f
                                       _stream(sample)))
 
 
+def _plms_step_noise(sample: Tensor, eps: Sequence[Tensor], mode: int, sample_coeff: float, alpha_diff: float,
+                     denom: float, out: Tensor, clean: Tensor, noisy: Tensor, noise: Optional[Tensor],
+                     u: Optional[Tensor], b: float, seed: int, offset: int) -> None:
+    _cuda(sample, out, clean, noisy, noise, u, *eps)
+    e = [_ptr(t) for t in eps] + [None] * (4 - len(eps))
+    check(_cabi.lib().ldiff_plms_step_noise(_ptr(sample), e[0], e[1], e[2], e[3], mode, sample_coeff, alpha_diff,
+                                            denom, _ptr(out), _ptr(clean), _ptr(noisy), _ptr(noise), _ptr(u), b,
+                                            seed, offset, sample.numel(), _dt(sample), _stream(sample)))
+
+
 def _decode_tail_gray(img: Tensor, rgb: Optional[Tensor], gray: Optional[Tensor]) -> None:
     _cuda(img, rgb, gray)
     B, _, H, W = img.shape
     gstride = gray.stride(0) if gray is not None else 0
     check(_cabi.lib().ldiff_decode_tail_gray(_ptr(img), _ptr(rgb), _ptr(gray), B, H, W, gstride,
                                              _dt(img), _stream(img)))
+
+
+def _decode_tail_fused(img: Tensor, rgb: Optional[Tensor], gray: Tensor, feat: Optional[Tensor], feat_channel: int,
+                       small_rgb: Optional[Tensor], label: Optional[Tensor], label_plane: Optional[Tensor],
+                       label_small: Optional[Tensor]) -> None:
+    _cuda(img, rgb, gray, feat, small_rgb, label, label_plane, label_small)
+    B, _, H, W = img.shape
+    check(_cabi.lib().ldiff_decode_tail_fused(
+        _ptr(img), _ptr(rgb), _ptr(gray), B, H, W, gray.stride(0), _dt(img), _ptr(feat),
+        _dt(feat) if feat is not None else _dt(img), feat.shape[1] if feat is not None else 1, feat_channel,
+        _ptr(small_rgb), _ptr(label), _ptr(label_plane), label_plane.stride(0) if label_plane is not None else 0,
+        _ptr(label_small), _stream(img)))
 
 
 def _decode_tail_model_input(img: Tensor, rgb: Optional[Tensor], gray: Optional[Tensor], model_input: Tensor,
@@ -176,12 +198,15 @@ def _bilinear_lift_backward(grad_out: Tensor, dst_channel: int, grad_src: Tensor
                                                    _stream(grad_out)))
 
 
-def _head_logits(feat: Tensor, weight: Tensor, bias: Optional[Tensor], logits: Tensor) -> None:
-    _cuda(feat, weight, bias, logits)
+def _head_logits(feat: Tensor, weight: Tensor, bias: Optional[Tensor], logits: Tensor,
+                 clear: Optional[Tensor] = None) -> None:
+    """``clear`` (optional int64 tensor): zeroed by the kernel as a side job (see ldiff.h)."""
+    _cuda(feat, weight, bias, logits, clear)
     B, Cin = feat.shape[:2]
     hw = feat[0, 0].numel()
     check(_cabi.lib().ldiff_head_logits(_ptr(feat), _ptr(weight), _ptr(bias), _ptr(logits), B, Cin,
-                                        weight.shape[0], hw, _dt(feat), _stream(feat)))
+                                        weight.shape[0], hw, _dt(feat), _ptr(clear),
+                                        0 if clear is None else clear.numel(), _stream(feat)))
 
 
 def _lift_argmax(logits: Tensor, mask: Tensor) -> None:
@@ -191,16 +216,37 @@ def _lift_argmax(logits: Tensor, mask: Tensor) -> None:
     check(_cabi.lib().ldiff_lift_argmax(_ptr(logits), _ptr(mask), B, K, h, w, H, W, _stream(logits)))
 
 
+def _lift_argmax_hist(logits: Tensor, mask: Tensor, gt: Tensor, C: Tensor, status: Tensor, xchg=None,
+                      channel: int = 0) -> None:
+    """``xchg``: the C handle of a ``dist.ConfusionExchange`` (peer push as the kernel's tail) or None."""
+    _cuda(logits, mask, gt, C, status)
+    B, K, h, w = logits.shape
+    _, H, W = mask.shape
+    check(_cabi.lib().ldiff_lift_argmax_hist(_ptr(logits), _ptr(mask), _ptr(gt), _ptr(C), B, K, h, w, H, W, xchg,
+                                             channel, _ptr(status), _stream(logits)))
+
+
+def _lut_paint_hist(inst: Tensor, lut: Tensor, mask: Tensor, gt: Tensor, C: Tensor, K: int, status: Tensor,
+                    xchg=None, channel: int = 0) -> None:
+    _cuda(inst, lut, mask, gt, C, status)
+    B = inst.shape[0]
+    n = inst[0].numel()
+    lut_stride = lut.stride(0) if lut.dim() == 2 else 0
+    check(_cabi.lib().ldiff_lut_paint_hist(_ptr(inst), _ptr(lut), _ptr(mask), _ptr(gt), _ptr(C), n, B, lut.shape[-1],
+                                           lut_stride, K, xchg, channel, _ptr(status), _stream(inst)))
+
+
 def _cell_classify(feats: Tensor, weight: Tensor, bias: Optional[Tensor], inst_ids: Tensor,
-                   lut: Tensor, logits_out: Optional[Tensor], status: Tensor) -> None:
-    """feats [B,N,Cin] (or [N,Cin]); lut [B,lut_size] (or [lut_size])."""
-    _cuda(feats, weight, bias, inst_ids, lut, logits_out, status)
+                   lut: Tensor, logits_out: Optional[Tensor], status: Tensor, clear: Optional[Tensor] = None) -> None:
+    """feats [B,N,Cin] (or [N,Cin]); lut [B,lut_size] (or [lut_size]); ``clear``: see ``_head_logits``."""
+    _cuda(feats, weight, bias, inst_ids, lut, logits_out, status, clear)
     B = feats.shape[0] if feats.dim() == 3 else 1
     N, Cin = feats.shape[-2], feats.shape[-1]
     lut_stride = lut.stride(0) if lut.dim() == 2 else 0
     check(_cabi.lib().ldiff_cell_classify(_ptr(feats), _ptr(weight), _ptr(bias), _ptr(inst_ids),
                                           _ptr(lut), lut.shape[-1], lut_stride, _ptr(logits_out), N, B, Cin,
-                                          weight.shape[0], _dt(feats), _ptr(status), _stream(feats)))
+                                          weight.shape[0], _dt(feats), _ptr(clear),
+                                          0 if clear is None else clear.numel(), _ptr(status), _stream(feats)))
 
 
 def _copy_planes_u8(src: Tensor, dst: Tensor) -> None:
@@ -305,17 +351,20 @@ torch.library.custom_op("ldiff::sw_tta_merge", mutates_args=("out",))(_sw_tta_me
 torch.library.custom_op("ldiff::sw_finalize_argmax", mutates_args=("seg", "logits_out", "status"))(_sw_finalize_argmax)
 torch.library.custom_op("ldiff::laplace_qsample", mutates_args=("out", "noise_out"))(_laplace_qsample)
 torch.library.custom_op("ldiff::plms_step", mutates_args=("out",))(_plms_step)
+torch.library.custom_op("ldiff::plms_step_noise", mutates_args=("out", "noisy"))(_plms_step_noise)
 torch.library.custom_op("ldiff::laplace_qsample_map", mutates_args=("out", "noise_out"))(_laplace_qsample_map)
 torch.library.custom_op("ldiff::scaled_residual", mutates_args=("out",))(_scaled_residual)
 torch.library.custom_op("ldiff::decode_tail_gray", mutates_args=("rgb", "gray"))(_decode_tail_gray)
+torch.library.custom_op("ldiff::decode_tail_fused", mutates_args=("rgb", "gray", "feat", "small_rgb", "label_plane", "label_small"))(_decode_tail_fused)
 torch.library.custom_op("ldiff::decode_tail_model_input",
                         mutates_args=("rgb", "gray", "model_input"))(_decode_tail_model_input)
 torch.library.custom_op("ldiff::bilinear_lift", mutates_args=("dst",))(_bilinear_lift)
 torch.library.custom_op("ldiff::bilinear_lift_multi", mutates_args=("dst",))(_bilinear_lift_multi)
 torch.library.custom_op("ldiff::bilinear_lift_backward", mutates_args=("grad_src",))(_bilinear_lift_backward)
-torch.library.custom_op("ldiff::head_logits", mutates_args=("logits",))(_head_logits)
+torch.library.custom_op("ldiff::head_logits", mutates_args=("logits", "clear"))(_head_logits)
 torch.library.custom_op("ldiff::lift_argmax", mutates_args=("mask",))(_lift_argmax)
-torch.library.custom_op("ldiff::cell_classify", mutates_args=("lut", "logits_out", "status"))(_cell_classify)
+# (the *_hist entry points take an opaque exchange handle and are not dispatcher ops; use ops.lift_argmax_hist / ops.lut_paint_hist)
+torch.library.custom_op("ldiff::cell_classify", mutates_args=("lut", "logits_out", "status", "clear"))(_cell_classify)
 torch.library.custom_op("ldiff::copy_planes_u8", mutates_args=("dst",))(_copy_planes_u8)
 torch.library.custom_op("ldiff::lut_paint", mutates_args=("mask", "status"))(_lut_paint)
 torch.library.custom_op("ldiff::argmax_channels", mutates_args=("out",))(_argmax_channels)
@@ -414,6 +463,29 @@ def plms_step(sample: Tensor, eps: Sequence[Tensor], mode: int, sample_coeff: fl
     return out
 
 
+def plms_step_noise(sample: Tensor, eps: Sequence[Tensor], mode: int, sample_coeff: float, alpha_diff: float,
+                    denom: float, clean: Tensor, b: float, *, noise: Optional[Tensor] = None,
+                    u: Optional[Tensor] = None, seed: int = 0, offset: int = 0, out: Optional[Tensor] = None,
+                    noisy_out: Optional[Tensor] = None):
+    """``plms_step`` on (sample, eps) and ``laplace_qsample`` on ``clean`` in ONE launch; returns
+    (prev_sample, noisy).  Bit-identical to the two separate operators."""
+    need = {0: 1, 1: 2, 2: 2, 3: 3, 4: 4}[mode]
+    if len(eps) < need:
+        raise ValueError(f"mode {mode} needs {need} model outputs")
+    eps = list(eps[:need])
+    _dense(sample, "sample")
+    for e in eps + [clean] + [t for t in (noise, u) if t is not None]:
+        if e.shape != sample.shape or e.dtype != sample.dtype or not e.is_contiguous():
+            raise ValueError("all tensors must match the sample in shape, dtype and be contiguous")
+    if noise is not None and u is not None:
+        raise ValueError("pass at most one of noise / u")
+    out = torch.empty_like(sample) if out is None else out
+    noisy_out = torch.empty_like(sample) if noisy_out is None else noisy_out
+    _plms_step_noise(sample, eps, mode, float(sample_coeff), float(alpha_diff), float(denom), out, clean, noisy_out,
+                     noise, u, float(b), int(seed), int(offset))
+    return out, noisy_out
+
+
 IMAGENET_MEAN = (0.485, 0.456, 0.406)
 IMAGENET_STD = (0.229, 0.224, 0.225)
 
@@ -461,6 +533,49 @@ def decode_tail_gray(img: Tensor, *, want_rgb: bool = True, gray_out: Optional[T
         raise ValueError("nothing to compute")
     _decode_tail_gray(img, rgb, gray)
     return rgb, gray
+
+
+def decode_tail_fused(img: Tensor, gray_out: Tensor, *, rgb_out: Optional[Tensor] = None,
+                      feat_out: Optional[Tensor] = None, feat_channel: int = 0, small_rgb_out: Optional[Tensor] = None,
+                      label: Optional[Tensor] = None, label_plane_out: Optional[Tensor] = None,
+                      label_small_out: Optional[Tensor] = None) -> None:
+    """``decode_tail_gray`` with the per-step consumers of the decoder output fused into the same pass:
+    channel ``feat_channel`` of ``feat_out`` [B,n,H/16,W/16] = weighted gray of the 16x bilinear
+    down-sample (ldiffusion.py:240-247), ``small_rgb_out`` [B,3,H/16,W/16] = that down-sample itself,
+    ``label_plane_out`` = ``label`` copied into a [B,H,W] slot of the pixel vectors,
+    ``label_small_out`` [B,1,H/16,W/16] = the label's bilinear down-sample truncated to uint8
+    (ldiffusion.py:224-226).  H and W must be multiples of 16 (otherwise use the separate operators)."""
+    if img.dim() != 4 or img.shape[1] != 3:
+        raise ValueError("img must be [B,3,H,W]")
+    _dense(img, "img")
+    B, _, H, W = img.shape
+    if H % 16 or W % 16:
+        raise ValueError("decode_tail_fused needs H and W to be multiples of 16")
+    fh, fw = H // 16, W // 16
+    if gray_out.shape != (B, H, W) or gray_out.dtype != torch.uint8 or gray_out.stride()[1:] != (W, 1):
+        raise ValueError("gray_out must be uint8 [B,H,W] with dense planes")
+    if feat_out is not None:
+        _dense(feat_out, "feat_out")
+        if feat_out.dim() != 4 or feat_out.shape[0] != B or feat_out.shape[2:] != (fh, fw) \
+                or feat_out.dtype not in (img.dtype, torch.float32) or not 0 <= feat_channel < feat_out.shape[1]:
+            raise ValueError("feat_out must be [B,n,H/16,W/16] in the image dtype or fp32")
+    if small_rgb_out is not None:
+        _dense(small_rgb_out, "small_rgb_out")
+        if small_rgb_out.shape != (B, 3, fh, fw) or small_rgb_out.dtype != img.dtype:
+            raise ValueError("small_rgb_out must be [B,3,H/16,W/16] in the image dtype")
+    if label_plane_out is not None or label_small_out is not None:
+        if label is None or label.dtype != torch.uint8 or label.shape != (B, H, W):
+            raise ValueError("label must be uint8 [B,H,W]")
+        _dense(label, "label")
+    if label_plane_out is not None and (label_plane_out.shape != (B, H, W) or label_plane_out.dtype != torch.uint8
+                                        or label_plane_out.stride()[1:] != (W, 1)):
+        raise ValueError("label_plane_out must be uint8 [B,H,W] with dense planes")
+    if label_small_out is not None:
+        _dense(label_small_out, "label_small_out")
+        if label_small_out.numel() != B * fh * fw or label_small_out.dtype != torch.uint8:
+            raise ValueError("label_small_out must be uint8 [B,1,H/16,W/16]")
+    _decode_tail_fused(img, rgb_out, gray_out, feat_out, int(feat_channel), small_rgb_out, label, label_plane_out,
+                       label_small_out)
 
 
 def bilinear_lift(src: Tensor, size, *, out: Optional[Tensor] = None, out_channel: int = 0,
@@ -621,6 +736,73 @@ def lut_paint(inst: Tensor, lut: Tensor, out: Optional[Tensor] = None) -> Tensor
     mask = torch.empty(inst.shape, dtype=torch.uint8, device=inst.device) if out is None else out
     _lut_paint(inst, lut, mask, status_word(inst.device))
     return mask
+
+
+def _check_hist_args(mask_shape, gt: Tensor, C: Optional[Tensor], K: int, device):
+    if gt.dtype != torch.uint8 or tuple(gt.shape) != tuple(mask_shape):
+        raise ValueError("gt must be a uint8 map of the mask's shape")
+    _dense(gt, "gt")
+    if C is None:
+        C = torch.zeros((K + 1, K), dtype=torch.int64, device=device)
+    elif C.shape != (K + 1, K) or C.dtype != torch.int64 or not C.is_contiguous():
+        raise ValueError("out must be a contiguous int64 [(K+1),K] tensor")
+    return C
+
+
+def lift_argmax_hist(logits: Tensor, size, gt: Tensor, *, out: Optional[Tensor] = None,
+                     mask_out: Optional[Tensor] = None, exchange=None, channel: int = 0):
+    """``lift_argmax`` and ``confusion_hist(mask, gt)`` in ONE kernel: returns (mask, C); C accumulates
+    over the whole batch.  ``exchange``: a ``dist.ConfusionExchange`` whose peer push rides as the
+    kernel's tail.  Shapes the fused kernel does not take (K > 15, lifts below 4x) run the two
+    separate kernels."""
+    _dense(logits, "logits")
+    if logits.dtype != torch.float32:
+        raise TypeError("logits must be fp32")
+    B, K, h, w = logits.shape
+    H, W = size
+    mask = torch.empty((B, H, W), dtype=torch.uint8, device=logits.device) if mask_out is None else mask_out
+    C = _check_hist_args(mask.shape, gt, out, K, logits.device)
+    st = status_word(logits.device)
+    try:
+        _lift_argmax_hist(logits, mask, gt, C, st, None if exchange is None else exchange._h, channel)
+    except LdiffError as e:
+        if "unsupported" not in str(e):
+            raise
+        _lift_argmax(logits, mask)
+        if exchange is None:
+            _confusion_hist(mask.view(-1), gt.view(-1), None, C, K, st)
+        else:
+            exchange.hist_push(mask.view(-1), gt.view(-1), C, channel=channel)
+    return mask, C
+
+
+def lut_paint_hist(inst: Tensor, lut: Tensor, gt: Tensor, num_classes: int, *, out: Optional[Tensor] = None,
+                   mask_out: Optional[Tensor] = None, exchange=None, channel: int = 0):
+    """``lut_paint`` and ``confusion_hist(mask, gt)`` in ONE kernel (6 B/pixel instead of 5 + 2): returns
+    (mask, C).  Falls back to the two separate kernels for K > 15 or planes that are not 16-pixel aligned."""
+    if inst.dtype != torch.int32:
+        raise TypeError("instance map must be int32")
+    _cuda(inst, lut, gt)
+    if inst.dim() == 2:
+        inst, gt = inst.unsqueeze(0), gt.unsqueeze(0) if gt.dim() == 2 else gt
+    _dense(inst, "inst"); _dense(lut, "lut")
+    if lut.dim() == 2 and lut.shape[0] != inst.shape[0]:
+        raise ValueError("per-image LUTs must be [B,lut_size]")
+    K = int(num_classes)
+    mask = torch.empty(inst.shape, dtype=torch.uint8, device=inst.device) if mask_out is None else mask_out
+    C = _check_hist_args(mask.shape, gt, out, K, inst.device)
+    st = status_word(inst.device)
+    try:
+        _lut_paint_hist(inst, lut, mask, gt, C, K, st, None if exchange is None else exchange._h, channel)
+    except LdiffError as e:
+        if "unsupported" not in str(e) and "aligned" not in str(e):
+            raise
+        _lut_paint(inst, lut, mask, st)
+        if exchange is None:
+            _confusion_hist(mask.view(-1), gt.view(-1), None, C, K, st)
+        else:
+            exchange.hist_push(mask.view(-1), gt.view(-1), C, channel=channel)
+    return mask, C
 
 
 def argmax_channels(x: Tensor) -> Tensor:

@@ -101,13 +101,11 @@ class HotPath:
         self.cell_b = torch.zeros(num_classes, device=dev)
         self.status = ops.status_word(dev)
         self.exchange = None                                               # set by attach_exchange (multi-GPU)
-        # experiment (tools/pass_persist.py): hold the decode tails back until the head's logits exist, so a
-        # persistent lift+argmax (ldiff_tune) is resident before the first decode tail occupies every SM
-        self.decode_after_head = os.environ.get("LDIFF_PASS_DECODE_AFTER_HEAD", "0") == "1"
-        # experiment (unmeasured): each classifier chain zeroes its own matrix instead of one memset on the
-        # caller's stream that all five chains wait for
-        self.zero_in_chains = os.environ.get("LDIFF_PASS_ZERO_IN_CHAINS", "0") == "1"
-        self._head_done = torch.cuda.Event()
+        # the per-step consumers of the decoder output ride inside the decode tails when the 16x down-sample is
+        # the exact 2x2 footprint (H, W multiples of 16 and a feature map of H/16 x W/16); LDIFF_PASS_FUSED=0
+        # keeps round 1's separate launches (A/B timing, and the reference point of the equivalence tests)
+        self.fused = (os.environ.get("LDIFF_PASS_FUSED", "1") == "1" and height % 16 == 0 and width % 16 == 0
+                      and tuple(feat_size) == (height // 16, width // 16) and num_classes <= 15)
 
     def attach_exchange(self, exchange, deferred: bool = True):
         """Multi-GPU: fuse the cross-rank sum of the two confusion matrices into the pass
@@ -130,7 +128,10 @@ class HotPath:
 
     # number of ldiff kernels one pass launches
     def launches_per_pass(self) -> int:
-        return 4 * self.n + 1 + 3 + 2 + 2 + 2 + (1 if self.exchange is not None else 0)   # steady state
+        xr = 1 if self.exchange is not None else 0                         # the exchange's one-block reduce
+        if self.fused:                                                     # sampler n, decode n, lifts 2, tissue 2, cell 2
+            return 2 * self.n + 2 + 2 + 2 + xr
+        return 4 * self.n + 1 + 3 + 2 + 2 + 2 + xr
 
     def _confusion(self, mask, gt, channel):
         if self.exchange is None:
@@ -142,14 +143,14 @@ class HotPath:
         """Enqueue one pass; returns nothing (results live in the preallocated buffers).
         Graph-capturable: no allocation, no sync.
 
-        The pass is five independent chains (sampler, decode tails, training-path lifts,
-        tissue head, cell head).  With ``concurrent`` they are forked onto prioritised side
-        streams and joined at the end, so inside a CUDA graph the latency-bound latent-sized
-        launches and the ALU-bound lift+argmax overlap the HBM-bound decode tails instead of
-        queueing behind them (and the caller's stream priority does not matter)."""
+        The pass is five independent chains (sampler, decode tails, up-lift, tissue head, cell head).
+        With ``concurrent`` they are forked onto prioritised side streams and joined at the end, so
+        inside a CUDA graph the latency-bound latent-sized launches and the classifier chains overlap
+        the HBM-bound decode tails instead of queueing behind them (and the caller's stream priority
+        does not matter)."""
         cur = torch.cuda.current_stream(self.device)
         n = self.n
-        if not self.zero_in_chains:
+        if not self.fused:
             self.C.zero_()                                                 # a memset every chain waits for
         if concurrent:
             side = self._side_streams()
@@ -168,17 +169,10 @@ class HotPath:
             self._chain_lifts(inp)
         with torch.cuda.stream(side[2]), _nvtx("ldiff.tissue"):
             self._chain_tissue(inp)
-        if concurrent and self.decode_after_head:
-            # the persistent lift+argmax must get its SMs before the first decode tail fills the chip
-            side[4].wait_event(self._head_done)
         with torch.cuda.stream(side[3]), _nvtx("ldiff.cell"):
             self._chain_cell(inp)
         with torch.cuda.stream(side[4]), _nvtx("ldiff.decode_tails"):      # the bandwidth-heavy chain
-            for i in range(n):
-                last = i == n - 1
-                ops.decode_tail_gray(inp.decoded[i], want_rgb=False, rgb_out=self.rgb if last else None,
-                                     gray_out=self.planes[:, i])
-            ops.copy_planes_u8(inp.gt, self.planes[:, n])                  # label slot of the pixel vectors
+            self._chain_decode(inp)
         if concurrent:
             for s in side:
                 cur.wait_stream(s)
@@ -211,33 +205,63 @@ class HotPath:
         x = inp.latents
         blocks = (self.lat_elems + 3) // 4
         for i in range(n):
-            ops.laplace_qsample(inp.latents, sch.laplace_scale(ts[i]), seed=self.seed, offset=i * blocks,
-                                out=self.noisy[i])
-            x = sch.step(inp.eps[i], ts[i], x, out=self.lat[i]).prev_sample
+            if self.fused:        # reverse update + forward noising of the step in ONE launch
+                x, _ = sch.step_then_noise(inp.eps[i], ts[i], x, inp.latents, seed=self.seed, offset=i * blocks,
+                                           out=self.lat[i], noisy_out=self.noisy[i])
+            else:
+                ops.laplace_qsample(inp.latents, sch.laplace_scale(ts[i]), seed=self.seed, offset=i * blocks,
+                                    out=self.noisy[i])
+                x = sch.step(inp.eps[i], ts[i], x, out=self.lat[i]).prev_sample
+
+    def _chain_decode(self, inp):
+        n = self.n
+        for i in range(n):
+            last = i == n - 1
+            if self.fused:
+                # the step's training-path feature (ldiffusion.py:240-247) and, on the last step, the label slot
+                # of the pixel vectors + the label's down-sample (ldiffusion.py:224-226) ride in the same pass
+                ops.decode_tail_fused(inp.decoded[i], self.planes[:, i], rgb_out=self.rgb if last else None,
+                                      feat_out=self.featcat, feat_channel=i,
+                                      label=inp.gt if last else None,
+                                      label_plane_out=self.planes[:, n] if last else None,
+                                      label_small_out=self.label_small if last else None)
+            else:
+                ops.decode_tail_gray(inp.decoded[i], want_rgb=False, rgb_out=self.rgb if last else None,
+                                     gray_out=self.planes[:, i])
+        if not self.fused:
+            ops.copy_planes_u8(inp.gt, self.planes[:, n])                  # label slot of the pixel vectors
 
     def _chain_lifts(self, inp):
         n = self.n
-        # one gather per step: inside the concurrent pass the single multi-source launch
-        # (ops.bilinear_lift_multi, what features.feature_concat uses stand-alone) measured 4 % slower —
-        # its burst of scattered reads lands on top of the first decode tail
-        for i in range(n):
-            ops.bilinear_lift(inp.decoded[i], self.feat_size, out=self.featcat, out_channel=i, gray=True)
-        ops.bilinear_lift(inp.gt.unsqueeze(1), self.feat_size, out=self.label_small)
+        if not self.fused:
+            # one gather per step: inside the concurrent pass the single multi-source launch
+            # (ops.bilinear_lift_multi, what features.feature_concat uses stand-alone) measured 4 % slower —
+            # its burst of scattered reads lands on top of the first decode tail
+            for i in range(n):
+                ops.bilinear_lift(inp.decoded[i], self.feat_size, out=self.featcat, out_channel=i, gray=True)
+            ops.bilinear_lift(inp.gt.unsqueeze(1), self.feat_size, out=self.label_small)
+        # ldiffusion.py:251: the last decode, down then up again (its own chain: the up-lift writes 6 B/pixel and
+        # must not wait for the five decode tails)
         ops.bilinear_lift(inp.decoded[n - 1], self.feat_size, out=self.rgb_small)
         ops.bilinear_lift(self.rgb_small, (self.H, self.W), out=self.rgb_up)
 
     def _chain_tissue(self, inp):
-        if self.zero_in_chains:
-            self.C[0].zero_()
+        if self.fused:
+            ops._head_logits(inp.head_feat, self.head_w, self.head_b, self.logits, self.C[0])   # also zeroes C[0]
+            ops.lift_argmax_hist(self.logits, (self.H, self.W), inp.gt, out=self.C[0], mask_out=self.mask_tissue,
+                                 exchange=self.exchange, channel=0)
+            return
         ops._head_logits(inp.head_feat, self.head_w, self.head_b, self.logits)
-        if self.decode_after_head:
-            self._head_done.record(torch.cuda.current_stream(self.device))
         ops._lift_argmax(self.logits, self.mask_tissue)
         self._confusion(self.mask_tissue, inp.gt, 0)
 
     def _chain_cell(self, inp):
-        if self.zero_in_chains:
-            self.C[1].zero_()
+        if self.fused:
+            ops._cell_classify(inp.inst_feats, self.cell_w, self.cell_b, self.inst_ids, self.lut, None, self.status,
+                               self.C[1])                                                       # also zeroes C[1]
+            ops.lut_paint_hist(inp.inst_map, self.lut, inp.gt, self.K, out=self.C[1], mask_out=self.mask_cell,
+                               exchange=self.exchange, channel=1)
+            return
         ops._cell_classify(inp.inst_feats, self.cell_w, self.cell_b, self.inst_ids, self.lut, None, self.status)
         ops.lut_paint(inp.inst_map, self.lut, out=self.mask_cell)
         self._confusion(self.mask_cell, inp.gt, 1)

@@ -70,11 +70,18 @@ class LaplacePLMSScheduler:
         return sample
 
     def _as_int(self, timestep):
-        """Timesteps iterated from ``self.timesteps`` may be device scalars; resolve
-        them from the host copy by position instead of synchronising."""
+        """Timesteps iterated from ``self.timesteps`` may be device scalars.  An element (or a slice's
+        element) of ``self.timesteps`` is resolved from the host copy BY ITS POSITION IN THAT TENSOR —
+        the value the caller passed, without a synchronisation, also for ``timesteps[t_start:]`` or a
+        reordered walk; any other device tensor is read back (one sync, as diffusers does)."""
         if isinstance(timestep, torch.Tensor):
-            if timestep.is_cuda and self._host_timesteps is not None and self.counter < len(self._host_timesteps):
-                return self._host_timesteps[self.counter]
+            ts = self.timesteps
+            if (timestep.is_cuda and timestep.dim() == 0 and ts is not None and ts.is_cuda
+                    and self._host_timesteps is not None
+                    and timestep.untyped_storage().data_ptr() == ts.untyped_storage().data_ptr()):
+                idx = timestep.storage_offset() - ts.storage_offset()
+                if 0 <= idx < len(self._host_timesteps):
+                    return self._host_timesteps[idx]
             return int(timestep)
         return int(timestep)
 
@@ -107,7 +114,7 @@ class LaplacePLMSScheduler:
         denom = a_t * b_p ** 0.5 + (a_t * b_t * a_p) ** 0.5
         return mode, sample_coeff.item(), (a_p - a_t).item(), denom.item()
 
-    def step(self, model_output, timestep, sample, return_dict: bool = True, out=None):
+    def step(self, model_output, timestep, sample, return_dict: bool = True, out=None, noise_of=None):
         if self.num_inference_steps is None:
             raise ValueError(
                 "Number of inference steps is 'None', you need to run 'set_timesteps' after creating the scheduler")
@@ -125,11 +132,32 @@ class LaplacePLMSScheduler:
             self.cur_sample = None
         else:
             eps = self.ets[::-1]
-        prev = ops.plms_step(sample, eps, mode, sc, dA, denom, out=out)
+        if noise_of is None:
+            prev = ops.plms_step(sample, eps, mode, sc, dA, denom, out=out)
+        else:
+            prev, noisy = ops.plms_step_noise(sample, eps, mode, sc, dA, denom, noise_of["clean"],
+                                              self.laplace_scale(noise_of.get("timestep", t)),
+                                              noise=noise_of.get("noise"), u=noise_of.get("u"),
+                                              seed=noise_of.get("seed", 0), offset=noise_of.get("offset", 0),
+                                              out=out, noisy_out=noise_of.get("out"))
         self.counter += 1
+        if noise_of is not None:
+            return SchedulerOutput(prev_sample=prev), noisy
         if not return_dict:
             return (prev,)
         return SchedulerOutput(prev_sample=prev)
+
+    def step_then_noise(self, model_output, timestep, sample, clean, *, noise_timestep=None, noise=None, u=None,
+                        seed: int = 0, offset: int = 0, out=None, noisy_out=None):
+        """The reverse update of ``step`` AND the Laplace forward noising of ``clean`` at
+        ``noise_timestep`` (default: ``timestep``) in ONE kernel launch — the two latent-sized ops the
+        reference runs per loop iteration (segmentor.py:100-104; ldiffusion.py:233-237).  Returns
+        (prev_sample, noisy); bit-identical to ``step`` + ``add_laplace_noise``."""
+        t = self._as_int(timestep)
+        spec = {"clean": clean, "timestep": t if noise_timestep is None else int(noise_timestep), "noise": noise,
+                "u": u, "seed": seed, "offset": offset, "out": noisy_out}
+        res, noisy = self.step(model_output, timestep, sample, out=out, noise_of=spec)
+        return res.prev_sample, noisy
 
     def __len__(self):
         return self.num_train_timesteps

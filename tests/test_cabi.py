@@ -67,7 +67,28 @@ def test_argument_errors_are_reported_without_a_gpu(built_lib):
     assert lib.ldiff_confusion_hist(16, 16, None, 16, 64, 0, 16, None) == EINVAL                       # K < 1
     assert lib.ldiff_confusion_hist(16, 16, None, 16, 64, 200, 16, None) == EUNSUP                     # K > 128
     assert lib.ldiff_lift_argmax(16, 16, 1, 300, 4, 4, 8, 8, None) == EINVAL
-    assert lib.ldiff_head_logits(16, 16, None, 16, 1, 256, 64, 1024, 1, None) == EUNSUP                # K > 32
+    assert lib.ldiff_head_logits(16, 16, None, 16, 1, 256, 64, 1024, 1, None, 0, None) == EUNSUP       # K > 32
+    assert lib.ldiff_head_logits(16, 16, None, 16, 1, 256, 8, 1024, 1, None, 4, None) == EINVAL        # clear without buffer
+    sn = lib.ldiff_plms_step_noise
+    assert sn(16, 16, None, None, None, 0, 1.0, 0.0, 1.0, 16, None, 16, None, None, 1.0, 0, 0, 8, 0, None) == EINVAL   # no clean
+    assert sn(16, 16, None, None, None, 3, 1.0, 0.0, 1.0, 16, 16, 16, None, None, 1.0, 0, 0, 8, 0, None) == EINVAL     # missing e1, e2
+    assert sn(16, 16, None, None, None, 0, 1.0, 0.0, 1.0, 16, 16, 16, 16, 16, 1.0, 0, 0, 8, 0, None) == EINVAL         # noise and u
+    assert sn(16, 16, None, None, None, 0, 1.0, 0.0, 1.0, 16, 16, 24, None, None, 1.0, 0, 0, 8, 0, None) == EALIGN
+    assert sn(16, 16, None, None, None, 0, 1.0, 0.0, 1.0, 16, 16, 16, None, None, 1.0, 0, 0, 0, 0, None) == 0          # n == 0
+    df = lib.ldiff_decode_tail_fused
+    assert df(16, None, 16, 1, 32, 32, 1024, 0, None, 0, 1, 0, None, None, None, 0, None, None) == EINVAL   # nothing fused
+    assert df(16, None, 16, 1, 32, 32, 1024, 0, None, 0, 1, 0, None, None, 16, 1024, None, None) == EINVAL  # plane without label
+    assert df(16, None, 16, 1, 40, 32, 1280, 0, 16, 0, 1, 0, None, None, None, 0, None, None) == EUNSUP     # H % 16
+    assert df(16, None, 16, 1, 32, 32, 1024, 0, 16, 0, 2, 2, None, None, None, 0, None, None) == EINVAL     # channel outside feat
+    assert df(16, None, 16, 1, 32, 32, 1024, 1, 16, 2, 1, 0, None, None, None, 0, None, None) == EUNSUP     # u8 feature
+    ph = lib.ldiff_lut_paint_hist
+    assert ph(16, 16, 16, None, 16, 64, 1, 8, 8, 5, None, 0, 16, None) == EINVAL                        # no gt
+    assert ph(16, 16, 16, 16, 16, 64, 1, 8, 8, 16, None, 0, 16, None) == EUNSUP                         # K > 15
+    assert ph(16, 16, 16, 16, 16, 60, 1, 8, 8, 5, None, 0, 16, None) == EALIGN                          # n % 16
+    ah = lib.ldiff_lift_argmax_hist
+    assert ah(16, 16, None, 16, 1, 5, 4, 4, 64, 64, None, 0, 16, None) == EINVAL                        # no gt
+    assert ah(16, 16, 16, 16, 1, 16, 4, 4, 64, 64, None, 0, 16, None) == EUNSUP                         # K > 15
+    assert ah(16, 16, 16, 16, 1, 5, 4, 4, 8, 8, None, 0, 16, None) == EUNSUP                            # lift below 4x
     assert lib.ldiff_launch_count() == 0
 
 
@@ -85,7 +106,7 @@ def test_ops_refuse_cpu_tensors():
 def test_custom_ops_are_registered():
     import torch
     import ldiffusion_b200  # noqa: F401
-    for name in ("laplace_qsample", "laplace_qsample_map", "scaled_residual", "plms_step", "decode_tail_gray", "bilinear_lift", "head_logits", "lift_argmax",
+    for name in ("laplace_qsample", "laplace_qsample_map", "scaled_residual", "plms_step", "plms_step_noise", "decode_tail_gray", "decode_tail_fused", "bilinear_lift", "head_logits", "lift_argmax",
                  "cell_classify", "lut_paint", "argmax_channels", "confusion_hist", "confusion_hist_batched"):
         assert hasattr(torch.ops.ldiff, name), name
 

@@ -1,9 +1,6 @@
-"""GPU parity of the opt-in kernel forms behind ``ldiff_tune`` (include/ldiff.h).  The persistent
-lift+argmax was measured in round 1 (profiles/r01_pass_persist.txt); the bulk-TMA staged decode tail has
-NOT run on a GPU yet, so this file only runs when asked to (``LDIFF_TEST_EXPERIMENTAL=1``): an unproven
-mbarrier pipeline must not be able to hang the default suite."""
-import os
-
+"""GPU parity of the kernel forms selectable through ``ldiff_tune`` (include/ldiff.h): every decode-tail
+staging shape and every lift+argmax variant must produce the same bytes; plus the training-caller kernels
+(lift adjoint, warm-up step).  All of them ship in the library, so all of them run in the default GPU suite."""
 import numpy as np
 import pytest
 import torch
@@ -11,9 +8,7 @@ import torch
 from oracle import decode_tail as odt
 from oracle import head as ohead
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("LDIFF_TEST_EXPERIMENTAL", "0") != "1",
-                                 reason="experimental kernels: set LDIFF_TEST_EXPERIMENTAL=1")]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.fixture
@@ -21,8 +16,8 @@ def tune():
     from ldiffusion_b200 import _cabi
     lib = _cabi.lib()
     yield lambda knob, value: lib.ldiff_tune(knob, value)
-    for knob in range(3):
-        lib.ldiff_tune(knob, 0)
+    for knob, default in ((_cabi.TUNE_ARGMAX_VARIANT, 0), (_cabi.TUNE_DECODE_TAIL_SMS, 0), (_cabi.TUNE_DECODE_TAIL_TMA, 1)):
+        lib.ldiff_tune(knob, default)
 
 
 @pytest.mark.timeout(120)
@@ -36,14 +31,15 @@ def test_decode_tail_tma_bit_exact(tune, shape, want_rgb, dtype):
     img = torch.empty(shape).uniform_(-1.3, 1.3, generator=g).to(dtype)
     tune(_cabi.TUNE_DECODE_TAIL_TMA, 0)
     rgb0, gray0 = ops.decode_tail_gray(img.cuda(), want_rgb=want_rgb)
-    tune(_cabi.TUNE_DECODE_TAIL_TMA, 1)
-    rgb1, gray1 = ops.decode_tail_gray(img.cuda(), want_rgb=want_rgb)
-    torch.cuda.synchronize()
-    assert torch.equal(gray0, gray1)
-    if want_rgb:
-        assert torch.equal(rgb0, rgb1)
-        if shape[-1] * shape[-2] <= 128 * 96:
-            assert np.array_equal(rgb1.cpu().numpy(), odt.decode_tail_chain(img))
+    for variant in (1, 2, 3, 4):
+        tune(_cabi.TUNE_DECODE_TAIL_TMA, variant)
+        rgb1, gray1 = ops.decode_tail_gray(img.cuda(), want_rgb=want_rgb)
+        torch.cuda.synchronize()
+        assert torch.equal(gray0, gray1), variant
+        if want_rgb:
+            assert torch.equal(rgb0, rgb1), variant
+            if shape[-1] * shape[-2] <= 128 * 96:
+                assert np.array_equal(rgb1.cpu().numpy(), odt.decode_tail_chain(img))
     # slot of a pixel-vector tensor (strided gray planes)
     planes = torch.zeros(shape[0], 3, shape[2], shape[3], dtype=torch.uint8, device="cuda")
     ops.decode_tail_gray(img.cuda(), want_rgb=False, gray_out=planes[:, 1])
@@ -51,15 +47,17 @@ def test_decode_tail_tma_bit_exact(tune, shape, want_rgb, dtype):
 
 
 @pytest.mark.timeout(120)
-def test_lift_argmax_persistent_bit_exact(tune):
+@pytest.mark.parametrize("variant", [0, 4, 5])
+def test_lift_argmax_variants_bit_exact(tune, variant):
+    """0 = envelope kernel (default), 4 / 5 = per-pixel evaluation with 2 / 1 columns per thread."""
     from ldiffusion_b200 import _cabi, ops
     g = torch.Generator().manual_seed(3)
-    for K, shape, size in ((11, (2, 32, 32), (1024, 1024)), (6, (1, 16, 16), (512, 512)), (7, (3, 8, 8), (128, 96))):
+    tune(_cabi.TUNE_ARGMAX_VARIANT, variant)
+    for K, shape, size in ((11, (2, 32, 32), (1024, 1024)), (6, (1, 16, 16), (512, 512)), (7, (3, 8, 8), (128, 96)),
+                           (15, (1, 8, 8), (64, 66)), (3, (1, 5, 7), (45, 63))):
         logits = torch.randn((shape[0], K) + shape[1:], generator=g)
-        tune(_cabi.TUNE_ARGMAX_PERSIST_BLOCKS, 52)
         got = ops.lift_argmax(logits.cuda(), size)
-        tune(_cabi.TUNE_ARGMAX_PERSIST_BLOCKS, 0)
-        assert np.array_equal(got.cpu().numpy(), ohead.lift_argmax_spec(logits.numpy(), size))
+        assert np.array_equal(got.cpu().numpy(), ohead.lift_argmax_spec(logits.numpy(), size)), (K, shape, size)
 
 
 @pytest.mark.timeout(120)
