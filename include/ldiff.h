@@ -53,8 +53,8 @@ enum { LDIFF_STATUS_PRED_RANGE = 1, LDIFF_STATUS_INST_RANGE = 2, LDIFF_STATUS_SW
  *    kernel, 4 / 5 = round 1's per-pixel evaluation kernel with 2 / 1 columns per thread (A/B timing);
  *  LDIFF_TUNE_DECODE_TAIL_SMS (env LDIFF_DT_SMS, default 0 = all): the register-staged decode tail sizes its
  *    one-wave grid for that many SMs;
- *  LDIFF_TUNE_DECODE_TAIL_TMA (env LDIFF_DT_TMA, default 1): 0 = register-staged decode tail, 1..4 = the
- *    bulk-TMA staged persistent kernel with (stages x CTAs/SM) = (4x2) / (3x3) / (2x4) / (2x3) for bf16. */
+ *  LDIFF_TUNE_DECODE_TAIL_TMA (env LDIFF_DT_TMA, default 6): 0 = register-staged decode tail, 1..6 = the
+ *    bulk-TMA staged persistent kernel with (stages x CTAs/SM) = (4x2) / (3x3) / (2x4) / (2x3) / (3x2) / (2x2) for bf16. */
 enum { LDIFF_TUNE_ARGMAX_VARIANT = 0, LDIFF_TUNE_DECODE_TAIL_SMS = 1, LDIFF_TUNE_DECODE_TAIL_TMA = 2,
        LDIFF_TUNE_COUNT = 3 };
 int ldiff_tune(int knob, int value);

@@ -240,7 +240,9 @@ lift_separable_kernel(const TS* __restrict__ src, int64_t sbs, int64_t scs, TD* 
       }
     };
     int cur0 = -1, cur1 = -1;
-    for (int yy = ya; yy < yb; ++yy) {
+    // output pointer of this thread's vector in channel (dch [+ c0]) of the current row, advanced by W per row
+    TD* orow = dst + ((int64_t)b * Ctot + dch + (GRAY ? 0 : c0)) * HW + (int64_t)(Y0 + ya) * W + X;
+    for (int yy = ya; yy < yb; ++yy, orow += W) {
       const int4 tp = s_tap[yy];
       const float l0 = __int_as_float(tp.z), l1 = __int_as_float(tp.w);
       if (tp.x != cur0 || tp.y != cur1) {                // block-uniform per sub-band
@@ -262,7 +264,6 @@ lift_separable_kernel(const TS* __restrict__ src, int64_t sbs, int64_t scs, TD* 
         }
         cur0 = tp.x; cur1 = tp.y;
       }
-      const int64_t row_off = (int64_t)(Y0 + yy) * W + X;
       float out[V];
       if (GRAY) {
         float ch[3][V];
@@ -272,13 +273,20 @@ lift_separable_kernel(const TS* __restrict__ src, int64_t sbs, int64_t scs, TD* 
           for (int k = 0; k < V; ++k) ch[c][k] = lerp_h(l0, T0[c % NC][k], l1, T1[c % NC][k]);
 #pragma unroll
         for (int k = 0; k < V; ++k) out[k] = gray3(ch[0][k], ch[1][k], ch[2][k]);
-        OutVec<TD>::store(dst + ((int64_t)b * Ctot + dch) * HW + row_off, out);
+        OutVec<TD>::store(orow, out);
       } else {
+        // two elements per instruction on the packed fp32x2 pipe: FMUL2 + FFMA2 are IEEE per lane, i.e. exactly
+        // lerp_h's fma(l0, a, fl(l1 * b)) (the product feeds the ADDEND of the fma, so nothing can be contracted)
+        const float2 l0p = make_float2(l0, l0), l1p = make_float2(l1, l1);
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
 #pragma unroll
-          for (int k = 0; k < V; ++k) out[k] = lerp_h(l0, T0[c][k], l1, T1[c][k]);
-          OutVec<TD>::store(dst + ((int64_t)b * Ctot + dch + c0 + c) * HW + row_off, out);
+          for (int k = 0; k < V; k += 2) {
+            const float2 v = __ffma2_rn(l0p, make_float2(T0[c][k], T0[c][k + 1]),
+                                        __fmul2_rn(l1p, make_float2(T1[c][k], T1[c][k + 1])));
+            out[k] = v.x; out[k + 1] = v.y;
+          }
+          OutVec<TD>::store(orow + c * HW, out);
         }
       }
     }

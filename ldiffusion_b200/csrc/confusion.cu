@@ -102,8 +102,10 @@ confusion_hist_push_kernel(const uint8_t* __restrict__ pred, const uint8_t* __re
 // AND C[gt[b,p]][mask[b,p]] += 1 while the mask byte is still in a register — the stand-alone histogram
 // would read the 1 B/pixel mask back and needs its own launch.  6 B/pixel: 4 (instance id) + 1 (gt) in,
 // 1 (mask) out.  K <= 15 (byte-sized bins); one matrix for the whole batch (grid.y = image picks the LUT).
+// (256-thread blocks of <= 48 registers: 12 K registers and 17 KB of shared memory per block, so that blocks slot in
+// next to the resident decode-tail CTAs of the concurrent pass instead of waiting for half an SM's register file)
 template <bool PUSH>
-__global__ void __launch_bounds__(512, 2)
+__global__ void __launch_bounds__(256, 5)
 lut_paint_hist_kernel(const int32_t* __restrict__ inst, const uint8_t* __restrict__ lut, uint8_t* __restrict__ mask,
                       const uint8_t* __restrict__ gt, unsigned long long* __restrict__ C, int64_t n, int lut_size,
                       int64_t lut_stride, int K, int* __restrict__ status, XchgPush px) {
@@ -396,10 +398,10 @@ extern "C" int ldiff_lut_paint_hist(const int32_t* inst, const uint8_t* lut, uin
   }
   if (n_per_image == 0 || B == 0) return xchg ? LDIFF_EINVAL : LDIFF_OK;   // a push needs a launch
   if (!aligned16(inst) || !aligned16(mask) || !aligned16(gt) || (n_per_image % 16)) return LDIFF_EALIGN;
-  const int threads = 512;
+  const int threads = 256;
   const size_t smem = (size_t)(K + 1) * K * 32 * 4;
   int64_t bx = ((n_per_image >> 4) + threads - 1) / threads;
-  const int64_t cap = ((int64_t)sm_count() * 2 + B - 1) / B;     // 2 blocks of 512 threads per SM over the batch
+  const int64_t cap = ((int64_t)sm_count() * 4 + B - 1) / B;     // 4 blocks of 256 threads per SM over the batch
   if (bx > cap) bx = cap > 0 ? cap : 1;
   const dim3 grid((unsigned)bx, (unsigned)B);
   unsigned long long* Cu = reinterpret_cast<unsigned long long*>(C);

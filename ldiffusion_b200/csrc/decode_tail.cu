@@ -121,41 +121,66 @@ __device__ __forceinline__ float half_lerp(float a, float b) {        // lerp_h(
   return __fmaf_rn(0.5f, a, __fmul_rn(0.5f, b));
 }
 
+// The extras in two halves, so that their scattered loads are in flight while the thread does its main work:
+// extras_load() issues them BEFORE the tile is read (nothing waits on the results yet), extras_finish()
+// consumes them after the tile's stores.
+struct ExtrasRegs {
+  float px[3][4];              // footprint of each channel: top-left, top-right, bottom-left, bottom-right
+  uint4 lab;                   // this thread's 16 label bytes (label plane copy)
+  uint32_t lab4;               // the label's 2x2 footprint, one byte each
+  int64_t o;                   // output pixel of a feature plane, -1: this thread owns no footprint
+};
+
 template <typename T>
-__device__ __forceinline__ void tail_extras(const T* __restrict__ img, const TailExtras& ex, int64_t b, int64_t hw,
-                                            int gidx) {
+__device__ __forceinline__ void extras_load(const T* __restrict__ img, const TailExtras& ex, int64_t b, int64_t hw,
+                                            int gidx, ExtrasRegs& er) {
   const int64_t p = (int64_t)gidx << 4;
-  if (ex.label_plane)
-    __stcs(reinterpret_cast<uint4*>(ex.label_plane + b * ex.label_plane_stride + p),
-           __ldg(reinterpret_cast<const uint4*>(ex.label + b * hw + p)));
+  if (ex.label_plane) er.lab = __ldg(reinterpret_cast<const uint4*>(ex.label + b * hw + p));
   const int y = ex.gpr_shift >= 0 ? (gidx >> ex.gpr_shift) : (gidx / ex.gpr);
+  er.o = -1;
   if ((y & 15) != 7) return;
-  const int g = gidx - y * ex.gpr;
-  const int64_t o = ((int64_t)(y >> 4)) * ex.gpr + g;                 // output pixel (y/16, g) of a plane
-  const int64_t fplane = (int64_t)ex.fh * ex.gpr;
+  er.o = ((int64_t)(y >> 4)) * ex.gpr + (gidx - y * ex.gpr);          // output pixel (y/16, g) of a plane
   if (ex.feat || ex.small_rgb) {
-    float v[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const T* r0 = img + (b * 3 + c) * hw + p + 7;
       const T* r1 = r0 + ex.W;
-      v[c] = half_lerp(half_lerp(to_f32(__ldg(r0)), to_f32(__ldg(r0 + 1))),
-                       half_lerp(to_f32(__ldg(r1)), to_f32(__ldg(r1 + 1))));
-      if (ex.small_rgb) static_cast<T*>(ex.small_rgb)[(b * 3 + c) * fplane + o] = from_f32<T>(v[c]);
-    }
-    if (ex.feat) {
-      const float gr = __fadd_rn(__fadd_rn(__fmul_rn(0.2989f, v[0]), __fmul_rn(0.5870f, v[1])), __fmul_rn(0.1140f, v[2]));
-      const int64_t fo = (b * ex.feat_ctot + ex.feat_ch) * fplane + o;
-      if (ex.feat_f32) static_cast<float*>(ex.feat)[fo] = gr;
-      else static_cast<T*>(ex.feat)[fo] = from_f32<T>(gr);
+      er.px[c][0] = to_f32(__ldg(r0)); er.px[c][1] = to_f32(__ldg(r0 + 1));
+      er.px[c][2] = to_f32(__ldg(r1)); er.px[c][3] = to_f32(__ldg(r1 + 1));
     }
   }
   if (ex.label_small) {
     const uint8_t* r0 = ex.label + b * hw + p + 7;
     const uint8_t* r1 = r0 + ex.W;
-    const float v = half_lerp(half_lerp((float)__ldg(r0), (float)__ldg(r0 + 1)),
-                              half_lerp((float)__ldg(r1), (float)__ldg(r1 + 1)));
-    ex.label_small[b * fplane + o] = from_f32<uint8_t>(v);
+    er.lab4 = (uint32_t)__ldg(r0) | ((uint32_t)__ldg(r0 + 1) << 8) | ((uint32_t)__ldg(r1) << 16) |
+              ((uint32_t)__ldg(r1 + 1) << 24);
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void extras_finish(const TailExtras& ex, int64_t b, int gidx, const ExtrasRegs& er) {
+  if (ex.label_plane)
+    __stcs(reinterpret_cast<uint4*>(ex.label_plane + b * ex.label_plane_stride + ((int64_t)gidx << 4)), er.lab);
+  if (er.o < 0) return;
+  const int64_t fplane = (int64_t)ex.fh * ex.gpr;
+  if (ex.feat || ex.small_rgb) {
+    float v[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      v[c] = half_lerp(half_lerp(er.px[c][0], er.px[c][1]), half_lerp(er.px[c][2], er.px[c][3]));
+      if (ex.small_rgb) static_cast<T*>(ex.small_rgb)[(b * 3 + c) * fplane + er.o] = from_f32<T>(v[c]);
+    }
+    if (ex.feat) {
+      const float gr = __fadd_rn(__fadd_rn(__fmul_rn(0.2989f, v[0]), __fmul_rn(0.5870f, v[1])), __fmul_rn(0.1140f, v[2]));
+      const int64_t fo = (b * ex.feat_ctot + ex.feat_ch) * fplane + er.o;
+      if (ex.feat_f32) static_cast<float*>(ex.feat)[fo] = gr;
+      else static_cast<T*>(ex.feat)[fo] = from_f32<T>(gr);
+    }
+  }
+  if (ex.label_small) {
+    const float v = half_lerp(half_lerp((float)(er.lab4 & 0xffu), (float)((er.lab4 >> 8) & 0xffu)),
+                              half_lerp((float)((er.lab4 >> 16) & 0xffu), (float)(er.lab4 >> 24)));
+    ex.label_small[b * fplane + er.o] = from_f32<uint8_t>(v);
   }
 }
 
@@ -179,7 +204,8 @@ decode_tail_vec16_kernel(const T* __restrict__ img, uint8_t* __restrict__ rgb,
   for (int gidx = blockIdx.x * blockDim.x + threadIdx.x; gidx < groups_per_img; gidx += stride) {
     const int64_t p = (int64_t)gidx << 4;
     const T* base = img + b * 3 * hw + p;
-    if (EXTRA) tail_extras<T>(img, ex, b, hw, gidx);
+    ExtrasRegs er;
+    if (EXTRA) extras_load<T>(img, ex, b, hw, gidx, er);
     uint32_t q[3][16];                                 // float bits 0x4B400000 | value
 #pragma unroll
     for (int c = 0; c < 3; ++c) quant16(base + c * hw, q[c]);
@@ -218,6 +244,7 @@ decode_tail_vec16_kernel(const T* __restrict__ img, uint8_t* __restrict__ rgb,
                                     s_norm[c * 256 + (q[c][4 * j + 3] & 255)]));
       }
     }
+    if (EXTRA) extras_finish<T>(ex, b, gidx, er);
   }
 }
 
@@ -279,30 +306,51 @@ __device__ __forceinline__ void quant16_staged(const float* p, uint32_t (&q)[16]
   }
 }
 
-// grid = persistent CTAs; tile t of the job = image t / tiles_per_img, pixels (t % tiles_per_img) * kDtTile ...
+// grid = persistent CTAs walking tiles of kDtTile pixels.  Without extras: tile t of the job = image
+// t / tiles_per_img, pixels (t % tiles_per_img) * kDtTile ...  With extras the tiles of an image are SHIFTED by
+// tile_off pixels (a whole number of rows; tiles_per_img then counts one more, the first and last tile are
+// partial): the shift is chosen by the host so that the 2x2 footprints of the 16x down-sample (rows 16e+7, 16e+8)
+// never straddle two tiles, and the thread that owns columns 16g..16g+15 of row 16e+7 reads all four footprint
+// pixels of each channel from SHARED memory — the feature costs no global load at all.
+// (Round-2 measurements at 8 x 1024^2 bf16, gray only, 2 stages x 3 CTAs: plain 11.3 us; footprints re-read
+// from global by the owning threads 13.4 us; by a dedicated ninth warp 14.9 us (latency-bound, and the label
+// copy through it 25 us); from shared memory: see profiles/.)
+// (register cap: 42 for the gray-only forms, 64 with RGB — the CTAs of this kernel are resident for a whole launch,
+// and what they leave of the register file is what the concurrent chains of the pass get to run in)
 template <typename T, bool RGB, bool GRAY, bool EXTRA, int STAGES, int CTAS>
-__global__ void __launch_bounds__(256, CTAS)
+__global__ void __launch_bounds__(256, (RGB ? 4 : 6) > CTAS ? (RGB ? 4 : 6) : CTAS)
 decode_tail_tma_kernel(const T* __restrict__ img, uint8_t* __restrict__ rgb,
                        uint8_t* __restrict__ gray, int64_t hw, int tiles_per_img, int total_tiles,
-                       int64_t gray_batch_stride, TailExtras ex) {
+                       int64_t gray_batch_stride, int tile_off, TailExtras ex) {
   constexpr int kDtStages = STAGES;
   extern __shared__ __align__(128) uint8_t dt_smem[];            // [kDtStages][3][kDtTile] T
+  const int tiles_shift = (tiles_per_img & (tiles_per_img - 1)) == 0 ? 31 - __clz(tiles_per_img) : -1;
   __shared__ __align__(8) uint64_t full[kDtStages];
   T* buf = reinterpret_cast<T*>(dt_smem);
   const int tid = threadIdx.x;
-  constexpr uint32_t kPlaneBytes = kDtTile * sizeof(T);
 
+  // tile t -> image b, first pixel p0, pixel count n (< kDtTile only for the partial tiles of a shifted image)
+  auto tile_of = [&](int t, int& b, int64_t& p0, int& n) {
+    b = tiles_shift >= 0 ? (t >> tiles_shift) : (t / tiles_per_img);
+    const int i = t - b * tiles_per_img;
+    if (!EXTRA || tile_off == 0) { p0 = (int64_t)i * kDtTile; n = kDtTile; return; }
+    p0 = i == 0 ? 0 : (int64_t)tile_off + (int64_t)(i - 1) * kDtTile;
+    const int64_t p1 = (int64_t)tile_off + (int64_t)i * kDtTile;
+    n = (int)((p1 < hw ? p1 : hw) - p0);
+  };
   // k-th tile of this CTA -> stage k % kDtStages (one thread issues; completion lands on full[stage])
   auto issue = [&](int k) {
     const int t = blockIdx.x + k * gridDim.x;
     if (t >= total_tiles) return;
     const int s = k % kDtStages;
-    const int b = t / tiles_per_img;
-    const int64_t p0 = (int64_t)(t - b * tiles_per_img) * kDtTile;
-    dt_mbar_expect_tx(&full[s], 3 * kPlaneBytes);
+    int b, n;
+    int64_t p0;
+    tile_of(t, b, p0, n);
+    const uint32_t bytes = (uint32_t)n * sizeof(T);
+    dt_mbar_expect_tx(&full[s], 3 * bytes);
 #pragma unroll
     for (int c = 0; c < 3; ++c)
-      dt_bulk_g2s(buf + (s * 3 + c) * kDtTile, img + ((int64_t)b * 3 + c) * hw + p0, kPlaneBytes, &full[s]);
+      dt_bulk_g2s(buf + (s * 3 + c) * kDtTile, img + ((int64_t)b * 3 + c) * hw + p0, bytes, &full[s]);
   };
   if (tid == 0) {
 #pragma unroll
@@ -318,33 +366,67 @@ decode_tail_tma_kernel(const T* __restrict__ img, uint8_t* __restrict__ rgb,
     const int t = blockIdx.x + k * gridDim.x;
     if (t >= total_tiles) break;                                 // (block-uniform)
     const int s = k % kDtStages;
-    const int64_t b = t / tiles_per_img;
-    const int64_t p = (int64_t)(t - (int)b * tiles_per_img) * kDtTile + tid * 16;
-    if (EXTRA) tail_extras<T>(img, ex, b, hw, (int)(p >> 4));      // (global loads: overlap the wait)
+    int bi, n;
+    int64_t p0;
+    tile_of(t, bi, p0, n);
+    const int64_t b = bi;
+    const bool mine = tid * 16 < n;                              // (partial tiles: the tail threads idle)
+    const int64_t p = p0 + tid * 16;
+    uint4 lab = make_uint4(0, 0, 0, 0);
+    if (EXTRA && ex.label_plane && mine) lab = __ldg(reinterpret_cast<const uint4*>(ex.label + b * hw + p));
     dt_mbar_wait(&full[s], (uint32_t)(k / kDtStages) & 1u);
-    uint32_t q[3][16];
+    if (mine) {
+      uint32_t q[3][16];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) quant16_staged(buf + (s * 3 + c) * kDtTile + tid * 16, q[c]);
-    if (GRAY) {
-      uint32_t w[4];
+      for (int c = 0; c < 3; ++c) quant16_staged(buf + (s * 3 + c) * kDtTile + tid * 16, q[c]);
+      if (GRAY) {
+        uint32_t w[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        w[j] = pack4<2>(luma_sum(q[0][4 * j], q[1][4 * j], q[2][4 * j]),
-                        luma_sum(q[0][4 * j + 1], q[1][4 * j + 1], q[2][4 * j + 1]),
-                        luma_sum(q[0][4 * j + 2], q[1][4 * j + 2], q[2][4 * j + 2]),
-                        luma_sum(q[0][4 * j + 3], q[1][4 * j + 3], q[2][4 * j + 3]));
-      __stcs(reinterpret_cast<uint4*>(gray + b * gray_batch_stride + p), make_uint4(w[0], w[1], w[2], w[3]));
-    }
-    if (RGB) {
-      uint32_t w[12];
+        for (int j = 0; j < 4; ++j)
+          w[j] = pack4<2>(luma_sum(q[0][4 * j], q[1][4 * j], q[2][4 * j]),
+                          luma_sum(q[0][4 * j + 1], q[1][4 * j + 1], q[2][4 * j + 1]),
+                          luma_sum(q[0][4 * j + 2], q[1][4 * j + 2], q[2][4 * j + 2]),
+                          luma_sum(q[0][4 * j + 3], q[1][4 * j + 3], q[2][4 * j + 3]));
+        __stcs(reinterpret_cast<uint4*>(gray + b * gray_batch_stride + p), make_uint4(w[0], w[1], w[2], w[3]));
+      }
+      if (RGB) {
+        uint32_t w[12];
 #pragma unroll
-      for (int j = 0; j < 12; ++j)
-        w[j] = pack4<0>(q[(4 * j) % 3][(4 * j) / 3], q[(4 * j + 1) % 3][(4 * j + 1) / 3],
-                        q[(4 * j + 2) % 3][(4 * j + 2) / 3], q[(4 * j + 3) % 3][(4 * j + 3) / 3]);
-      uint4* o = reinterpret_cast<uint4*>(rgb + (b * hw + p) * 3);
-      __stcs(o, make_uint4(w[0], w[1], w[2], w[3]));
-      __stcs(o + 1, make_uint4(w[4], w[5], w[6], w[7]));
-      __stcs(o + 2, make_uint4(w[8], w[9], w[10], w[11]));
+        for (int j = 0; j < 12; ++j)
+          w[j] = pack4<0>(q[(4 * j) % 3][(4 * j) / 3], q[(4 * j + 1) % 3][(4 * j + 1) / 3],
+                          q[(4 * j + 2) % 3][(4 * j + 2) / 3], q[(4 * j + 3) % 3][(4 * j + 3) / 3]);
+        uint4* o = reinterpret_cast<uint4*>(rgb + (b * hw + p) * 3);
+        __stcs(o, make_uint4(w[0], w[1], w[2], w[3]));
+        __stcs(o + 1, make_uint4(w[4], w[5], w[6], w[7]));
+        __stcs(o + 2, make_uint4(w[8], w[9], w[10], w[11]));
+      }
+      if (EXTRA) {
+        const int gidx = (int)(p >> 4);
+        if (ex.label_plane)
+          __stcs(reinterpret_cast<uint4*>(ex.label_plane + b * ex.label_plane_stride + p), lab);
+        const int y = ex.gpr_shift >= 0 ? (gidx >> ex.gpr_shift) : (gidx / ex.gpr);
+        if ((y & 15) == 7) {                                     // this thread owns a footprint: all of it is in the tile
+          ExtrasRegs er;
+          er.o = ((int64_t)(y >> 4)) * ex.gpr + (gidx - y * ex.gpr);
+          if (ex.feat || ex.small_rgb) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const T* r0 = buf + (s * 3 + c) * kDtTile + tid * 16 + 7;
+              er.px[c][0] = to_f32(r0[0]); er.px[c][1] = to_f32(r0[1]);
+              er.px[c][2] = to_f32(r0[ex.W]); er.px[c][3] = to_f32(r0[ex.W + 1]);
+            }
+          }
+          if (ex.label_small) {
+            const uint8_t* r0 = ex.label + b * hw + p + 7;
+            const uint8_t* r1 = r0 + ex.W;
+            er.lab4 = (uint32_t)__ldg(r0) | ((uint32_t)__ldg(r0 + 1) << 8) | ((uint32_t)__ldg(r1) << 16) |
+                      ((uint32_t)__ldg(r1 + 1) << 24);
+          }
+          TailExtras fx = ex;
+          fx.label_plane = nullptr;                              // (stored above)
+          extras_finish<T>(fx, b, gidx, er);
+        }
+      }
     }
     __syncthreads();                                             // every thread has read stage s
     if (tid == 0) {
@@ -396,14 +478,14 @@ static void ensure_smem_attr(F kernel, int bytes, bool (&done)[kMaxDevices]) {
 
 template <typename T, bool RGB, bool GRAY, bool EXTRA, int STAGES, int CTAS>
 static void launch_tma_one(const T* p, uint8_t* rgb, uint8_t* gray, int64_t hw, int tiles_per_img, int total,
-                           int64_t gray_batch_stride, const TailExtras& ex, cudaStream_t st) {
+                           int64_t gray_batch_stride, int tile_off, const TailExtras& ex, cudaStream_t st) {
   static bool attr[kMaxDevices] = {};
   const size_t smem = (size_t)STAGES * 3 * kDtTile * sizeof(T);
   auto k = decode_tail_tma_kernel<T, RGB, GRAY, EXTRA, STAGES, CTAS>;
   ensure_smem_attr(k, (int)smem, attr);
   const int cap = CTAS * sm_count();
   const int grid = total < cap ? total : cap;
-  k<<<grid, 256, smem, st>>>(p, rgb, gray, hw, tiles_per_img, total, gray_batch_stride, ex);
+  k<<<grid, 256, smem, st>>>(p, rgb, gray, hw, tiles_per_img, total, gray_batch_stride, tile_off, ex);
 }
 
 // pipeline shapes (stages x CTAs per SM) selectable through LDIFF_TUNE_DECODE_TAIL_TMA: smem in flight per SM is
@@ -412,22 +494,24 @@ template <typename T> struct TmaShapes;
 template <> struct TmaShapes<__nv_bfloat16> {
   template <bool RGB, bool GRAY, bool EXTRA>
   static void launch(int variant, const __nv_bfloat16* p, uint8_t* rgb, uint8_t* gray, int64_t hw, int tpi, int total,
-                     int64_t gbs, const TailExtras& ex, cudaStream_t st) {
+                     int64_t gbs, int toff, const TailExtras& ex, cudaStream_t st) {
     typedef __nv_bfloat16 T;
     switch (variant) {
-      case 2: launch_tma_one<T, RGB, GRAY, EXTRA, 3, 3>(p, rgb, gray, hw, tpi, total, gbs, ex, st); break;   // 216 KB
-      case 3: launch_tma_one<T, RGB, GRAY, EXTRA, 2, 4>(p, rgb, gray, hw, tpi, total, gbs, ex, st); break;   // 192 KB
-      case 4: launch_tma_one<T, RGB, GRAY, EXTRA, 2, 3>(p, rgb, gray, hw, tpi, total, gbs, ex, st); break;   // 144 KB
-      default: launch_tma_one<T, RGB, GRAY, EXTRA, 4, 2>(p, rgb, gray, hw, tpi, total, gbs, ex, st); break;  // 192 KB
+      case 2: launch_tma_one<T, RGB, GRAY, EXTRA, 3, 3>(p, rgb, gray, hw, tpi, total, gbs, toff, ex, st); break;   // 216 KB
+      case 3: launch_tma_one<T, RGB, GRAY, EXTRA, 2, 4>(p, rgb, gray, hw, tpi, total, gbs, toff, ex, st); break;   // 192 KB
+      case 4: launch_tma_one<T, RGB, GRAY, EXTRA, 2, 3>(p, rgb, gray, hw, tpi, total, gbs, toff, ex, st); break;   // 144 KB
+      case 5: launch_tma_one<T, RGB, GRAY, EXTRA, 3, 2>(p, rgb, gray, hw, tpi, total, gbs, toff, ex, st); break;   // 144 KB
+      case 6: launch_tma_one<T, RGB, GRAY, EXTRA, 2, 2>(p, rgb, gray, hw, tpi, total, gbs, toff, ex, st); break;   //  96 KB
+      default: launch_tma_one<T, RGB, GRAY, EXTRA, 4, 2>(p, rgb, gray, hw, tpi, total, gbs, toff, ex, st); break;  // 192 KB
     }
   }
 };
 template <> struct TmaShapes<float> {
   template <bool RGB, bool GRAY, bool EXTRA>
   static void launch(int variant, const float* p, uint8_t* rgb, uint8_t* gray, int64_t hw, int tpi, int total,
-                     int64_t gbs, const TailExtras& ex, cudaStream_t st) {
-    if (variant == 2 || variant == 3) launch_tma_one<float, RGB, GRAY, EXTRA, 2, 2>(p, rgb, gray, hw, tpi, total, gbs, ex, st);
-    else launch_tma_one<float, RGB, GRAY, EXTRA, 4, 1>(p, rgb, gray, hw, tpi, total, gbs, ex, st);
+                     int64_t gbs, int toff, const TailExtras& ex, cudaStream_t st) {
+    if (variant == 2 || variant == 3) launch_tma_one<float, RGB, GRAY, EXTRA, 2, 2>(p, rgb, gray, hw, tpi, total, gbs, toff, ex, st);
+    else launch_tma_one<float, RGB, GRAY, EXTRA, 4, 1>(p, rgb, gray, hw, tpi, total, gbs, toff, ex, st);
   }
 };
 
@@ -443,17 +527,27 @@ static int launch_decode_tail(const void* img, uint8_t* rgb, uint8_t* gray, int 
   const TailExtras ex = extra ? *exp : TailExtras{};
   const int tma = tune_get(LDIFF_TUNE_DECODE_TAIL_TMA);
   if (vec_ok && !na.out && (hw % kDtTile) == 0 && tma > 0 && (int64_t)B * (hw / kDtTile) <= 0x7fffffff) {
-    const int tiles_per_img = (int)(hw / kDtTile), total = B * tiles_per_img;
+    // extras: shift the tiles of an image by half a tile's rows (whole tiles of >= 16 rows need no shift) so that
+    // rows 16e+7 and 16e+8 always share a tile; needs a tile to be a whole, power-of-two number of rows
+    const int tile_rows = (W > 0 && kDtTile % W == 0) ? kDtTile / W : 0;
+    int tile_off = 0;
+    bool smem_extras = extra && tile_rows >= 2 && (tile_rows & (tile_rows - 1)) == 0;
+    if (smem_extras) tile_off = ((tile_rows / 2) % 8) * W;
+    if (extra && !smem_extras) goto reg_path;          // odd geometry: the register-staged kernel re-reads the footprints
+    {
+    const int tiles_per_img = (int)(hw / kDtTile) + (tile_off ? 1 : 0), total = B * tiles_per_img;
     const T* p = (const T*)img;
 #define DTT(R, G, E) TmaShapes<T>::template launch<R, G, E>(tma, p, rgb, gray, hw, tiles_per_img, total, \
-                                                            gray_batch_stride, ex, st)
+                                                            gray_batch_stride, tile_off, ex, st)
     if (extra) { if (rgb) DTT(true, true, true); else DTT(false, true, true); }
     else if (rgb && gray) DTT(true, true, false);
     else if (gray) DTT(false, true, false);
     else DTT(true, false, false);
 #undef DTT
     return check_launch();
+    }
   }
+reg_path:
   if (vec_ok) {
     if ((hw >> 4) > 0x7fffffff / 2 || B > 65535) return LDIFF_EUNSUPPORTED;
     const int gpi = (int)(hw >> 4);

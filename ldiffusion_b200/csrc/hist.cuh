@@ -132,6 +132,16 @@ struct BlockHist {
       for (int k = 0; k < 4; ++k) pixel((pw >> (8 * k)) & 0xffu, (gw >> (8 * k)) & 0xffu);
     }
   }
+  // 4 packed pixels whose predictions are known to be < K (a fused producer that emits them itself): no range check
+  __device__ __forceinline__ void word_trusted(uint32_t pw, uint32_t gw) {
+    static_assert(SMALLK, "byte-sized bins only");
+    const uint32_t gm = (bytes_ge(gw, K) >> 7) * 0xffu;               // 0xff where gt >= K
+    const uint32_t bins = ((gw & ~gm) | (k4 & gm)) * K + pw;
+    atomicAdd(my + (bins & 0xffu) * R, 1u);
+    atomicAdd(my + ((bins >> 8) & 0xffu) * R, 1u);
+    atomicAdd(my + ((bins >> 16) & 0xffu) * R, 1u);
+    atomicAdd(my + (bins >> 24) * R, 1u);
+  }
   // after a __syncthreads(): fold the replicas, one 64-bit global atomic per non-empty bin.  wrap32: the
   // block used move(), so a replica may hold a count "below zero" that another replica compensates; the
   // fold is then taken modulo 2^32 (a block never owns 2^32 pixels of one bin in that mode)

@@ -33,8 +33,10 @@ namespace ldiff {
 // class word of the row loop meets the gt word in registers; uncertain pixels are entered as class 0 and
 // moved to their resolved class by the epilogue), PUSH: with the NVLink peer push as the kernel's tail.
 constexpr int kEnvSegs = 7;        // segments per column and band (byte 7 of the packed vectors stays 0)
-constexpr int kEnvSrcW = 72;       // source columns a block stages in shared memory
-constexpr int kEnvRows = 127;      // rows per band (start rows are bytes; 0xff = "no further segment")
+constexpr int kEnvSrcW = 40;       // source columns a block stages in shared memory
+constexpr int kEnvRows = 127;
+constexpr int kEnvThreads = 128;   // threads per block (128 x 2 columns: twice the blocks of a 256-thread tiling, an
+                                   // even spread over the 148 SMs: 512 blocks were 3.46 per SM, i.e. 4 on some, 3 on others)      // rows per band (start rows are bytes; 0xff = "no further segment")
 
 // byte `sel & 7` of {hi, lo} in byte 0 (selector nibbles 1..3 = 7: the always-zero top byte of hi) — the raw PRMT;
 // __byte_perm would mask the selector first
@@ -51,15 +53,21 @@ __device__ __forceinline__ float rcp_approx(float x) {
 }
 
 template <int K, int COLS, bool HIST, bool PUSH>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(kEnvThreads, 1024 / kEnvThreads)   // 64 registers
 lift_argmax_env_kernel(const float* __restrict__ logits, uint8_t* __restrict__ mask, const uint8_t* __restrict__ gt,
                        unsigned long long* __restrict__ C, AxisH ay, AxisH ax, int nxb, int B,
                        int* __restrict__ status, XchgPush px) {
   __shared__ float2 s_l[kBand];
   __shared__ float s_src[2 * K * kEnvSrcW];
-  __shared__ uint32_t s_q[8][kQueue];
-  __shared__ int s_qn[8];
+  __shared__ uint32_t s_q[kEnvThreads / 32][kQueue];
+  __shared__ int s_qn[kEnvThreads / 32];
+  __shared__ int s_y[2];
   __shared__ uint32_t s_hist[HIST ? (K + 1) * K * 32 : 1];
+  // the band's ground-truth tile, fetched with cp.async at the start of the item and read by the row loop long
+  // after it has landed (a global load per row put ~7 us of exposed latency into the histogram form)
+  constexpr int kGtRows = (HIST && K <= 12) ? 32 : 1;    // (the 1.5x taller first band reads gt from global)
+  constexpr int kRowBytes = kEnvThreads * COLS;
+  __shared__ __align__(16) uint8_t s_gt[kGtRows * kRowBytes];
   __shared__ unsigned long long s_step;
   BlockHist<32, true> h;
   if (HIST) h.init(s_hist, K);
@@ -79,27 +87,45 @@ lift_argmax_env_kernel(const float* __restrict__ logits, uint8_t* __restrict__ m
   for (int item = blockIdx.x; item < items; item += gridDim.x) {
     const int bx = item % nxb, rest = item / nxb;
     const int iy = rest % ay.in, b = rest / ay.in;
-    const int Y0 = first_row(iy);
-    const int Y1 = (iy + 1 >= ay.in) ? ay.out : first_row(iy + 1);
-    __syncthreads();                                     // previous item's epilogue has read s_l / s_src / s_q
+    __syncthreads();                                     // previous item's epilogue has read s_l / s_src / s_q / s_y
+    if (threadIdx.x < 2)                                 // the band's first and one-past-last output row
+      s_y[threadIdx.x] = (threadIdx.x == 1 && iy + 1 >= ay.in) ? ay.out : first_row(iy + (int)threadIdx.x);
+    if (threadIdx.x < kEnvThreads / 32) s_qn[threadIdx.x] = 0;
+    __syncthreads();
+    const int Y0 = s_y[0], Y1 = s_y[1];
     if (Y0 >= Y1) continue;                              // (block-uniform)
-    if (threadIdx.x < 8) s_qn[threadIdx.x] = 0;
-    if (threadIdx.x < Y1 - Y0) {
-      const TapH t = tap(ay, Y0 + threadIdx.x);
-      s_l[threadIdx.x] = make_float2(t.l0, t.l1);
+    for (int i = threadIdx.x; i < Y1 - Y0; i += kEnvThreads) {
+      const TapH t = tap(ay, Y0 + i);
+      s_l[i] = make_float2(t.l0, t.l1);
+    }
+    bool gt_staged = false;
+    if (HIST && kGtRows > 1) {
+      const uint8_t* g0 = gt + ((int64_t)b * ay.out + Y0) * ax.out + bx * kRowBytes;
+      gt_staged = (Y1 - Y0) <= kGtRows && (kRowBytes % 16) == 0 && (ax.out % 16) == 0 &&
+                  (reinterpret_cast<uintptr_t>(gt) & 15u) == 0 && (bx + 1) * kRowBytes <= ax.out;
+      if (gt_staged) {
+        constexpr int kChunks = kRowBytes / 16 > 0 ? kRowBytes / 16 : 1;
+        for (int i = threadIdx.x; i < (Y1 - Y0) * kChunks; i += kEnvThreads) {
+          const int r = i / kChunks, ch = i - r * kChunks;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(
+                           s_gt + r * kRowBytes + ch * 16)), "l"(g0 + (int64_t)r * ax.out + ch * 16) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
     }
     const int i0 = min(iy, ay.in - 1), i1 = min(iy + 1, ay.in - 1);   // the band's source row pair
     const float* lb = logits + (int64_t)b * K * plane;
-    // stage the two source rows of every class for this block's columns
-    const int xfirst = bx * 256 * COLS, xlast = min(xfirst + 256 * COLS, ax.out) - 1;
+    // stage the two source rows of every class for this block's columns: warp w takes (row, class) pairs
+    // w, w + 8, ..., lane = source column (no index divisions)
+    const int xfirst = bx * kEnvThreads * COLS, xlast = min(xfirst + kEnvThreads * COLS, ax.out) - 1;
     const int c_lo = tap(ax, xfirst).i0, c_hi = tap(ax, xlast).i1;
     const int ncol = c_hi - c_lo + 1;
     const bool staged = ncol <= kEnvSrcW;
     if (staged) {
-      for (int i = threadIdx.x; i < 2 * K * ncol; i += blockDim.x) {
-        const int j = i % ncol, rk = i / ncol;           // rk = rowsel * K + k
-        const int k = rk % K, rs = rk / K;
-        s_src[i] = __ldg(lb + k * plane + (rs ? i1 : i0) * ax.in + c_lo + j);
+      for (int rk = warp_in_block; rk < 2 * K; rk += kEnvThreads / 32) {
+        const int rs = rk >= K ? 1 : 0, k = rk - rs * K;
+        const float* row = lb + k * plane + (rs ? i1 : i0) * ax.in + c_lo;
+        for (int j = (int)(threadIdx.x & 31); j < ncol; j += 32) s_src[rk * ncol + j] = __ldg(row + j);
       }
     }
     const int kstride = staged ? ncol : plane;
@@ -122,8 +148,8 @@ lift_argmax_env_kernel(const float* __restrict__ logits, uint8_t* __restrict__ m
 #pragma unroll
     for (int c = 0; c < COLS; ++c) {
       slo[c] = 0xffffffffu; shi[c] = 0x00ffffffu; clo[c] = 0u; chi[c] = 0u;
-      if (nrow > 0) {
-        const TapH tx = tap(ax, x0 + c);
+      {                                                  // (every lane, active or not: the sweep loop votes warp-wide)
+        const TapH tx = tap(ax, min(x0 + c, ax.out - 1));
         // classes in pairs for the packed fp32x2 pipe (FFMA2 / FADD2 / FMUL2: IEEE per lane); an odd K is padded
         // with a flat line far below every real logit.  dl: the slopes once more, dynamically indexed (local)
         constexpr int KP = (K + 1) / 2;
@@ -152,7 +178,10 @@ lift_argmax_env_kernel(const float* __restrict__ logits, uint8_t* __restrict__ m
         const bool sane = M < 1.0e29f;                   // (false for NaN / Inf / absurd logits: no fast path at all)
         int nseg = 0, r = 0;
         bool last_unc = false;
-        while (r < nrow) {
+        // warp-uniform trip count (every lane stays until the slowest column of the warp is done): the code behind
+        // the loop then runs converged — a per-lane `while (r < nrow)` left the warp split for the rest of the kernel
+        while (__any_sync(0xffffffffu, r < nrow)) {
+          if (r >= nrow) continue;
           const float l = s_l[r].y;
           const float2 l2 = make_float2(l, l);
           float2 v2[KP];
@@ -221,12 +250,13 @@ lift_argmax_env_kernel(const float* __restrict__ logits, uint8_t* __restrict__ m
           r = rend;
         }
       }
-      // lanes leave the sweep after different numbers of segments: bring the warp back together before the next
-      // column's set-up / the row loop (without this the tail of the kernel ran at ~11 of 32 lanes: ncu, r2)
-      __syncwarp();
     }
 
     // ---- row loop: replay the segments; 4 instructions per pixel + the packed store (+ histogram)
+    if (HIST && kGtRows > 1) {                           // (block-uniform)
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      __syncthreads();
+    }
     {
       uint32_t sel[COLS], nxt[COLS], cur[COLS];
 #pragma unroll
@@ -236,10 +266,40 @@ lift_argmax_env_kernel(const float* __restrict__ logits, uint8_t* __restrict__ m
         cur[c] = pick_byte(clo[c], chi[c], sel[c]);
       }
       uint8_t* op = mask + ((int64_t)b * ay.out + Y0) * ax.out + x0;
-      const uint8_t* gp = HIST ? gt + ((int64_t)b * ay.out + Y0) * ax.out + x0 : nullptr;
-      uint32_t accp = 0, accg = 0;
-      int phase = 0;
-      for (int r = 0; r < nrow; ++r, op += ax.out) {
+      const uint8_t* gp = HIST ? (gt_staged ? s_gt + threadIdx.x * COLS : gt + ((int64_t)b * ay.out + Y0) * ax.out + x0)
+                               : nullptr;
+      const int gstep = gt_staged ? kRowBytes : ax.out;
+      // 4 / COLS rows per iteration: their packed classes and gt bytes form one 4-pixel histogram word
+      constexpr int RPW = 4 / COLS;
+      int r = 0;
+      for (; r + RPW <= nrow; r += RPW) {
+        uint32_t pk[RPW], gk[RPW];
+#pragma unroll
+        for (int q = 0; q < RPW; ++q) {
+          uint32_t packed = 0;
+#pragma unroll
+          for (int c = 0; c < COLS; ++c) {
+            if ((uint32_t)(r + q) >= nxt[c]) ++sel[c];
+            nxt[c] = pick_byte(slo[c], shi[c], sel[c]);
+            cur[c] = pick_byte(clo[c], chi[c], sel[c]);
+            packed |= cur[c] << (8 * c);
+          }
+          pk[q] = packed;
+          gk[q] = 0;
+          if (COLS == 1) { op[0] = (uint8_t)packed; if (HIST) gk[q] = gp[0]; }
+          else if (COLS == 2) { *reinterpret_cast<uint16_t*>(op) = (uint16_t)packed; if (HIST) gk[q] = *reinterpret_cast<const uint16_t*>(gp); }
+          else { *reinterpret_cast<uint32_t*>(op) = packed; if (HIST) gk[q] = *reinterpret_cast<const uint32_t*>(gp); }
+          op += ax.out;
+          if (HIST) gp += gstep;
+        }
+        if (HIST) {
+          if (COLS == 4) h.word_trusted(pk[0], gk[0]);
+          else if (COLS == 2) h.word_trusted(__byte_perm(pk[0], pk[RPW - 1], 0x5410), __byte_perm(gk[0], gk[RPW - 1], 0x5410));
+          else h.word_trusted(__byte_perm(__byte_perm(pk[0], pk[1 % RPW], 0x0040), __byte_perm(pk[2 % RPW], pk[3 % RPW], 0x0040), 0x5410),
+                              __byte_perm(__byte_perm(gk[0], gk[1 % RPW], 0x0040), __byte_perm(gk[2 % RPW], gk[3 % RPW], 0x0040), 0x5410));
+        }
+      }
+      for (; r < nrow; ++r, op += ax.out) {              // the band's last (nrow mod RPW) rows
         uint32_t packed = 0;
 #pragma unroll
         for (int c = 0; c < COLS; ++c) {
@@ -248,19 +308,13 @@ lift_argmax_env_kernel(const float* __restrict__ logits, uint8_t* __restrict__ m
           cur[c] = pick_byte(clo[c], chi[c], sel[c]);
           packed |= cur[c] << (8 * c);
         }
-        uint32_t g = 0;
-        if (COLS == 1) { op[0] = (uint8_t)packed; if (HIST) g = gp[0]; }
-        else if (COLS == 2) { *reinterpret_cast<uint16_t*>(op) = (uint16_t)packed; if (HIST) g = *reinterpret_cast<const uint16_t*>(gp); }
-        else { *reinterpret_cast<uint32_t*>(op) = packed; if (HIST) g = *reinterpret_cast<const uint32_t*>(gp); }
-        if (HIST) {
-          gp += ax.out;
-          accp |= packed << (8 * COLS * phase);
-          accg |= g << (8 * COLS * phase);
-          if (++phase == 4 / COLS) { h.word(accp, accg); accp = accg = 0; phase = 0; }
+#pragma unroll
+        for (int c = 0; c < COLS; ++c) {
+          op[c] = (uint8_t)(packed >> (8 * c));
+          if (HIST) h.pixel((packed >> (8 * c)) & 0xffu, gp[c]);
         }
+        if (HIST) gp += gstep;
       }
-      if (HIST)
-        for (int i = 0; i < phase * COLS; ++i) h.pixel((accp >> (8 * i)) & 0xffu, (accg >> (8 * i)) & 0xffu);
     }
 
     // ---- cold epilogue: the warp's queued pixels, spread over its lanes, through the pinned softmax
@@ -317,12 +371,12 @@ template <int K, int COLS>
 static void launch_env_k(const float* logits, uint8_t* mask, const uint8_t* gt, unsigned long long* C, AxisH ay,
                          AxisH ax, int nxb, int B, int grid, int* status, const XchgPush* px, cudaStream_t st) {
   if (px)
-    lift_argmax_env_kernel<K, COLS, true, true><<<grid, 256, 0, st>>>(logits, mask, gt, C, ay, ax, nxb, B, status, *px);
+    lift_argmax_env_kernel<K, COLS, true, true><<<grid, kEnvThreads, 0, st>>>(logits, mask, gt, C, ay, ax, nxb, B, status, *px);
   else if (gt)
-    lift_argmax_env_kernel<K, COLS, true, false><<<grid, 256, 0, st>>>(logits, mask, gt, C, ay, ax, nxb, B, status,
+    lift_argmax_env_kernel<K, COLS, true, false><<<grid, kEnvThreads, 0, st>>>(logits, mask, gt, C, ay, ax, nxb, B, status,
                                                                        XchgPush{});
   else
-    lift_argmax_env_kernel<K, COLS, false, false><<<grid, 256, 0, st>>>(logits, mask, nullptr, nullptr, ay, ax, nxb, B,
+    lift_argmax_env_kernel<K, COLS, false, false><<<grid, kEnvThreads, 0, st>>>(logits, mask, nullptr, nullptr, ay, ax, nxb, B,
                                                                         status, XchgPush{});
 }
 
@@ -335,13 +389,14 @@ bool lift_argmax_env_ok(int K, int h, int H) {
 int launch_lift_argmax_env(const float* logits, uint8_t* mask, const uint8_t* gt, int64_t* C, int B, int K, int h,
                            int w, int H, int W, int* status, const XchgPush* px, cudaStream_t st) {
   AxisH ay{(float)h / (float)H, h, H}, ax{(float)w / (float)W, w, W};
-  const bool two = (W % 2) == 0 && (reinterpret_cast<uintptr_t>(mask) & 1u) == 0 &&
-                   (reinterpret_cast<uintptr_t>(gt) & 1u) == 0;
+  // two columns per thread (16-bit stores) when the rows allow it.  (Four columns per thread measured slower:
+  // 30.3 vs 24.8 us at the bench shape — half the warps, and the kernel lives on latency hiding.)
+  const bool two = (W % 2) == 0 && ((reinterpret_cast<uintptr_t>(mask) | reinterpret_cast<uintptr_t>(gt)) & 1u) == 0;
   const int cols = two ? 2 : 1;
-  const int nxb = (W / cols + 255) / 256;
+  const int nxb = (W / cols + kEnvThreads - 1) / kEnvThreads;
   const int64_t items = (int64_t)nxb * h * B;
   if (items > 0x7fffffff) return LDIFF_EUNSUPPORTED;
-  const int64_t cap = (int64_t)sm_count() * 8;           // whole bands per block; a block walks several on big batches
+  const int64_t cap = (int64_t)sm_count() * (2048 / kEnvThreads);   // whole bands per block; a block walks several on big batches
   const int grid = (int)(items < cap ? items : cap);
   unsigned long long* Cu = reinterpret_cast<unsigned long long*>(C);
   switch (K) {

@@ -106,6 +106,12 @@ class HotPath:
         # keeps round 1's separate launches (A/B timing, and the reference point of the equivalence tests)
         self.fused = (os.environ.get("LDIFF_PASS_FUSED", "1") == "1" and height % 16 == 0 and width % 16 == 0
                       and tuple(feat_size) == (height // 16, width // 16) and num_classes <= 15)
+        # the tissue chain's histogram: fused into lift+argmax (one launch less, 8 MB less traffic) or its own launch
+        # (measured at the bench shape: 118 us per pass with the separate launch against 121 us fused — the histogram's
+        # ~8 instructions per pixel land on an issue-bound kernel, while the stand-alone histogram is latency-bound
+        # and overlaps the other chains; the fused entry point stays in the library for callers without that overlap)
+        self.tissue_hist_fused = os.environ.get("LDIFF_PASS_TISSUE_HIST_FUSED", "0") == "1"
+        self.decode_streams = max(1, min(num_steps, int(os.environ.get("LDIFF_DECODE_STREAMS", "1"))))
 
     def attach_exchange(self, exchange, deferred: bool = True):
         """Multi-GPU: fuse the cross-rank sum of the two confusion matrices into the pass
@@ -130,7 +136,7 @@ class HotPath:
     def launches_per_pass(self) -> int:
         xr = 1 if self.exchange is not None else 0                         # the exchange's one-block reduce
         if self.fused:                                                     # sampler n, decode n, lifts 2, tissue 2, cell 2
-            return 2 * self.n + 2 + 2 + 2 + xr
+            return 2 * self.n + 2 + 2 + 2 + xr + (0 if self.tissue_hist_fused else 1)
         return 4 * self.n + 1 + 3 + 2 + 2 + 2 + xr
 
     def _confusion(self, mask, gt, channel):
@@ -157,7 +163,7 @@ class HotPath:
             for s in side:
                 s.wait_stream(cur)
         else:
-            side = [cur] * 5
+            side = [cur] * (4 + self.decode_streams)
         with torch.cuda.stream(side[0]), _nvtx("ldiff.sampler"):
             self._chain_sampler(inp)
             if self.exchange is not None and self.exchange_deferred and self._unreduced > 0:
@@ -171,8 +177,9 @@ class HotPath:
             self._chain_tissue(inp)
         with torch.cuda.stream(side[3]), _nvtx("ldiff.cell"):
             self._chain_cell(inp)
-        with torch.cuda.stream(side[4]), _nvtx("ldiff.decode_tails"):      # the bandwidth-heavy chain
-            self._chain_decode(inp)
+        for j in range(self.decode_streams):                               # the bandwidth-heavy chain(s)
+            with torch.cuda.stream(side[4 + j]), _nvtx("ldiff.decode_tails"):
+                self._chain_decode(inp, j)
         if concurrent:
             for s in side:
                 cur.wait_stream(s)
@@ -194,7 +201,7 @@ class HotPath:
         if st is None:
             env = os.environ.get("LDIFF_SIDE_PRIOS")
             prios = [int(x) for x in env.split(",")] if env else list(self.CHAIN_PRIORITIES)
-            st = [torch.cuda.Stream(self.device, priority=prios[i]) for i in range(5)]
+            st = [torch.cuda.Stream(self.device, priority=prios[min(i, 4)]) for i in range(4 + self.decode_streams)]
             self._side = st
         return st
 
@@ -213,9 +220,12 @@ class HotPath:
                                     out=self.noisy[i])
                 x = sch.step(inp.eps[i], ts[i], x, out=self.lat[i]).prev_sample
 
-    def _chain_decode(self, inp):
+    def _chain_decode(self, inp, part: int = 0):
+        """Decode tails of the steps i = part (mod decode_streams).  The n tails have no data dependence on one
+        another (step i's image is step i's VAE output); spread over two streams, the start-up and drain of one
+        tail overlap the steady state of the other."""
         n = self.n
-        for i in range(n):
+        for i in range(part, n, self.decode_streams):
             last = i == n - 1
             if self.fused:
                 # the step's training-path feature (ldiffusion.py:240-247) and, on the last step, the label slot
@@ -228,7 +238,7 @@ class HotPath:
             else:
                 ops.decode_tail_gray(inp.decoded[i], want_rgb=False, rgb_out=self.rgb if last else None,
                                      gray_out=self.planes[:, i])
-        if not self.fused:
+        if not self.fused and part == (n - 1) % self.decode_streams:
             ops.copy_planes_u8(inp.gt, self.planes[:, n])                  # label slot of the pixel vectors
 
     def _chain_lifts(self, inp):
@@ -248,8 +258,12 @@ class HotPath:
     def _chain_tissue(self, inp):
         if self.fused:
             ops._head_logits(inp.head_feat, self.head_w, self.head_b, self.logits, self.C[0])   # also zeroes C[0]
-            ops.lift_argmax_hist(self.logits, (self.H, self.W), inp.gt, out=self.C[0], mask_out=self.mask_tissue,
-                                 exchange=self.exchange, channel=0)
+            if self.tissue_hist_fused:
+                ops.lift_argmax_hist(self.logits, (self.H, self.W), inp.gt, out=self.C[0], mask_out=self.mask_tissue,
+                                     exchange=self.exchange, channel=0)
+            else:
+                ops._lift_argmax(self.logits, self.mask_tissue)
+                self._confusion(self.mask_tissue, inp.gt, 0)
             return
         ops._head_logits(inp.head_feat, self.head_w, self.head_b, self.logits)
         ops._lift_argmax(self.logits, self.mask_tissue)
@@ -343,6 +357,50 @@ class HotPath:
                 "featcat": self.featcat, "label_small": self.label_small, "rgb_up": self.rgb_up,
                 "logits": self.logits, "mask_tissue": self.mask_tissue, "mask_cell": self.mask_cell,
                 "confusion": self.C}
+
+
+class HotPathRing:
+    """``n_in_flight`` passes of consecutive batches in flight at once: each slot is a ``HotPath`` with its own
+    buffers and chain streams, enqueued on its own stream, so the tail of one pass (the last classifier kernels,
+    the join) overlaps the head of the next instead of leaving the machine half empty — a pass is five chains of
+    kernels with different bottlenecks (HBM, issue, launch latency) and no single pass keeps all of them busy.
+    Measured at the bench shape (8 x 1024^2, K=11, 5 steps, bf16): 119 us per pass alone, 101 us with two in
+    flight, 99.5 us with three (tools/pass_overlap.py).  Results of pass i live in ``slot(i).results()`` until
+    pass i + n_in_flight is enqueued."""
+
+    def __init__(self, n_in_flight: int = 2, *args, **kwargs):
+        if n_in_flight < 1:
+            raise ValueError("n_in_flight must be >= 1")
+        self.slots = [HotPath(*args, **kwargs) for _ in range(n_in_flight)]
+        dev = self.slots[0].device
+        self.streams = [torch.cuda.Stream(dev) for _ in range(n_in_flight)]
+        self.device = dev
+
+    def __len__(self):
+        return len(self.slots)
+
+    def slot(self, i: int) -> "HotPath":
+        return self.slots[i % len(self.slots)]
+
+    def stream(self, i: int) -> torch.cuda.Stream:
+        return self.streams[i % len(self.streams)]
+
+    def fork(self):
+        """Make every slot's stream wait for the caller's current stream (call before the first ``run``)."""
+        cur = torch.cuda.current_stream(self.device)
+        for s in self.streams:
+            s.wait_stream(cur)
+
+    def run(self, i: int, inp: HotPathInputs):
+        """Enqueue pass i on its slot's stream (graph-capturable per slot)."""
+        with torch.cuda.stream(self.stream(i)):
+            self.slot(i).run(inp)
+
+    def join(self):
+        """Make the caller's current stream wait for every slot."""
+        cur = torch.cuda.current_stream(self.device)
+        for s in self.streams:
+            cur.wait_stream(s)
 
 
 def synth_inputs(batch, height, width, num_classes, num_steps=5, dtype=torch.bfloat16, device="cpu",

@@ -30,7 +30,7 @@ def tune():
     from ldiffusion_b200 import _cabi
     lib = _cabi.lib()
     yield lambda knob, value: lib.ldiff_tune(knob, value)
-    for knob, default in ((_cabi.TUNE_ARGMAX_VARIANT, 0), (_cabi.TUNE_DECODE_TAIL_SMS, 0), (_cabi.TUNE_DECODE_TAIL_TMA, 1)):
+    for knob, default in ((_cabi.TUNE_ARGMAX_VARIANT, 0), (_cabi.TUNE_DECODE_TAIL_SMS, 0), (_cabi.TUNE_DECODE_TAIL_TMA, 6)):
         lib.ldiff_tune(knob, default)
 
 
@@ -83,7 +83,7 @@ def test_scheduler_step_then_noise_loop_matches_oracle():
 
 @pytest.mark.parametrize("shape", [(2, 3, 64, 64), (1, 3, 48, 80), (2, 3, 1024, 1024), (1, 3, 128, 32)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("tma", [0, 1])
+@pytest.mark.parametrize("tma", [0, 1, 4, 6])
 def test_decode_tail_fused_equals_separate_launches(tune, shape, dtype, tma):
     from ldiffusion_b200 import _cabi
     ops = _ops()
@@ -219,8 +219,11 @@ def test_lift_argmax_tall_bands(h, H):
 
 
 @pytest.mark.parametrize("case", sorted(CASES))
-def test_lift_argmax_hist_equals_separate_launches(case):
+@pytest.mark.parametrize("variant", [0])
+def test_lift_argmax_hist_equals_separate_launches(tune, case, variant):
+    from ldiffusion_b200 import _cabi
     ops = _ops()
+    tune(_cabi.TUNE_ARGMAX_VARIANT, variant)
     logits = CASES[case]()
     B, K, h, w = logits.shape
     size = (h * 32, w * 32)
@@ -228,7 +231,8 @@ def test_lift_argmax_hist_equals_separate_launches(case):
     gt = rng.integers(0, K + 2, (B,) + size).astype(np.uint8)
     gt[gt >= K] = 255
     ld, gd = torch.from_numpy(logits).cuda(), torch.from_numpy(gt).cuda()
-    mask, C = ops.lift_argmax_hist(ld, size, gd)
+    poisoned = torch.full((B,) + size, 0xEE, dtype=torch.uint8, device="cuda")
+    mask, C = ops.lift_argmax_hist(ld, size, gd, mask_out=poisoned)
     want = ohead.lift_argmax_spec(logits, size)
     assert np.array_equal(mask.cpu().numpy(), want)
     assert np.array_equal(C.cpu().numpy(), omet.confusion_matrix(want, gt, K))
@@ -290,17 +294,71 @@ def test_fused_pass_equals_unfused_pass(dtype):
                           for f in (host.latents, host.eps, host.decoded, host.head_feat, host.inst_map,
                                     host.inst_feats, host.gt)])
     outs = []
-    for fused in (True, False):
+    for fused, tissue_fused in ((True, False), (True, True), (False, False)):
         hp = HotPath(dtype=dtype, device="cuda", head_hw=(8, 8), feat_size=(16, 16), seed=5, **cfg)
-        assert hp.fused
-        hp.fused = fused
+        assert hp.fused and not hp.tissue_hist_fused
+        hp.fused, hp.tissue_hist_fused = fused, tissue_fused
         c0 = _cabi.launch_count()
         hp.run(dev)
         assert _cabi.launch_count() - c0 == hp.launches_per_pass()
         torch.cuda.synchronize()
         outs.append({k: ([t.clone() for t in v] if isinstance(v, list) else v.clone()) for k, v in hp.results().items()})
-    assert HotPath(dtype=dtype, device="cuda", head_hw=(8, 8), feat_size=(16, 16), **cfg).launches_per_pass() == 16
-    for k in outs[0]:
-        a, b = outs[0][k], outs[1][k]
-        for x, y in zip(a if isinstance(a, list) else [a], b if isinstance(b, list) else [b]):
-            assert torch.equal(x, y), k
+    assert HotPath(dtype=dtype, device="cuda", head_hw=(8, 8), feat_size=(16, 16), **cfg).launches_per_pass() == 17
+    for other in outs[1:]:
+        for k in outs[0]:
+            a, b = outs[0][k], other[k]
+            for x, y in zip(a if isinstance(a, list) else [a], b if isinstance(b, list) else [b]):
+                assert torch.equal(x, y), k
+
+
+def test_ring_of_passes_in_flight_equals_single_passes():
+    """HotPathRing: three batches through two slots (graph per slot, replayed on the slots' streams) give the
+    same results as one HotPath run batch after batch."""
+    from ldiffusion_b200.pipeline import HotPath, HotPathInputs, HotPathRing, synth_inputs
+    cfg = dict(batch=2, height=256, width=256, num_classes=11, num_steps=5, n_instances=40)
+    kw = dict(dtype=torch.bfloat16, device="cuda", head_hw=(8, 8), feat_size=(16, 16), seed=5, **cfg)
+    devs = []
+    for seed in (31, 32, 33, 34):
+        host = synth_inputs(2, 256, 256, 11, 5, dtype=torch.bfloat16, device="cpu", head_hw=(8, 8), n_instances=40, seed=seed)
+        devs.append(HotPathInputs(*[([t.cuda() for t in f] if isinstance(f, list) else f.cuda())
+                                    for f in (host.latents, host.eps, host.decoded, host.head_feat, host.inst_map,
+                                              host.inst_feats, host.gt)]))
+    single = HotPath(**kw)
+    want = []
+    for d in devs:
+        single.run(d)
+        torch.cuda.synchronize()
+        want.append({k: ([t.clone() for t in v] if isinstance(v, list) else v.clone()) for k, v in single.results().items()})
+    ring = HotPathRing(2, **kw)
+    ring.fork()
+    for i in range(2):                                      # warm-up outside capture (side streams, first launches)
+        ring.run(i, devs[i])
+    torch.cuda.synchronize()
+    graphs = []
+    for i in range(2):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=ring.stream(i)):
+            ring.slot(i).run(devs[i])
+        graphs.append(g)
+    for v in ring.slot(0).results().values():               # scribble, then replay both slots concurrently
+        for t_ in (v if isinstance(v, list) else [v]):
+            t_.zero_()
+    for i in range(2):
+        with torch.cuda.stream(ring.stream(i)):
+            graphs[i].replay()
+    ring.join()
+    torch.cuda.synchronize()
+    for i in range(2):
+        got = ring.slot(i).results()
+        for k in want[i]:
+            for x, y in zip(got[k] if isinstance(got[k], list) else [got[k]],
+                            want[i][k] if isinstance(want[i][k], list) else [want[i][k]]):
+                assert torch.equal(x, y), (i, k)
+    for i in (2, 3):                                        # eager passes through the ring: slot reuse
+        ring.run(i, devs[i])
+    ring.join()
+    torch.cuda.synchronize()
+    for i in (2, 3):
+        got = ring.slot(i).results()
+        for k in ("mask_tissue", "mask_cell", "confusion", "pixel_planes", "featcat", "latents"):
+            assert torch.equal(got[k], want[i][k]), (i, k)

@@ -16,7 +16,7 @@ def tune():
     from ldiffusion_b200 import _cabi
     lib = _cabi.lib()
     yield lambda knob, value: lib.ldiff_tune(knob, value)
-    for knob, default in ((_cabi.TUNE_ARGMAX_VARIANT, 0), (_cabi.TUNE_DECODE_TAIL_SMS, 0), (_cabi.TUNE_DECODE_TAIL_TMA, 1)):
+    for knob, default in ((_cabi.TUNE_ARGMAX_VARIANT, 0), (_cabi.TUNE_DECODE_TAIL_SMS, 0), (_cabi.TUNE_DECODE_TAIL_TMA, 6)):
         lib.ldiff_tune(knob, default)
 
 
@@ -31,7 +31,7 @@ def test_decode_tail_tma_bit_exact(tune, shape, want_rgb, dtype):
     img = torch.empty(shape).uniform_(-1.3, 1.3, generator=g).to(dtype)
     tune(_cabi.TUNE_DECODE_TAIL_TMA, 0)
     rgb0, gray0 = ops.decode_tail_gray(img.cuda(), want_rgb=want_rgb)
-    for variant in (1, 2, 3, 4):
+    for variant in (1, 2, 3, 4, 5, 6):
         tune(_cabi.TUNE_DECODE_TAIL_TMA, variant)
         rgb1, gray1 = ops.decode_tail_gray(img.cuda(), want_rgb=want_rgb)
         torch.cuda.synchronize()
@@ -56,7 +56,8 @@ def test_lift_argmax_variants_bit_exact(tune, variant):
     for K, shape, size in ((11, (2, 32, 32), (1024, 1024)), (6, (1, 16, 16), (512, 512)), (7, (3, 8, 8), (128, 96)),
                            (15, (1, 8, 8), (64, 66)), (3, (1, 5, 7), (45, 63))):
         logits = torch.randn((shape[0], K) + shape[1:], generator=g)
-        got = ops.lift_argmax(logits.cuda(), size)
+        got = torch.full((shape[0],) + size, 0xEE, dtype=torch.uint8, device="cuda")   # poisoned: a kernel that skips
+        ops._lift_argmax(logits.cuda(), got)                                            # pixels cannot pass on stale data
         assert np.array_equal(got.cpu().numpy(), ohead.lift_argmax_spec(logits.numpy(), size)), (K, shape, size)
 
 

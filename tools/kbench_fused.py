@@ -30,9 +30,11 @@ for variant in (4, 0):
     lib.ldiff_tune(_cabi.TUNE_ARGMAX_VARIANT, variant)
     for nm, lg in (("random", logits), ("smooth", smooth)):
         line(f"lift_argmax variant={variant} {nm}", timeit(lambda i: ops._lift_argmax(lg, mask), 1), px)
+for variant in (0,):
+  lib.ldiff_tune(_cabi.TUNE_ARGMAX_VARIANT, variant)
+  for nm, lg in (("random", logits), ("smooth", smooth)):
+    line(f"lift_argmax_hist variant={variant} {nm}", timeit(lambda i: ops.lift_argmax_hist(lg, (H, W), gt, out=C, mask_out=mask), 1), 2 * px)
 lib.ldiff_tune(_cabi.TUNE_ARGMAX_VARIANT, 0)
-for nm, lg in (("random", logits), ("smooth", smooth)):
-    line(f"lift_argmax_hist {nm}", timeit(lambda i: ops.lift_argmax_hist(lg, (H, W), gt, out=C, mask_out=mask), 1), 2 * px)
 line("confusion_hist (stand-alone)", timeit(lambda i: ops.confusion_hist(mask.view(-1), gt.view(-1), K, out=C), 1), 2 * px)
 
 # paint (+ hist)

@@ -30,11 +30,20 @@ DEFAULT = [
 ]
 configs = [ast.literal_eval(a) for a in sys.argv[1:]] or DEFAULT
 ref = None
-for label, fused, tma, amax, prios in configs:
+for cfg in configs:
+    label, fused, tma, amax, prios = cfg[:5]
+    dstreams = cfg[5] if len(cfg) > 5 else 1
+    skip = cfg[6] if len(cfg) > 6 else ()                  # chains left out (where does the pass's time go?)
     lib.ldiff_tune(_cabi.TUNE_DECODE_TAIL_TMA, tma)
     lib.ldiff_tune(_cabi.TUNE_ARGMAX_VARIANT, amax)
     hp = HotPath(B, H, W, K, N, dtype=torch.bfloat16, device=dev, n_instances=800)
     hp.fused = hp.fused and fused
+    hp.decode_streams = dstreams
+    if len(cfg) > 7:
+        for k, v in cfg[7].items():                          # extra HotPath attributes, e.g. {'tissue_hist_fused': False}
+            setattr(hp, k, v)
+    for name in skip:
+        setattr(hp, "_chain_" + name, lambda *a, **k: None)
     if prios is not None:
         hp.CHAIN_PRIORITIES = tuple(prios)
     st = torch.cuda.Stream()
@@ -62,7 +71,9 @@ for label, fused, tma, amax, prios in configs:
     ops.check_status(dev)
     out = {k: ([t.clone() for t in v] if isinstance(v, list) else v.clone()) for k, v in hp.results().items()}
     same = ""
-    if ref is None:
+    if skip:
+        pass
+    elif ref is None:
         ref = out
     else:
         same = "  results_equal=" + str(all(
