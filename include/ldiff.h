@@ -47,16 +47,19 @@ enum {
 enum { LDIFF_STATUS_PRED_RANGE = 1, LDIFF_STATUS_INST_RANGE = 2, LDIFF_STATUS_SW_INF = 4,
        LDIFF_STATUS_XCHG_TIMEOUT = 8, LDIFF_STATUS_LABEL_RANGE = 16 };
 
-/* Scheduling / variant knobs (no effect on results).  A value set here applies to the launches issued
- * after the call.  Before the first ldiff_tune of a knob its environment variable, else the default, applies.
+/* Scheduling / variant knobs (no effect on results, except LDIFF_TUNE_PHILOX_ROUNDS).  A value set here applies to
+ * the launches issued after the call.  Before the first ldiff_tune of a knob its environment variable, else the default, applies.
  *  LDIFF_TUNE_ARGMAX_VARIANT (env LDIFF_ARGMAX_VARIANT, default 0): ldiff_lift_argmax runs 0 = the envelope
  *    kernel, 4 / 5 = round 1's per-pixel evaluation kernel with 2 / 1 columns per thread (A/B timing);
  *  LDIFF_TUNE_DECODE_TAIL_SMS (env LDIFF_DT_SMS, default 0 = all): the register-staged decode tail sizes its
  *    one-wave grid for that many SMs;
  *  LDIFF_TUNE_DECODE_TAIL_TMA (env LDIFF_DT_TMA, default 6): 0 = register-staged decode tail, 1..6 = the
- *    bulk-TMA staged persistent kernel with (stages x CTAs/SM) = (4x2) / (3x3) / (2x4) / (2x3) / (3x2) / (2x2) for bf16. */
+ *    bulk-TMA staged persistent kernel with (stages x CTAs/SM) = (4x2) / (3x3) / (2x4) / (2x3) / (3x2) / (2x2) for bf16;
+ *  LDIFF_TUNE_PHILOX_ROUNDS (env LDIFF_PHILOX_ROUNDS, default 0 = 10): rounds of the Philox4x32 stream behind the
+ *    Laplace noise - THIS knob changes the random stream (not the distribution): 7 = the smallest round count that
+ *    passes BigCrush in the Philox paper, anything else = the published default of 10. */
 enum { LDIFF_TUNE_ARGMAX_VARIANT = 0, LDIFF_TUNE_DECODE_TAIL_SMS = 1, LDIFF_TUNE_DECODE_TAIL_TMA = 2,
-       LDIFF_TUNE_COUNT = 3 };
+       LDIFF_TUNE_PHILOX_ROUNDS = 3, LDIFF_TUNE_COUNT = 4 };
 int ldiff_tune(int knob, int value);
 
 int ldiff_abi_version(void);
@@ -71,8 +74,12 @@ int64_t ldiff_launch_count(void);
  * Exactly one source of randomness is used:
  *   noise_in != NULL : injected noise (parity mode; out = x + noise_in, one add)
  *   u_in     != NULL : injected uniforms in (-1,1)
- *   otherwise        : Philox4x32-10, key = seed, element i takes word i%4 of
- *                      counter offset + i/4 (restated in oracle/laplace.py)
+ *   otherwise        : Philox4x32-10 (LDIFF_TUNE_PHILOX_ROUNDS = 7: 7 rounds), key = seed.  fp32 storage: element i
+ *                      takes word i%4 of counter offset + i/4; bits [22:0] of the word are |u| (23 bits), bit 31 the
+ *                      sign.  bf16 storage: element i takes half-word i%8 of counter offset + i/8 (sign + 15-bit
+ *                      magnitude; the top magnitude cell is refined by a second 23-bit draw, so the exponential tail
+ *                      is not truncated).  Advancing offset by ceil(n/4) between calls never reuses a counter in
+ *                      either form.  Both streams are restated in oracle/laplace.py
  * noise_out (optional) receives the fp32/bf16 noise that was added. */
 int ldiff_laplace_qsample(const void* x, void* out, const void* noise_in, const void* u_in,
                           void* noise_out, float b, uint64_t seed, uint64_t offset,
@@ -286,6 +293,9 @@ int ldiff_xchg_destroy(void* handle);
 int ldiff_confusion_hist_push(const uint8_t* pred, const uint8_t* gt, const uint8_t* gt_lut,
                               int64_t* C, int64_t n, int K, void* xchg, int channel, int* status,
                               void* stream);
+/* stand-alone push of all channels at once (C int64 [channels][n_i64], e.g. the totals of a whole evaluation:
+ * the reference sums once per evaluation); counts as one push of every channel */
+int ldiff_xchg_push(void* xchg, const int64_t* C, void* stream);
 int ldiff_xchg_reduce(void* xchg, int64_t* out, int* status, void* stream);
 /* B planes of n bytes -> a strided slot (the label plane of the pixel vectors,
  * pixel_latent_vector.py:92); n and dst_stride multiples of 16 */

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libldiff_sm100.so")
 ABI_VERSION = 2
 
 F32, BF16, U8 = 0, 1, 2
-TUNE_ARGMAX_VARIANT, TUNE_DECODE_TAIL_SMS, TUNE_DECODE_TAIL_TMA = 0, 1, 2
+TUNE_ARGMAX_VARIANT, TUNE_DECODE_TAIL_SMS, TUNE_DECODE_TAIL_TMA, TUNE_PHILOX_ROUNDS = 0, 1, 2, 3
 STATUS_PRED_RANGE, STATUS_INST_RANGE, STATUS_SW_INF, STATUS_XCHG_TIMEOUT, STATUS_LABEL_RANGE = 1, 2, 4, 8, 16
 
 # name -> (restype, argtypes); mirrors include/ldiff.h one to one
@@ -72,6 +72,7 @@ SIGNATURES = {
     "ldiff_xchg_destroy": (c_int, [c_void_p]),
     "ldiff_confusion_hist_push": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int,
                                           c_void_p, c_void_p]),
+    "ldiff_xchg_push": (c_int, [c_void_p, c_void_p, c_void_p]),
     "ldiff_xchg_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "ldiff_labels_to_u8": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "ldiff_infonce_sample": (c_int, [c_void_p, c_int, c_int64, c_int, c_int, c_uint64, c_uint64, c_void_p, c_void_p,

@@ -26,9 +26,10 @@ int sm_count() {
 }
 
 // tuning knobs: -1 = not set yet (the environment variable, else the built-in default, is taken on first use)
-static int g_tune[LDIFF_TUNE_COUNT] = {-1, -1, -1};
-static const char* const kTuneEnv[LDIFF_TUNE_COUNT] = {"LDIFF_ARGMAX_VARIANT", "LDIFF_DT_SMS", "LDIFF_DT_TMA"};
-static const int kTuneDefault[LDIFF_TUNE_COUNT] = {0, 0, 6};
+static int g_tune[LDIFF_TUNE_COUNT] = {-1, -1, -1, -1};
+static const char* const kTuneEnv[LDIFF_TUNE_COUNT] = {"LDIFF_ARGMAX_VARIANT", "LDIFF_DT_SMS", "LDIFF_DT_TMA",
+                                                        "LDIFF_PHILOX_ROUNDS"};
+static const int kTuneDefault[LDIFF_TUNE_COUNT] = {0, 0, 6, 0};
 
 int tune_get(int knob) {
   int v = __atomic_load_n(&g_tune[knob], __ATOMIC_RELAXED);

@@ -187,6 +187,28 @@ xchg_reduce_kernel(XchgHeader* __restrict__ win, unsigned long long* __restrict_
   if (threadIdx.x == 0) win->reduced = want;
 }
 
+// Stand-alone push: every channel's finished matrix (C[channels][n], e.g. the totals of a whole evaluation) goes to
+// every rank's window in one launch of one block — the exchange without a producer kernel to ride on.
+__global__ void __launch_bounds__(256)
+xchg_push_kernel(const unsigned long long* __restrict__ C, XchgPush px) {
+  for (int ch = 0; ch < px.channels; ++ch) {
+    const unsigned long long step = px.win->step[ch] + 1;
+    const unsigned long long tag = (step & 0xffffffffull) << 32;
+    const int slot = (int)(step % kXSlots);
+    for (int bin = threadIdx.x; bin < px.n; bin += blockDim.x) {
+      const unsigned long long v = C[(int64_t)ch * px.n + bin];
+      const unsigned long long w0 = (v & 0xffffffffull) | tag, w1 = (v >> 32) | tag;
+      for (int q = 0; q < px.world; ++q) {
+        unsigned long long* row = xchg_row(px.peers[q], slot, px.rank, ch, px.world, px.channels, px.n);
+        st_relaxed_sys(row + 2 * bin, w0);
+        st_relaxed_sys(row + 2 * bin + 1, w1);
+      }
+    }
+    __syncthreads();                                   // every thread has read step[ch]
+    if (threadIdx.x == 0) px.win->step[ch] = step;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 labels_to_u8_kernel(const int64_t* __restrict__ in, uint8_t* __restrict__ out, int64_t n) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -423,6 +445,16 @@ extern "C" int ldiff_confusion_hist_push(const uint8_t* pred, const uint8_t* gt,
   const int rc = xchg_push_args(xchg, channel, (K + 1) * K, &px);
   if (rc != LDIFF_OK) return rc;
   return launch_confusion(pred, gt, gt_lut, C, n, 1, K, status, (cudaStream_t)stream, px);
+}
+
+extern "C" int ldiff_xchg_push(void* xchg, const int64_t* C, void* stream) {
+  if (!xchg || !C) return LDIFF_EINVAL;
+  Xchg* x = static_cast<Xchg*>(xchg);
+  XchgPush px{};
+  const int rc = xchg_push_args(xchg, 0, x->n, &px);
+  if (rc != LDIFF_OK) return rc;
+  xchg_push_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long*>(C), px);
+  return check_launch();
 }
 
 extern "C" int ldiff_xchg_reduce(void* xchg, int64_t* out, int* status, void* stream) {

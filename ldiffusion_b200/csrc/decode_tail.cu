@@ -279,6 +279,9 @@ __device__ __forceinline__ void dt_mbar_wait(uint64_t* bar, uint32_t parity) {
       "DT_DONE:\n\t}" ::"r"(dt_smem_u32(bar)), "r"(parity)
       : "memory");
 }
+__device__ __forceinline__ void dt_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(dt_smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void dt_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                    dt_smem_u32(dst_smem)),
@@ -317,8 +320,12 @@ __device__ __forceinline__ void quant16_staged(const float* p, uint32_t (&q)[16]
 // copy through it 25 us); from shared memory: see profiles/.)
 // (register cap: 42 for the gray-only forms, 64 with RGB — the CTAs of this kernel are resident for a whole launch,
 // and what they leave of the register file is what the concurrent chains of the pass get to run in)
-template <typename T, bool RGB, bool GRAY, bool EXTRA, int STAGES, int CTAS>
-__global__ void __launch_bounds__(256, (RGB ? 4 : 6) > CTAS ? (RGB ? 4 : 6) : CTAS)
+// PW: a ninth warp is the PRODUCER (canonical TMA pipeline): it alone waits for a stage to be released (one
+// mbarrier arrive per consumer warp) and refills it, so the eight consumer warps never meet at a CTA-wide barrier
+// — each one goes from tile to tile as fast as its own data arrives.
+template <typename T, bool RGB, bool GRAY, bool EXTRA, int STAGES, int CTAS, bool PW = false>
+__global__ void __launch_bounds__(256 + (PW ? 32 : 0),
+                                  (PW ? (RGB ? 3 : 5) : (RGB ? 4 : 6)) > CTAS ? (PW ? (RGB ? 3 : 5) : (RGB ? 4 : 6)) : CTAS)
 decode_tail_tma_kernel(const T* __restrict__ img, uint8_t* __restrict__ rgb,
                        uint8_t* __restrict__ gray, int64_t hw, int tiles_per_img, int total_tiles,
                        int64_t gray_batch_stride, int tile_off, TailExtras ex) {
@@ -326,6 +333,7 @@ decode_tail_tma_kernel(const T* __restrict__ img, uint8_t* __restrict__ rgb,
   extern __shared__ __align__(128) uint8_t dt_smem[];            // [kDtStages][3][kDtTile] T
   const int tiles_shift = (tiles_per_img & (tiles_per_img - 1)) == 0 ? 31 - __clz(tiles_per_img) : -1;
   __shared__ __align__(8) uint64_t full[kDtStages];
+  __shared__ __align__(8) uint64_t empty[PW ? kDtStages : 1];
   T* buf = reinterpret_cast<T*>(dt_smem);
   const int tid = threadIdx.x;
 
@@ -354,11 +362,27 @@ decode_tail_tma_kernel(const T* __restrict__ img, uint8_t* __restrict__ rgb,
   };
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < kDtStages; ++s) dt_mbar_init(&full[s], 1);
+    for (int s = 0; s < kDtStages; ++s) {
+      dt_mbar_init(&full[s], 1);
+      if (PW) dt_mbar_init(&empty[s], 8);                        // one arrive per consumer warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (tid == 0) {
+  if (PW && tid >= 256) {                                        // ---- producer warp (one lane issues)
+    if (tid == 256) {
+      for (int k = 0;; ++k) {
+        if (blockIdx.x + k * gridDim.x >= total_tiles) break;
+        if (k >= kDtStages) {
+          dt_mbar_wait(&empty[k % kDtStages], (uint32_t)(k / kDtStages - 1) & 1u);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        issue(k);
+      }
+    }
+    return;
+  }
+  if (!PW && tid == 0) {
 #pragma unroll
     for (int k = 0; k < kDtStages; ++k) issue(k);
   }
@@ -428,11 +452,16 @@ decode_tail_tma_kernel(const T* __restrict__ img, uint8_t* __restrict__ rgb,
         }
       }
     }
-    __syncthreads();                                             // every thread has read stage s
-    if (tid == 0) {
-      // the refill is an async-proxy write over memory just read through the generic proxy
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      issue(k + kDtStages);
+    if (PW) {                                                    // this warp has read stage s: release it
+      __syncwarp();
+      if ((tid & 31) == 0) dt_mbar_arrive(&empty[s]);
+    } else {
+      __syncthreads();                                           // every thread has read stage s
+      if (tid == 0) {
+        // the refill is an async-proxy write over memory just read through the generic proxy
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue(k + kDtStages);
+      }
     }
   }
 }
@@ -476,16 +505,16 @@ static void ensure_smem_attr(F kernel, int bytes, bool (&done)[kMaxDevices]) {
   }
 }
 
-template <typename T, bool RGB, bool GRAY, bool EXTRA, int STAGES, int CTAS>
+template <typename T, bool RGB, bool GRAY, bool EXTRA, int STAGES, int CTAS, bool PW = false>
 static void launch_tma_one(const T* p, uint8_t* rgb, uint8_t* gray, int64_t hw, int tiles_per_img, int total,
                            int64_t gray_batch_stride, int tile_off, const TailExtras& ex, cudaStream_t st) {
   static bool attr[kMaxDevices] = {};
   const size_t smem = (size_t)STAGES * 3 * kDtTile * sizeof(T);
-  auto k = decode_tail_tma_kernel<T, RGB, GRAY, EXTRA, STAGES, CTAS>;
+  auto k = decode_tail_tma_kernel<T, RGB, GRAY, EXTRA, STAGES, CTAS, PW>;
   ensure_smem_attr(k, (int)smem, attr);
   const int cap = CTAS * sm_count();
   const int grid = total < cap ? total : cap;
-  k<<<grid, 256, smem, st>>>(p, rgb, gray, hw, tiles_per_img, total, gray_batch_stride, tile_off, ex);
+  k<<<grid, 256 + (PW ? 32 : 0), smem, st>>>(p, rgb, gray, hw, tiles_per_img, total, gray_batch_stride, tile_off, ex);
 }
 
 // pipeline shapes (stages x CTAs per SM) selectable through LDIFF_TUNE_DECODE_TAIL_TMA: smem in flight per SM is
@@ -502,6 +531,10 @@ template <> struct TmaShapes<__nv_bfloat16> {
       case 4: launch_tma_one<T, RGB, GRAY, EXTRA, 2, 3>(p, rgb, gray, hw, tpi, total, gbs, toff, ex, st); break;   // 144 KB
       case 5: launch_tma_one<T, RGB, GRAY, EXTRA, 3, 2>(p, rgb, gray, hw, tpi, total, gbs, toff, ex, st); break;   // 144 KB
       case 6: launch_tma_one<T, RGB, GRAY, EXTRA, 2, 2>(p, rgb, gray, hw, tpi, total, gbs, toff, ex, st); break;   //  96 KB
+      case 7: launch_tma_one<T, RGB, GRAY, EXTRA, 2, 3, true>(p, rgb, gray, hw, tpi, total, gbs, toff, ex, st); break;   // producer warp
+      case 8: launch_tma_one<T, RGB, GRAY, EXTRA, 3, 2, true>(p, rgb, gray, hw, tpi, total, gbs, toff, ex, st); break;
+      case 9: launch_tma_one<T, RGB, GRAY, EXTRA, 2, 2, true>(p, rgb, gray, hw, tpi, total, gbs, toff, ex, st); break;
+      case 10: launch_tma_one<T, RGB, GRAY, EXTRA, 4, 2, true>(p, rgb, gray, hw, tpi, total, gbs, toff, ex, st); break;
       default: launch_tma_one<T, RGB, GRAY, EXTRA, 4, 2>(p, rgb, gray, hw, tpi, total, gbs, toff, ex, st); break;  // 192 KB
     }
   }

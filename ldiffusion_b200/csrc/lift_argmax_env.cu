@@ -35,8 +35,8 @@ namespace ldiff {
 constexpr int kEnvSegs = 7;        // segments per column and band (byte 7 of the packed vectors stays 0)
 constexpr int kEnvSrcW = 40;       // source columns a block stages in shared memory
 constexpr int kEnvRows = 127;
-constexpr int kEnvThreads = 128;   // threads per block (128 x 2 columns: twice the blocks of a 256-thread tiling, an
-                                   // even spread over the 148 SMs: 512 blocks were 3.46 per SM, i.e. 4 on some, 3 on others)      // rows per band (start rows are bytes; 0xff = "no further segment")
+constexpr int kEnvThreads = 256;   // threads per block.  (128 measured 22.8 / 24.2 us on i.i.d. / smooth logits against
+                                   // 21.6 / 17.2 us with 256: the per-block prologue is paid twice as often)      // rows per band (start rows are bytes; 0xff = "no further segment")
 
 // byte `sel & 7` of {hi, lo} in byte 0 (selector nibbles 1..3 = 7: the always-zero top byte of hi) — the raw PRMT;
 // __byte_perm would mask the selector first

@@ -10,11 +10,14 @@
 namespace ldiff {
 
 // ---------------------------------------------------------------------------
-// Philox4x32-10 (Salmon et al., SC'11), counter-based: no state in memory.
+// Philox4x32-R (Salmon et al., SC'11), counter-based: no state in memory.  R = 10 is the published default
+// (cuRAND's and torch's choice), R = 7 the smallest round count that passes BigCrush in the paper's table: 30 %
+// fewer multiply rounds for the bf16 instantiation, whose kernel is bound by exactly those IMAD.WIDEs.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+template <int R>
+__device__ __forceinline__ uint4 philox4x32(uint4 c, uint2 k) {
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < R; ++r) {
     const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
     const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
     c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
@@ -24,47 +27,63 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
   return c;
 }
 
-// 23 random bits k -> u = (2k + 1 - 2^23) * 2^-23: odd multiple of 2^-23 in (-1, 1).
-// Built from the bit pattern of 1 + k*2^-23 (no int->float conversion): f - 1.5 is
-// exact, and 2*(f - 1.5) + 2^-23 is exact.
-__device__ __forceinline__ float uniform_pm1(uint32_t w) {
-  const float f = __uint_as_float(0x3f800000u | (w >> 9));
-  return __fmaf_rn(__fadd_rn(f, -1.5f), 2.f, 1.1920928955078125e-07f);
-}
-
-// log2 of a NORMAL positive number: the bare MUFU.LG2.  (__log2f without .ftz brackets the
-// MUFU with a denormal pre-scaling — FSETP, FMUL, FADD per element — that 1 - |u| >= 2^-23
-// never needs.)
+// One 32-bit word -> one Laplace(0, b) variate.  Bits [22:0] are the magnitude m (23 bits), bit 31 the sign (each a
+// single LOP3 on the word; bits [30:23] are not used):
+//   |u| = m * 2^-23 in [0, 1)      (f = 1 + |u| is built from the bit pattern, no int->float conversion;
+//   1 - |u| = 2 - f                 both subtractions are exact)
+//   noise = sign * b * (-ln(1 - |u|))           == torch's  -b * sign(u) * log1p(-|u|)  with u = sign * |u|
+// A symmetric 24-bit uniform: |u| never reaches 1 (the largest magnitude is b * 23 ln 2 = 15.9 b), u = 0 has
+// probability 2^-23.  log: the bare MUFU.LG2 (1 - |u| >= 2^-23 is never denormal, so __log2f's FSETP/FMUL/FADD
+// bracket is dead weight).
+//  SERIES (fp32 storage): |u| >= 2^-5 uses the hardware log2 (relative error <= 6e-6 there), smaller |u| a
+//   5-term series (relative error < 1e-8): the SAME variate as the libm chain to ~6e-6 relative, far inside the
+//   1e-3 contract, at a third of libm's instruction count (libm made the fused kernel issue-bound at 0.59).
+//  !SERIES (bf16 storage, where half the bytes move per element and the kernel is ALU-bound): the hardware
+//   log2 everywhere (absolute error <= 1.7e-7 b, below a bf16 ulp of any noise value above 5e-5 b), sign and
+//   scale folded into one signed multiplier.
 __device__ __forceinline__ float lg2_normal(float w) {
   float r;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(w));
   return r;
 }
-
-// Philox mode only: -b * sign(u) * log1p(-|u|) with a short log1p.  w = 1 - |u| is exact;
-// |u| >= 2^-5 uses the hardware log2 (relative error <= 6e-6 there), smaller |u| a
-// 5-term series (relative error < 1e-8).  The result is the SAME random variate to
-// ~6e-6 relative, far below the 1e-3 contract, at a third of libm's instruction count
-// (which made the fused kernel issue-bound at 59 % of the HBM roofline).
-// SERIES = false (bf16 storage, where half the bytes move per element and the kernel is
-// ALU-bound): the hardware log2 everywhere, -b ln2 folded into one multiply.  Its absolute
-// error (<= 2^-22 in log2 near 1) is <= 1.7e-7 b in the noise, i.e. below a bf16 ulp of any
-// noise value above 5e-5 b; 7 instructions per element fewer.
 template <bool SERIES>
-__device__ __forceinline__ float laplace_from_uniform_fast(float u, float b) {
-  const float a = fabsf(u);
-  if (!SERIES) return copysignf(lg2_normal(__fsub_rn(1.f, a)) * (b * -0.6931471805599453f), u);
-  const float lg = lg2_normal(__fsub_rn(1.f, a)) * 0.6931471805599453f;
+__device__ __forceinline__ float laplace_from_word(uint32_t w, float b) {
+  const float f = __uint_as_float(0x3f800000u | (w & 0x007fffffu));
+  const float t = __fsub_rn(2.f, f);                                   // 1 - |u|, exact
+  const uint32_t sgn = w & 0x80000000u;
+  if (!SERIES)
+    return lg2_normal(t) * __uint_as_float(__float_as_uint(b * -0.6931471805599453f) ^ sgn);
+  const float a = __fadd_rn(f, -1.f);                                  // |u|, exact
+  const float lg = lg2_normal(t) * 0.6931471805599453f;
   float p = __fmaf_rn(a, 0.2f, 0.25f);
   p = __fmaf_rn(a, p, 0.3333333333f);
   p = __fmaf_rn(a, p, 0.5f);
   p = __fmaf_rn(a, p, 1.f);
-  const float l = (a < 0.03125f) ? -a * p : lg;           // log1p(-a) <= 0
-  // noise = -b * sign(u) * l = copysign(b * (-l), u)
-  return copysignf(b * -l, u);
+  const float l = (a < 0.03125f) ? -a * p : lg;                        // log1p(-a) <= 0
+  return __uint_as_float(__float_as_uint(b * -l) ^ sgn);
 }
-template <typename T> struct FastLaplace { static constexpr bool kSeries = true; };
-template <> struct FastLaplace<__nv_bfloat16> { static constexpr bool kSeries = false; };
+template <typename T> struct FastLaplace { static constexpr bool kSeries = true; static constexpr bool kHalfWords = false; };
+template <> struct FastLaplace<__nv_bfloat16> { static constexpr bool kSeries = false; static constexpr bool kHalfWords = true; };
+
+// bf16 storage draws TWO variates from every 32-bit word (the kernel is bound by Philox's IMAD.WIDEs, and a bf16 sum
+// cannot resolve a 23-bit uniform anyway): each half-word is a sign bit + a 15-bit magnitude m, |u| = m * 2^-15.
+// The exponential tail is NOT truncated at 15 ln 2: by the memorylessness of -ln(1 - U), the top cell m = 2^15 - 1
+// (probability 2^-15) is refined with 23 more bits of a second draw, |noise| = b * (15 ln 2 - ln(1 - m2 * 2^-23)), so
+// the support reaches 38 ln 2 = 26.3 b (the 24-bit fp32 form stops at 15.9 b).
+//   half 0 = bits [31:16] (sign 31, magnitude [30:16]), half 1 = bits [15:0] (sign 15, magnitude [14:0])
+// lg2_of_half: log2(1 - |u|) of one half and its sign bit; the rare top cell is flagged for the caller.
+__device__ __forceinline__ float lg2_of_half(uint32_t w, int half, uint32_t& sgn, bool& top) {
+  const uint32_t m8 = (half == 0 ? (w >> 8) : (w << 8)) & 0x007fff00u;    // the 15 magnitude bits at mantissa [22:8]
+  sgn = (half == 0 ? w : (w << 16)) & 0x80000000u;
+  top = m8 == 0x007fff00u;
+  return lg2_normal(__fsub_rn(2.f, __uint_as_float(0x3f800000u | m8)));   // 1 - |u| >= 2^-15: exact, normal
+}
+// second-level draw for element e (0..7) of the 8-element group whose counter is c: log2 of the refined tail
+template <int R>
+__device__ __noinline__ float lg2_tail_extension(uint64_t c, int e, uint2 key) {
+  const uint4 r = philox4x32<R>(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 1u + (uint32_t)e, 0u), key);
+  return -15.f + lg2_normal(__fsub_rn(2.f, __uint_as_float(0x3f800000u | (r.x & 0x007fffffu))));
+}
 
 // torch.distributions.Laplace.rsample with loc = 0:
 //   noise = 0 - (scale * sign(u)) * log1p(-|u|)
@@ -75,21 +94,69 @@ __device__ __forceinline__ float laplace_from_uniform(float u, float b) {
   return __fsub_rn(0.f, __fmul_rn(t, l));
 }
 
-enum { SRC_PHILOX = 0, SRC_UNIFORM = 1, SRC_NOISE = 2 };
+enum { SRC_PHILOX = 0, SRC_UNIFORM = 1, SRC_NOISE = 2, SRC_PHILOX7 = 3 };   // SRC_PHILOX: 10 rounds
+template <int SRC> struct IsPhilox { static constexpr bool value = SRC == SRC_PHILOX || SRC == SRC_PHILOX7; };
+template <int SRC> struct Rounds { static constexpr int value = SRC == SRC_PHILOX7 ? 7 : 10; };
+
+// rounds of the Philox stream: 10 (the published default) unless LDIFF_TUNE_PHILOX_ROUNDS = 7 asks for the
+// paper's Crush-resistant minimum
+template <typename T> static bool philox_seven() { return tune_get(LDIFF_TUNE_PHILOX_ROUNDS) == 7; }
+
+// 8 elements of the half-word form: lg[i] = log2(1 - |u_i|) <= 0 (tail extension applied), sg[i] = sign bit
+template <int R>
+__device__ __forceinline__ void philox_half8(int64_t base, uint2 key, uint64_t offset, float (&lg)[8], uint32_t (&sg)[8]) {
+  const uint64_t c = offset + (uint64_t)(base >> 3);
+  const uint4 r = philox4x32<R>(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0u, 0u), key);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  bool any_top = false;
+  bool top[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    lg[i] = lg2_of_half(w[i >> 1], i & 1, sg[i], top[i]);
+    any_top |= top[i];
+  }
+  if (any_top) {                                       // probability 2^-12 per group
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (top[i]) lg[i] = lg2_tail_extension<R>(c, i, key);
+  }
+}
+
+// the 8 Philox words of elements [base, base + 8)
+template <int SRC>
+__device__ __forceinline__ void philox_words8(int64_t base, uint2 key, uint64_t offset, uint32_t (&w)[8]) {
+  constexpr int R = SRC == SRC_PHILOX7 ? 7 : 10;
+  const uint64_t c0 = offset + (uint64_t)(base >> 2);
+  const uint4 r0 = philox4x32<R>(make_uint4((uint32_t)c0, (uint32_t)(c0 >> 32), 0u, 0u), key);
+  const uint64_t c1 = c0 + 1;
+  const uint4 r1 = philox4x32<R>(make_uint4((uint32_t)c1, (uint32_t)(c1 >> 32), 0u, 0u), key);
+  w[0] = r0.x; w[1] = r0.y; w[2] = r0.z; w[3] = r0.w; w[4] = r1.x; w[5] = r1.y; w[6] = r1.z; w[7] = r1.w;
+}
+
+// x + noise for the bf16-storage Philox form when the noise itself is not emitted: the scale-and-sign multiply and
+// the add are ONE fma (the sum is rounded to bf16 right after, so the fp32 rounding of the noise it skips is 2^-16
+// of a storage ulp; the emitting form keeps noise and sum separate so that out == x + noise_out exactly)
+template <typename T, int SRC> struct FusedAdd {
+  static constexpr bool value = IsPhilox<SRC>::value && FastLaplace<T>::kHalfWords;
+};
 
 // noise of the 8 elements [base, base + 8) / of element t (shared by the stand-alone kernel and the
 // fused step+noise kernel, so both produce the same bits)
 template <typename T, int SRC>
 __device__ __forceinline__ void laplace_noise8(const T* __restrict__ inj, int64_t base, float b, uint2 key,
                                                uint64_t offset, float (&nz)[8]) {
-  if (SRC == SRC_PHILOX) {
-    const uint64_t c0 = offset + (uint64_t)(base >> 2);
-    const uint4 r0 = philox4x32_10(make_uint4((uint32_t)c0, (uint32_t)(c0 >> 32), 0u, 0u), key);
-    const uint64_t c1 = c0 + 1;
-    const uint4 r1 = philox4x32_10(make_uint4((uint32_t)c1, (uint32_t)(c1 >> 32), 0u, 0u), key);
-    const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+  if (IsPhilox<SRC>::value && FastLaplace<T>::kHalfWords) {
+    float lg[8];
+    uint32_t sg[8];
+    philox_half8<Rounds<SRC>::value>(base, key, offset, lg, sg);
+    const uint32_t kb = __float_as_uint(b * -0.6931471805599453f);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) nz[i] = laplace_from_uniform_fast<FastLaplace<T>::kSeries>(uniform_pm1(w[i]), b);
+    for (int i = 0; i < 8; ++i) nz[i] = lg[i] * __uint_as_float(kb ^ sg[i]);
+  } else if (IsPhilox<SRC>::value) {
+    uint32_t w[8];
+    philox_words8<SRC>(base, key, offset, w);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) nz[i] = laplace_from_word<FastLaplace<T>::kSeries>(w[i], b);
   } else {
     Vec8<T>::load(inj + base, nz);
     if (SRC == SRC_UNIFORM) {
@@ -101,11 +168,24 @@ __device__ __forceinline__ void laplace_noise8(const T* __restrict__ inj, int64_
 template <typename T, int SRC>
 __device__ __forceinline__ float laplace_noise1(const T* __restrict__ inj, int64_t t, float b, uint2 key,
                                                 uint64_t offset) {
-  if (SRC == SRC_PHILOX) {
-    const uint64_t c = offset + (uint64_t)(t >> 2);
-    const uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0u, 0u), key);
+  if (IsPhilox<SRC>::value && FastLaplace<T>::kHalfWords) {
+    constexpr int R = Rounds<SRC>::value;
+    const uint64_t c = offset + (uint64_t)(t >> 3);
+    const uint4 r = philox4x32<R>(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0u, 0u), key);
     const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-    return laplace_from_uniform_fast<FastLaplace<T>::kSeries>(uniform_pm1(w[t & 3]), b);
+    const int e = (int)(t & 7);
+    uint32_t sg;
+    bool top;
+    float lg = lg2_of_half(w[e >> 1], e & 1, sg, top);
+    if (top) lg = lg2_tail_extension<R>(c, e, key);
+    return lg * __uint_as_float(__float_as_uint(b * -0.6931471805599453f) ^ sg);
+  }
+  if (IsPhilox<SRC>::value) {
+    constexpr int R = Rounds<SRC>::value;
+    const uint64_t c = offset + (uint64_t)(t >> 2);
+    const uint4 r = philox4x32<R>(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0u, 0u), key);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+    return laplace_from_word<FastLaplace<T>::kSeries>(w[t & 3], b);
   }
   const float nzs = to_f32(inj[t]);
   return SRC == SRC_UNIFORM ? laplace_from_uniform(nzs, b) : nzs;
@@ -117,15 +197,29 @@ laplace_qsample_kernel(const T* __restrict__ x, T* __restrict__ out, const T* __
                        T* __restrict__ noise_out, float b, uint2 key, uint64_t offset, int64_t n) {
   const int64_t nvec = n >> 3;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
-    const int64_t base = v << 3;
+  auto body = [&](int64_t base) {
     float xv[8], nz[8];
     Vec8<T>::load(x + base, xv);
-    laplace_noise8<T, SRC>(inj, base, b, key, offset, nz);
-    if (EMIT) Vec8<T>::store(noise_out + base, nz);
+    if (!EMIT && FusedAdd<T, SRC>::value) {
+      float lg[8];
+      uint32_t sg[8];
+      philox_half8<Rounds<SRC>::value>(base, key, offset, lg, sg);
+      const uint32_t kb = __float_as_uint(b * -0.6931471805599453f);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) xv[i] = __fadd_rn(xv[i], nz[i]);
+      for (int i = 0; i < 8; ++i) xv[i] = __fmaf_rn(lg[i], __uint_as_float(kb ^ sg[i]), xv[i]);
+    } else {
+      laplace_noise8<T, SRC>(inj, base, b, key, offset, nz);
+      if (EMIT) Vec8<T>::store(noise_out + base, nz);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) xv[i] = __fadd_rn(xv[i], nz[i]);
+    }
     Vec8<T>::store(out + base, xv);
+  };
+  if (n < (int64_t(1) << 31)) {                          // 32-bit index arithmetic (the bf16 form is ALU-bound)
+    const uint32_t nv = (uint32_t)nvec, st = (uint32_t)stride;
+    for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += st) body((int64_t)(v << 3));
+  } else {
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) body(v << 3);
   }
   // scalar tail (n % 8 elements), one thread each
   const int64_t t = (nvec << 3) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -154,7 +248,8 @@ static int launch_qsample(const void* x, void* out, const void* noise_in, const 
   } else if (u_in) {
     if (no) LQ(SRC_UNIFORM, true, u_in); else LQ(SRC_UNIFORM, false, u_in);
   } else {
-    if (no) LQ(SRC_PHILOX, true, nullptr); else LQ(SRC_PHILOX, false, nullptr);
+    if (philox_seven<T>()) { if (no) LQ(SRC_PHILOX7, true, nullptr); else LQ(SRC_PHILOX7, false, nullptr); }
+    else if (no) LQ(SRC_PHILOX, true, nullptr); else LQ(SRC_PHILOX, false, nullptr);
   }
 #undef LQ
   return check_launch();
@@ -255,13 +350,23 @@ plms_step_noise_kernel(const T* __restrict__ x, const T* __restrict__ e0, const 
     if (MODE >= 3) Vec8<T>::load(e2 + base, c);
     if (MODE >= 4) Vec8<T>::load(e3 + base, d);
     Vec8<T>::load(clean + base, cl);
-    laplace_noise8<T, SRC>(inj, base, b, key, offset, nz);
+    if (FusedAdd<T, SRC>::value) {                     // (exactly laplace_qsample_kernel's non-emitting form)
+      float lg[8];
+      uint32_t sg[8];
+      philox_half8<Rounds<SRC>::value>(base, key, offset, lg, sg);
+      const uint32_t kb = __float_as_uint(b * -0.6931471805599453f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) cl[i] = __fmaf_rn(lg[i], __uint_as_float(kb ^ sg[i]), cl[i]);
+    } else {
+      laplace_noise8<T, SRC>(inj, base, b, key, offset, nz);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) cl[i] = __fadd_rn(cl[i], nz[i]);
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float eh = plms_eps<MODE>(a[i], MODE >= 1 ? bb[i] : 0.f, MODE >= 3 ? c[i] : 0.f,
                                       MODE >= 4 ? d[i] : 0.f);
       xv[i] = __fsub_rn(__fmul_rn(sc, xv[i]), __fdiv_rn(__fmul_rn(dA, eh), denom));
-      cl[i] = __fadd_rn(cl[i], nz[i]);
     }
     Vec8<T>::store(prev + base, xv);
     Vec8<T>::store(noisy + base, cl);
@@ -292,6 +397,7 @@ static int launch_plms_noise(const void* x, const void* e0, const void* e1, cons
   do {                                                  \
     if (noise_in) PSN(M, SRC_NOISE, noise_in);          \
     else if (u_in) PSN(M, SRC_UNIFORM, u_in);           \
+    else if (philox_seven<T>()) PSN(M, SRC_PHILOX7, nullptr); \
     else PSN(M, SRC_PHILOX, nullptr);                   \
   } while (0)
   switch (mode) {
@@ -350,37 +456,14 @@ laplace_qsample_map_kernel(const T* __restrict__ x, const T* __restrict__ scale,
     float xv[8], nz[8], sv[8];
     Vec8<T>::load(x + base, xv);
     Vec8<T>::load(scale + map_index(base, mi), sv);
-    if (SRC == SRC_PHILOX) {
-      const uint64_t c0 = offset + (uint64_t)(base >> 2);
-      const uint4 r0 = philox4x32_10(make_uint4((uint32_t)c0, (uint32_t)(c0 >> 32), 0u, 0u), key);
-      const uint64_t c1 = c0 + 1;
-      const uint4 r1 = philox4x32_10(make_uint4((uint32_t)c1, (uint32_t)(c1 >> 32), 0u, 0u), key);
-      const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-      for (int i = 0; i < 8; ++i) nz[i] = laplace_from_uniform_fast<FastLaplace<T>::kSeries>(uniform_pm1(w[i]), 1.f);
-    } else {
-      Vec8<T>::load(inj + base, nz);
-      if (SRC == SRC_UNIFORM) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) nz[i] = laplace_from_uniform(nz[i], 1.f);
-      }
-    }
+    laplace_noise8<T, SRC>(inj, base, 1.f, key, offset, nz);
     if (EMIT) Vec8<T>::store(noise_out + base, nz);
 #pragma unroll
     for (int i = 0; i < 8; ++i) xv[i] = __fadd_rn(__fmul_rn(x_mul, xv[i]), __fmul_rn(nz[i], sv[i]));
     Vec8<T>::store(out + base, xv);
   }
   for (int64_t t = (nvec << 3) + tid; t < n; t += stride) {
-    float nzs;
-    if (SRC == SRC_PHILOX) {
-      const uint64_t c = offset + (uint64_t)(t >> 2);
-      const uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0u, 0u), key);
-      const uint32_t w = (t & 2) ? ((t & 1) ? r.w : r.z) : ((t & 1) ? r.y : r.x);
-      nzs = laplace_from_uniform_fast<FastLaplace<T>::kSeries>(uniform_pm1(w), 1.f);
-    } else {
-      nzs = to_f32(inj[t]);
-      if (SRC == SRC_UNIFORM) nzs = laplace_from_uniform(nzs, 1.f);
-    }
+    const float nzs = laplace_noise1<T, SRC>(inj, t, 1.f, key, offset);
     if (EMIT) noise_out[t] = from_f32<T>(nzs);
     const float s = to_f32(scale[map_index(t, mi)]);
     out[t] = from_f32<T>(__fadd_rn(__fmul_rn(x_mul, to_f32(x[t])), __fmul_rn(nzs, s)));
@@ -446,7 +529,8 @@ static int launch_qsample_map(const void* x, const void* scale, void* out, const
   } else if (u_in) {
     if (no) LQM(SRC_UNIFORM, true, u_in); else LQM(SRC_UNIFORM, false, u_in);
   } else {
-    if (no) LQM(SRC_PHILOX, true, nullptr); else LQM(SRC_PHILOX, false, nullptr);
+    if (philox_seven<T>()) { if (no) LQM(SRC_PHILOX7, true, nullptr); else LQM(SRC_PHILOX7, false, nullptr); }
+    else if (no) LQM(SRC_PHILOX, true, nullptr); else LQM(SRC_PHILOX, false, nullptr);
   }
 #undef LQM
   return check_launch();

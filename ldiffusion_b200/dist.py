@@ -154,6 +154,20 @@ class ConfusionExchange:
             torch.cuda.current_stream(pred.device).cuda_stream))
         return C
 
+    def push(self, C: torch.Tensor) -> None:
+        """Push finished matrices of ALL channels (int64 [channels, K+1, K]) without a histogram kernel to ride
+        on — the once-per-evaluation sum (the reference adds its counts at the end of evaluation)."""
+        from . import ops
+        if C.dtype != torch.int64 or C.numel() != self.channels * self.n or not C.is_contiguous():
+            raise ValueError("C must be a contiguous int64 [channels, K+1, K] tensor")
+        ops._cuda(C)
+        self._check(self._lib.ldiff_xchg_push(self._h, C.data_ptr(), torch.cuda.current_stream(C.device).cuda_stream))
+
+    def allreduce(self, C: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+        """push + reduce: the sum over ranks of C, through the peer windows."""
+        self.push(C)
+        return self.reduce(out)
+
     def reduce(self, out: torch.Tensor = None) -> torch.Tensor:
         """Sum over ranks of the next not-yet-reduced step's matrices: int64 [channels, K+1, K]."""
         from . import ops

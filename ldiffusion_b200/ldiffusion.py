@@ -18,7 +18,8 @@ from .segmentor import Segmentor
 
 
 class LDiffusionModel:
-    def __init__(self, diffusion_path, level, local_rank=-1, pipeline_loader=None, model_factory=None):
+    def __init__(self, diffusion_path, level, local_rank=-1, pipeline_loader=None, model_factory=None,
+                 allow_standins: bool = False):
         self.local_rank = local_rank
         self.world_size = int(os.environ.get("WORLD_SIZE", "1"))
         self.global_rank = int(os.environ.get("RANK", "0"))
@@ -34,13 +35,15 @@ class LDiffusionModel:
         self.pipeline, self.vae = None, None
         self.linear_layer = None
         self._pipeline_loader, self._model_factory = pipeline_loader, model_factory
+        self._allow_standins = bool(allow_standins)
 
     def _is_main_process(self):
         return self.global_rank == 0
 
     def _segmentor(self, train_loader, val_loader, num_classes):
         return Segmentor(train_loader, val_loader, self.level, num_classes,
-                         pipeline_loader=self._pipeline_loader, model_factory=self._model_factory)
+                         pipeline_loader=self._pipeline_loader, model_factory=self._model_factory,
+                         allow_standins=self._allow_standins)
 
     def inference(self, image_path, ldiffusion_weight, segmentor_weight, num_classes):
         """ldiffusion.py:317-324 -> (PIL.Image, np.uint8 mask [H0,W0])."""
@@ -98,20 +101,25 @@ class LDiffusionModel:
         text = proj(text)                                                                 # :219
         sched = pipeline.scheduler
         sched.set_timesteps(num_inference_steps, device=dev)                              # :229
+        # per-rank, per-purpose Philox keys: every rank draws its own noise for its own batch (the reference's
+        # per-process torch generators), and the contrastive sampler never shares counters with the noise stream
+        rank = int(getattr(self, "global_rank", 0))
+        noise_seed = (int(seed) ^ (rank << 32) ^ 0x4C61706C61636500) & (2 ** 64 - 1)      # "Laplace"
+        pair_seed = (int(seed) ^ (rank << 32) ^ 0x496E666F4E434500) & (2 ** 64 - 1)       # "InfoNCE"
         blocks = (latents.numel() + 3) // 4
         n = len(sched.timesteps)
         grays = []
         for i, t in enumerate(sched.timesteps):
             with torch.no_grad():
                 x = sched.scale_model_input(latents, t)                                   # :233
-                noisy = sched.add_laplace_noise(x, sched._host_timesteps[i], seed=seed,
+                noisy = sched.add_laplace_noise(x, sched._host_timesteps[i], seed=noise_seed,
                                                 offset=(step_index * n + i) * blocks,
                                                 noise=None if noise is None else noise[i])   # :234-237
             denoised = unet(noisy, t, text).sample                                        # :238
             decoded = vae.decode(denoised.to(torch.float32)).sample                       # :240
             grays.append(ops.bilinear_lift_autograd(decoded, size, gray=True))            # :240-242
         gray = torch.cat(grays, dim=1)                                                    # :244-247
-        loss = pixel_contrastive_loss(gray, label64, pairs=pairs, seed=seed, offset=step_index)   # :252
+        loss = pixel_contrastive_loss(gray, label64, pairs=pairs, seed=pair_seed, offset=step_index)   # :252
         optimizer.zero_grad(set_to_none=True)
         loss.backward()                                                                   # :254
         params = [p for g in optimizer.param_groups for p in g["params"] if p.grad is not None]

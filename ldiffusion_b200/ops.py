@@ -57,25 +57,35 @@ def status_word(device) -> Tensor:
 
 
 def check_status(device):
-    """Synchronising read of the status word; raises like the reference does."""
+    """Synchronising read of the status word; raises like the reference does.  Only the bit that is reported is
+    cleared: a second error recorded at the same time surfaces on the next call instead of being dropped."""
     w = status_word(device)
     bits = int(w.item())
-    if bits:
-        w.zero_()
-        if bits & _cabi.STATUS_PRED_RANGE:
-            # F.one_hot at evaluate.py:70 raises this for a predicted label >= K
-            raise RuntimeError("Class values must be smaller than num_classes.")
-        if bits & _cabi.STATUS_INST_RANGE:
-            raise RuntimeError("ldiff: instance id outside the class LUT")
-        if bits & _cabi.STATUS_SW_INF:
-            # predict_from_raw_data.py:581-585
-            raise RuntimeError("Encountered inf in predicted array. Aborting... If this problem persists, "
-                               "reduce value_scaling_factor in compute_gaussian or increase the dtype of "
-                               "predicted_logits to fp32")
-        if bits & _cabi.STATUS_LABEL_RANGE:
-            raise RuntimeError("ldiff: label value >= 32 in the contrastive sampler")
-        if bits & _cabi.STATUS_XCHG_TIMEOUT:
-            raise RuntimeError("ldiff: a rank did not deliver its confusion matrix in time (peer exchange)")
+    if not bits:
+        return
+
+    def report(bit, exc):
+        w.bitwise_and_(~bit)
+        raise exc
+
+    if bits & _cabi.STATUS_PRED_RANGE:
+        # F.one_hot at evaluate.py:70 raises this for a predicted label >= K
+        report(_cabi.STATUS_PRED_RANGE, RuntimeError("Class values must be smaller than num_classes."))
+    if bits & _cabi.STATUS_INST_RANGE:
+        report(_cabi.STATUS_INST_RANGE, RuntimeError("ldiff: instance id outside the class LUT"))
+    if bits & _cabi.STATUS_SW_INF:
+        # predict_from_raw_data.py:581-585
+        report(_cabi.STATUS_SW_INF, RuntimeError(
+            "Encountered inf in predicted array. Aborting... If this problem persists, "
+            "reduce value_scaling_factor in compute_gaussian or increase the dtype of "
+            "predicted_logits to fp32"))
+    if bits & _cabi.STATUS_LABEL_RANGE:
+        report(_cabi.STATUS_LABEL_RANGE, RuntimeError("ldiff: label value >= 32 in the contrastive sampler"))
+    if bits & _cabi.STATUS_XCHG_TIMEOUT:
+        report(_cabi.STATUS_XCHG_TIMEOUT, RuntimeError(
+            "ldiff: a rank did not deliver its confusion matrix in time (peer exchange): the sums read since "
+            "are partial"))
+    w.zero_()                                          # unknown bits
 
 
 # ---------------------------------------------------------------------------

@@ -42,12 +42,43 @@ class HotPathInputs:
     inst_map: torch.Tensor           # int32 [B,H,W] Cellpose instance ids
     inst_feats: torch.Tensor         # [B,N,256] pooled instance features
     gt: torch.Tensor                 # uint8 [B,H,W] ground-truth classes
+    slab = None                      # set by packed(): the uint8 tensor all fields are views of
 
     def tensors(self):
         return [self.latents, *self.eps, *self.decoded, self.head_feat, self.inst_map, self.inst_feats, self.gt]
 
     def nbytes(self):
         return sum(t.numel() * t.element_size() for t in self.tensors())
+
+    def fields(self):
+        return (self.latents, self.eps, self.decoded, self.head_feat, self.inst_map, self.inst_feats, self.gt)
+
+    # ---- one contiguous slab per batch: a step's host->device transfer is ONE copy instead of 17 -------------
+    def slab_layout(self):
+        """[(offset, nbytes, shape, dtype)] of every tensor in ``tensors()`` order, 256-byte aligned; total bytes."""
+        off, lay = 0, []
+        for t in self.tensors():
+            nb = t.numel() * t.element_size()
+            lay.append((off, nb, tuple(t.shape), t.dtype))
+            off += (nb + 255) & ~255
+        return lay, off
+
+    def packed(self, pin: bool = True, device=None) -> "HotPathInputs":
+        """A copy of this batch whose tensors are views of ONE uint8 slab (``.slab``): pinned host memory by
+        default, or device memory (``device=...``) for the receiving side."""
+        lay, total = self.slab_layout()
+        if device is None:
+            slab = torch.empty(total, dtype=torch.uint8, pin_memory=pin)
+        else:
+            slab = torch.empty(total, dtype=torch.uint8, device=device)
+        views = [slab[o:o + nb].view(dt).view(shape) for (o, nb, shape, dt) in lay]
+        if device is None:
+            for v, t in zip(views, self.tensors()):
+                v.copy_(t)
+        n = len(self.eps)
+        out = HotPathInputs(views[0], views[1:1 + n], views[1 + n:1 + 2 * n], *views[1 + 2 * n:])
+        out.slab = slab
+        return out
 
 
 class _nvtx:
@@ -81,18 +112,33 @@ class HotPath:
         self.lat_elems = batch * 4 * (height // 8) * (width // 8)
         e = lambda *s, dt=dtype: torch.empty(s, dtype=dt, device=dev)          # noqa: E731
         self.noisy = [e(*lat) for _ in range(num_steps)]
-        self.lat = [e(*lat) for _ in range(num_steps)]
-        self.planes = e(batch, num_steps + 1, height, width, dt=torch.uint8)
-        self.rgb = e(batch, height, width, 3, dt=torch.uint8)
-        self.featcat = e(batch, num_steps, *feat_size)
-        self.label_small = e(batch, 1, *feat_size, dt=torch.uint8)
+        self.lat = [e(*lat) for _ in range(num_steps - 1)]
+        # the results the reference hands to the HOST (RESULT_KEYS) are views of ONE slab, so that a step's
+        # device->host transfer is a single copy: final latents, pixel vectors (pixel_latent_vector.py:89-101 writes
+        # them to CSV), the uint8 image (a PIL image in the reference), the two masks (np.ndarray at
+        # ldiffusion.py:545), the confusion matrices, and the small training-path tensors
+        spec = [("latents", lat, dtype), ("pixel_planes", (batch, num_steps + 1, height, width), torch.uint8),
+                ("rgb", (batch, height, width, 3), torch.uint8), ("featcat", (batch, num_steps, *feat_size), dtype),
+                ("label_small", (batch, 1, *feat_size), torch.uint8),
+                ("mask_tissue", (batch, height, width), torch.uint8), ("mask_cell", (batch, height, width), torch.uint8),
+                ("confusion", (2, num_classes + 1, num_classes), torch.int64)]
+        off, self._out_layout = 0, []
+        for name, shape, dt in spec:
+            nb = torch.empty(0, dtype=dt).element_size()
+            for d in shape:
+                nb *= d
+            self._out_layout.append((name, off, nb, tuple(shape), dt))
+            off += (nb + 255) & ~255
+        self.out_slab = torch.zeros(off, dtype=torch.uint8, device=dev)
+        ov = {name: self.out_slab[o:o + nb].view(dt).view(shape) for name, o, nb, shape, dt in self._out_layout}
+        self.lat.append(ov["latents"])
+        self.planes, self.rgb, self.featcat, self.label_small = ov["pixel_planes"], ov["rgb"], ov["featcat"], ov["label_small"]
+        self.mask_tissue, self.mask_cell, self.C = ov["mask_tissue"], ov["mask_cell"], ov["confusion"]
+        # device-only results (the reference keeps them on the GPU: ldiffusion.py:251-252 feeds rgb_up to the loss)
         self.rgb_small = e(batch, 3, *feat_size)
         self.rgb_up = e(batch, 3, height, width)
         self.logits = e(batch, num_classes, *head_hw, dt=torch.float32)
-        self.mask_tissue = e(batch, height, width, dt=torch.uint8)
         self.lut = torch.zeros((batch, n_instances + 1), dtype=torch.uint8, device=dev)
-        self.mask_cell = e(batch, height, width, dt=torch.uint8)
-        self.C = torch.zeros((2, num_classes + 1, num_classes), dtype=torch.int64, device=dev)
         self.inst_ids = torch.arange(1, n_instances + 1, dtype=torch.int32, device=dev)
         g = torch.Generator(device="cpu").manual_seed(seed)
         self.head_w = (torch.randn(num_classes, head_channels, generator=g) / 16).to(dev, dtype)
@@ -111,6 +157,10 @@ class HotPath:
         # ~8 instructions per pixel land on an issue-bound kernel, while the stand-alone histogram is latency-bound
         # and overlaps the other chains; the fused entry point stays in the library for callers without that overlap)
         self.tissue_hist_fused = os.environ.get("LDIFF_PASS_TISSUE_HIST_FUSED", "0") == "1"
+        # accumulate: the confusion matrices are NOT cleared at the start of a pass — they add up over the passes of an
+        # evaluation (reset_confusion() starts a new one) and are summed across ranks once at its end, as the
+        # reference does; False: every pass starts from zero (and can push its matrices, attach_exchange)
+        self.accumulate = False
         self.decode_streams = max(1, min(num_steps, int(os.environ.get("LDIFF_DECODE_STREAMS", "1"))))
 
     def attach_exchange(self, exchange, deferred: bool = True):
@@ -125,11 +175,20 @@ class HotPath:
         self.exchange, self.exchange_deferred, self._unreduced = exchange, bool(deferred), 0
         self.C_global = torch.zeros_like(self.C)
 
-    def flush_exchange(self):
-        """Reduce the passes whose matrices were pushed but not summed yet (deferred mode)."""
+    def reset_confusion(self):
+        self.C.zero_()
+
+    def _reduce_pending(self):
         while self.exchange is not None and self._unreduced > 0:
             self.exchange.reduce(out=self.C_global)
             self._unreduced -= 1
+
+    def flush_exchange(self):
+        """Reduce the passes whose matrices were pushed but not summed yet (deferred mode) and read the status
+        word (a synchronising call: not for use inside a graph capture)."""
+        self._reduce_pending()
+        if self.exchange is not None:
+            ops.check_status(self.device)              # a peer that timed out means C_global is a PARTIAL sum: raise
         return self.C_global
 
     # number of ldiff kernels one pass launches
@@ -156,7 +215,7 @@ class HotPath:
         does not matter)."""
         cur = torch.cuda.current_stream(self.device)
         n = self.n
-        if not self.fused:
+        if not self.fused and not self.accumulate:
             self.C.zero_()                                                 # a memset every chain waits for
         if concurrent:
             side = self._side_streams()
@@ -186,7 +245,7 @@ class HotPath:
         if self.exchange is not None:
             self._unreduced += 1
             if not self.exchange_deferred:
-                self.flush_exchange()
+                self._reduce_pending()
 
     # CUDA stream priorities of the five chains (sampler, lifts, tissue, cell, decode tails); captured
     # graphs keep them per kernel node.  When blocks of several chains are waiting for an SM, the
@@ -257,7 +316,8 @@ class HotPath:
 
     def _chain_tissue(self, inp):
         if self.fused:
-            ops._head_logits(inp.head_feat, self.head_w, self.head_b, self.logits, self.C[0])   # also zeroes C[0]
+            ops._head_logits(inp.head_feat, self.head_w, self.head_b, self.logits,
+                             None if self.accumulate else self.C[0])                             # also zeroes C[0]
             if self.tissue_hist_fused:
                 ops.lift_argmax_hist(self.logits, (self.H, self.W), inp.gt, out=self.C[0], mask_out=self.mask_tissue,
                                      exchange=self.exchange, channel=0)
@@ -272,7 +332,7 @@ class HotPath:
     def _chain_cell(self, inp):
         if self.fused:
             ops._cell_classify(inp.inst_feats, self.cell_w, self.cell_b, self.inst_ids, self.lut, None, self.status,
-                               self.C[1])                                                       # also zeroes C[1]
+                               None if self.accumulate else self.C[1])                          # also zeroes C[1]
             ops.lut_paint_hist(inp.inst_map, self.lut, inp.gt, self.K, out=self.C[1], mask_out=self.mask_cell,
                                exchange=self.exchange, channel=1)
             return
@@ -283,22 +343,14 @@ class HotPath:
     # ------------------------------------------------------------------
     # host-facing API: pinned host batches in, pinned host results out
     # ------------------------------------------------------------------
-    RESULT_KEYS = ("latents", "pixel_planes", "rgb", "featcat", "label_small", "rgb_up", "mask_tissue",
-                   "mask_cell", "confusion")
+    RESULT_KEYS = ("latents", "pixel_planes", "rgb", "featcat", "label_small", "mask_tissue", "mask_cell", "confusion")
 
     def _host_state(self, like: "HotPathInputs"):
         st = getattr(self, "_hs", None)
         if st is None:
             dev = self.device
-
-            def mirror(f):
-                return [torch.empty_like(t, device=dev) for t in f] if isinstance(f, list) \
-                    else torch.empty_like(f, device=dev)
-
             st = {
-                "in": [HotPathInputs(*[mirror(f) for f in (like.latents, like.eps, like.decoded, like.head_feat,
-                                                           like.inst_map, like.inst_feats, like.gt)])
-                       for _ in range(2)],
+                "in": [like.packed(device=dev) for _ in range(2)],          # two device-side input slabs
                 "s_in": torch.cuda.Stream(dev), "s_run": torch.cuda.Stream(dev), "s_out": torch.cuda.Stream(dev),
                 "in_ready": [torch.cuda.Event() for _ in range(2)],
                 "in_free": [torch.cuda.Event() for _ in range(2)],
@@ -308,46 +360,55 @@ class HotPath:
         return st
 
     def alloc_host_results(self):
-        res = self.results()
-        return {k: torch.empty(res[k].shape, dtype=res[k].dtype, pin_memory=True) for k in self.RESULT_KEYS}
+        """Pinned host mirror of the result slab: a dict of views by RESULT_KEYS, plus the slab under ``"_slab"``."""
+        slab = torch.empty(self.out_slab.numel(), dtype=torch.uint8, pin_memory=True)
+        out = {name: slab[o:o + nb].view(dt).view(shape) for name, o, nb, shape, dt in self._out_layout}
+        out["_slab"] = slab
+        return out
+
+    def host_bytes_per_step(self, batch: "HotPathInputs"):
+        """(host->device, device->host) bytes ``run_host`` moves per batch."""
+        return batch.nbytes(), sum(nb for _, _, nb, _, _ in self._out_layout)
 
     def run_host(self, batches, host_out, after_run=None):
-        """Process a sequence of host-resident batches (HotPathInputs of pinned CPU
-        tensors); the results of batch i are copied into ``host_out[i % len(host_out)]``.
+        """Process a sequence of host-resident batches; the results of batch i are copied into
+        ``host_out[i % len(host_out)]`` (from ``alloc_host_results``).
 
-        Three streams pipeline the work: while batch i computes, batch i+1 streams
-        host->device into the other input set and batch i-1's results stream
-        device->host, so a long run costs max(H2D, compute, D2H) per batch instead
-        of their sum (PCIe is full duplex).  ``after_run`` (optional) is called on
-        the compute stream after each pass (e.g. the confusion all-reduce)."""
+        A batch from ``HotPathInputs.packed()`` (one pinned slab) moves host->device as ONE copy and the
+        results come back as ONE copy; a plain ``HotPathInputs`` of separate pinned tensors is copied tensor by
+        tensor.  Three streams pipeline the work: while batch i computes, batch i+1 streams host->device into
+        the other input slab and batch i-1's results stream device->host, so a long run costs
+        max(H2D, compute, D2H) per batch instead of their sum (PCIe is full duplex).  ``after_run`` (optional)
+        is called on the compute stream after each pass (e.g. the confusion all-reduce)."""
         st = self._host_state(batches[0])
         s_in, s_run, s_out = st["s_in"], st["s_run"], st["s_out"]
         cur = torch.cuda.current_stream(self.device)
         for s in (s_in, s_run, s_out):
             s.wait_stream(cur)
-        res = self.results()
         for i, hb in enumerate(batches):
             slot = i & 1
+            dst = st["in"][slot]
             with torch.cuda.stream(s_in):
                 if i >= 2:
-                    s_in.wait_event(st["in_free"][slot])          # pass i-2 has consumed this set
-                for src, dst in zip(hb.tensors(), st["in"][slot].tensors()):
-                    dst.copy_(src, non_blocking=True)
+                    s_in.wait_event(st["in_free"][slot])          # pass i-2 has consumed this slab
+                if hb.slab is not None and hb.slab.numel() == dst.slab.numel():
+                    dst.slab.copy_(hb.slab, non_blocking=True)
+                else:
+                    for src, d in zip(hb.tensors(), dst.tensors()):
+                        d.copy_(src, non_blocking=True)
                 st["in_ready"][slot].record(s_in)
             with torch.cuda.stream(s_run):
                 s_run.wait_event(st["in_ready"][slot])
                 if i >= 1:
-                    s_run.wait_event(st["out_done"])              # results of pass i-1 are out of the buffers
-                self.run(st["in"][slot])
+                    s_run.wait_event(st["out_done"])              # results of pass i-1 are out of the slab
+                self.run(dst)
                 if after_run is not None:
                     after_run()
                 st["in_free"][slot].record(s_run)
                 st["run_done"].record(s_run)
             with torch.cuda.stream(s_out):
                 s_out.wait_event(st["run_done"])
-                ho = host_out[i % len(host_out)]
-                for k in self.RESULT_KEYS:
-                    ho[k].copy_(res[k], non_blocking=True)
+                host_out[i % len(host_out)]["_slab"].copy_(self.out_slab, non_blocking=True)
                 st["out_done"].record(s_out)
         for s in (s_in, s_run, s_out):
             cur.wait_stream(s)

@@ -16,6 +16,8 @@ Out of scope and therefore injected: the SD pipeline / fine-tuned UNet loader
 and ``model_factory`` default to the stand-ins of ``ldiffusion_b200.standin`` when
 the real packages are not importable.
 """
+import os
+
 import numpy as np
 import torch
 from PIL import Image
@@ -39,7 +41,12 @@ def _to_tensor_1024(image: Image.Image, device, normalize: bool):
 
 
 class Segmentor:
-    def __init__(self, train_loader, val_loader, level, num_classes, pipeline_loader=None, model_factory=None):
+    _NO_LOADER = ("{what} is outside this package (the SD-v1.5 UNet / VAE and the segmentor networks are cuDNN library "
+                  "calls, SURVEY 8): inject {arg}=..., or pass allow_standins=True to run the hot path on the "
+                  "randomly initialised stand-ins of ldiffusion_b200.standin (results are then meaningless as masks)")
+
+    def __init__(self, train_loader, val_loader, level, num_classes, pipeline_loader=None, model_factory=None,
+                 allow_standins: bool = False):
         if not torch.cuda.is_available():
             raise RuntimeError("ldiffusion_b200.Segmentor needs a CUDA device (no CPU fallback)")
         self.device = torch.device("cuda", torch.cuda.current_device())
@@ -50,6 +57,7 @@ class Segmentor:
         self.ldiffusion_proj = None
         self.pipeline_loader = pipeline_loader
         self.model_factory = model_factory
+        self.allow_standins = bool(allow_standins)
 
     # -- out-of-scope pieces, injected ------------------------------------------
     def load_ldiffusion(self, ldiffusion_weight, diffusion_path):
@@ -57,6 +65,8 @@ class Segmentor:
         replaced by the product scheduler (same duck-type)."""
         if self.pipeline_loader is not None:
             pipeline, unet, vae = self.pipeline_loader(ldiffusion_weight, diffusion_path)
+        elif not self.allow_standins:
+            raise RuntimeError(self._NO_LOADER.format(what="loading the diffusion pipeline", arg="pipeline_loader"))
         else:
             from .standin import StandInPipeline
             pipeline = StandInPipeline(self.device)
@@ -66,12 +76,29 @@ class Segmentor:
             pipeline.scheduler = LaplacePLMSScheduler()
         return pipeline, unet, vae
 
-    def initialize_model(self, level, num_classes):
-        """segmentor.py:62-74."""
+    def initialize_model(self, level, num_classes, segmentor_weight=None):
+        """segmentor.py:62-74, plus the weight loading the reference does right after it
+        (``load_state_dict(torch.load(<segmentor_weight>/cellclassifier.pth))`` at segmentor.py:497; the nnU-Net
+        predictor reads its own folder at :405/:465).  A ``model_factory`` that takes a third argument receives
+        ``segmentor_weight`` and loads it itself; a two-argument factory gets the reference's cell-level load
+        applied to what it returns."""
         if level not in ("tissue", "cell"):
             raise ValueError("Invalid level specified. Choose 'tissue' or 'cell'.")
         if self.model_factory is not None:
-            return self.model_factory(level, num_classes)
+            import inspect
+            try:
+                takes_weight = len(inspect.signature(self.model_factory).parameters) >= 3
+            except (TypeError, ValueError):
+                takes_weight = False
+            if takes_weight:
+                return self.model_factory(level, num_classes, segmentor_weight)
+            model = self.model_factory(level, num_classes)
+            ckpt = os.path.join(str(segmentor_weight), "cellclassifier.pth") if segmentor_weight else None
+            if level == "cell" and ckpt and os.path.exists(ckpt) and hasattr(model, "load_state_dict"):
+                model.load_state_dict(torch.load(ckpt, weights_only=True))
+            return model
+        if not self.allow_standins:
+            raise RuntimeError(self._NO_LOADER.format(what="building the segmentor network", arg="model_factory"))
         from .standin import StandInCellModel, StandInTissueModel
         return (StandInTissueModel if level == "tissue" else StandInCellModel)(num_classes, device=self.device)
 
@@ -109,7 +136,7 @@ class Segmentor:
             latents = sched.scale_model_input(latents, t)
             output = unet(latents, t, text_embeddings)
             latents = sched.step(output[0].contiguous(), t, latents).prev_sample
-            decoded = vae.decode(latents / 0.18215).sample            # decode_latents' first half
+            decoded = vae.decode((1 / 0.18215) * latents).sample      # decode_latents' first half: `1 / 0.18215 * latents`
             if model_input and i == n - 1:
                 rgb, _, mi = ops.decode_tail_model_input(decoded.contiguous())
             else:
@@ -183,7 +210,7 @@ class Segmentor:
     def inference_cell_model(self, image_path, diffusion_path, ldiffusion_weight, segmentor_weight):
         """segmentor.py:490-545 -> (PIL decoded image, uint8 mask [H0,W0])."""
         if self.model is None:
-            self.model = self.initialize_model("cell", self.num_classes)
+            self.model = self.initialize_model("cell", self.num_classes, segmentor_weight)
         pipeline, unet, vae = self.load_ldiffusion(ldiffusion_weight, diffusion_path)
         image = self._load_rgb(image_path)
         width, height = image.size
@@ -213,7 +240,7 @@ class Segmentor:
         segmentor.py:536).  The nnU-Net predictor of the reference is out of scope; the mask comes
         from ``self.model.features`` + ``self.model.head`` through the fused head kernels."""
         if self.model is None:
-            self.model = self.initialize_model("tissue", self.num_classes)
+            self.model = self.initialize_model("tissue", self.num_classes, segmentor_weight)
         pipeline, unet, vae = self.load_ldiffusion(ldiffusion_weight, diffusion_path)
         image = self._load_rgb(image_path)
         width, height = image.size

@@ -93,12 +93,12 @@ _M0, _M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
 _W0, _W1 = np.uint32(0x9E3779B9), np.uint32(0xBB67AE85)
 
 
-def philox4x32_10(counter, key):
-    """counter: uint32 [N,4]; key: uint32 [2] -> uint32 [N,4]."""
+def philox4x32(counter, key, rounds=10):
+    """counter: uint32 [N,4]; key: uint32 [2] -> uint32 [N,4] (Philox4x32-R, Salmon et al. SC'11)."""
     c = np.array(counter, dtype=np.uint32, copy=True)
     k0, k1 = np.uint32(key[0]), np.uint32(key[1])
     with np.errstate(over="ignore"):
-        for _ in range(10):
+        for _ in range(rounds):
             p0 = _M0 * c[:, 0].astype(np.uint64)
             p1 = _M1 * c[:, 2].astype(np.uint64)
             hi0, lo0 = (p0 >> np.uint64(32)).astype(np.uint32), p0.astype(np.uint32)
@@ -109,11 +109,12 @@ def philox4x32_10(counter, key):
     return c
 
 
-def philox_uniform_pm1(n, seed, offset):
-    """The kernel's uniform stream: element i uses word (i % 4) of
-    philox(counter = offset + i // 4, key = seed); with k = word >> 9 (23 bits),
-    u = (2k + 1 - 2^23) * 2^-23: odd multiples of 2^-23, symmetric, never 0 and
-    strictly inside (-1, 1); every step is exact in fp32.  Returns fp32 [n]."""
+def philox4x32_10(counter, key):
+    return philox4x32(counter, key, 10)
+
+
+def philox_words(n, seed, offset, rounds=10):
+    """The kernel's word stream: element i uses word (i % 4) of philox(counter = offset + i // 4, key = seed)."""
     nblk = (n + 3) // 4
     ctr = np.uint64(offset) + np.arange(nblk, dtype=np.uint64)
     counter = np.zeros((nblk, 4), dtype=np.uint32)
@@ -121,12 +122,58 @@ def philox_uniform_pm1(n, seed, offset):
     counter[:, 1] = (ctr >> np.uint64(32)).astype(np.uint32)
     key = np.array([np.uint64(seed) & np.uint64(0xFFFFFFFF), np.uint64(seed) >> np.uint64(32)],
                    dtype=np.uint64).astype(np.uint32)
-    words = philox4x32_10(counter, key).reshape(-1)[:n]
-    k = (words >> np.uint32(9)).astype(np.int64)
-    return (2 * k + 1 - (1 << 23)).astype(np.float32) * np.float32(2.0 ** -23)
+    return philox4x32(counter, key, rounds).reshape(-1)[:n]
 
 
-def laplace_philox(n, scale, seed, offset):
-    """noise the CUDA kernel draws in Philox mode (transform as in rsample)."""
-    u = torch.from_numpy(philox_uniform_pm1(n, seed, offset))
+def philox_uniform_pm1(n, seed, offset, rounds=10):
+    """The kernel's uniform stream: bits [22:0] of a word are the magnitude m (23 bits), bit 31 the sign:
+    u = +- m * 2^-23 — a symmetric 24-bit uniform strictly inside (-1, 1) (u = 0 with probability 2^-23); every
+    step is exact in fp32.  Returns fp32 [n] (a zero keeps its sign bit: -0.0 where bit 31 is set)."""
+    words = philox_words(n, seed, offset, rounds)
+    mag = (words & np.uint32(0x007FFFFF)).astype(np.float32) * np.float32(2.0 ** -23)
+    return np.where(words >> np.uint32(31), -mag, mag).astype(np.float32)
+
+
+def laplace_philox(n, scale, seed, offset, rounds=10, storage="f32"):
+    """noise the CUDA kernel draws in Philox mode.
+
+    ``storage="f32"``: one 32-bit word per element (24-bit symmetric uniform), torch's rsample transform
+    -b * sign(u) * log1p(-|u|) (the noise carries the sign of u, log1p(-|u|) being negative).
+    ``storage="bf16"``: TWO variates per word (see ``philox_half_stream``): 15-bit magnitude + sign, the top
+    magnitude cell refined by a second 23-bit draw (the exponential tail is memoryless), so
+    |noise| = b * (15 ln 2 - ln(1 - m2 * 2^-23)) there.  ``rounds``: 10 by default (LDIFF_TUNE_PHILOX_ROUNDS = 7
+    selects the 7-round stream)."""
+    if storage == "bf16":
+        lg2, neg = philox_half_stream(n, seed, offset, rounds)
+        mag = torch.from_numpy(lg2.astype(np.float64)) * (-float(np.log(2.0))) * float(scale)
+        return (torch.where(torch.from_numpy(neg), -mag, mag)).to(torch.float32)
+    u = torch.from_numpy(philox_uniform_pm1(n, seed, offset, rounds))
     return laplace_from_uniform_chain(u, scale)
+
+
+def philox_half_stream(n, seed, offset, rounds=10):
+    """The bf16-storage stream: element i uses half (i % 2) of word ((i % 8) // 2) of philox(counter = offset + i // 8,
+    key = seed); half 0 = bits [31:16], half 1 = bits [15:0]; in a half, bit 15 is the sign and bits [14:0] the
+    magnitude m: |u| = m * 2^-15.  m = 2^15 - 1 (the top cell) is refined: word 0 of philox(counter with its third
+    word = 1 + (i % 8)) gives m2 = its low 23 bits and log2(1 - |u|) := -15 + log2(1 - m2 * 2^-23).
+    Returns (log2(1 - |u|) as float64 [n], sign-is-negative bool [n])."""
+    ngrp = (n + 7) // 8
+    ctr = np.uint64(offset) + np.arange(ngrp, dtype=np.uint64)
+    counter = np.zeros((ngrp, 4), dtype=np.uint32)
+    counter[:, 0] = ctr.astype(np.uint32)
+    counter[:, 1] = (ctr >> np.uint64(32)).astype(np.uint32)
+    key = np.array([np.uint64(seed) & np.uint64(0xFFFFFFFF), np.uint64(seed) >> np.uint64(32)],
+                   dtype=np.uint64).astype(np.uint32)
+    words = philox4x32(counter, key, rounds)                                   # [ngrp, 4]
+    halves = np.stack([words >> np.uint32(16), words & np.uint32(0xFFFF)], axis=2).reshape(ngrp, 8)
+    halves = halves.reshape(-1)[:n].astype(np.uint32)
+    m = (halves & np.uint32(0x7FFF)).astype(np.float64)
+    neg = (halves >> np.uint32(15)).astype(bool)
+    lg2 = np.log2(1.0 - m * 2.0 ** -15)
+    top = np.nonzero((halves & np.uint32(0x7FFF)) == 0x7FFF)[0]
+    for i in top:                                                              # rare: 2^-15 of the elements
+        c = counter[i // 8].copy()
+        c[2] = np.uint32(1 + (i % 8))
+        m2 = float(philox4x32(c[None, :], key, rounds)[0, 0] & np.uint32(0x007FFFFF))
+        lg2[i] = -15.0 + np.log2(1.0 - m2 * 2.0 ** -23)
+    return lg2, neg

@@ -19,14 +19,22 @@ from .scheduler import PNDMOracle
 
 
 def run_chain(inp, num_classes, head_w, head_b, cell_w, cell_b, feat_size=(64, 64), noise=None,
-              metrics="chain", paint="lut"):
+              metrics="chain", paint="lut", storage=None, spec_lifts=False):
     """inp: an object with the fields of HotPathInputs holding CPU tensors (any
     float dtype; computed in fp32 as the reference does).  ``noise``: optional
     list of injected Laplace noise tensors (else torch's own sampler is used, as
-    at ldiffusion.py:235-236).  Returns a dict of outputs."""
+    at ldiffusion.py:235-236).  Returns a dict of outputs.
+
+    ``storage`` (e.g. torch.bfloat16) emulates a build that STORES every floating tensor it hands from one
+    stage to the next in that type while computing in fp32: each stage's result is rounded once to
+    ``storage`` (and widened again for the next stage), exactly what the CUDA pass does with bf16 buffers —
+    the bf16 pass is then compared bit for bit instead of within a tolerance.  ``spec_lifts``: take the
+    bilinear stages from the pinned-rounding spec tier (``oracle.bilinear.*_spec``) instead of ATen-CPU, whose
+    down-sampling bits depend on its loop specialisation (<= 2 ulp apart)."""
     K = num_classes
     n = len(inp.eps)
     f32 = lambda t: t.to(torch.float32)                                   # noqa: E731
+    st = (lambda t: t.to(storage).to(torch.float32)) if storage is not None else (lambda t: t)   # noqa: E731
     sch = PNDMOracle()
     sch.set_timesteps(n - 1)
     x = f32(inp.latents)
@@ -37,25 +45,31 @@ def run_chain(inp, num_classes, head_w, head_b, cell_w, cell_b, feat_size=(64, 6
     for i, t in enumerate(sch.timesteps):
         # a-1 (ldiffusion.py:233-237)
         if noise is not None:
-            out["noisy"].append(olap.qsample_injected(f32(inp.latents), noise[i]))
+            out["noisy"].append(st(olap.qsample_injected(f32(inp.latents), noise[i])))
         else:
-            out["noisy"].append(olap.qsample_chain(f32(inp.latents), t)[0])
+            out["noisy"].append(st(olap.qsample_chain(f32(inp.latents), t)[0]))
         # a-2 (segmentor.py:102-104)
-        x = sch.step(f32(inp.eps[i]), t, sch.scale_model_input(x, t))
+        x = st(sch.step(f32(inp.eps[i]), t, sch.scale_model_input(x, t)))
         out["lat"].append(x)
         # a-3 (pixel_latent_vector.py:80-86)
         rgb_u8 = odt.decode_tail_chain(inp.decoded[i])
         grays.append(odt.gray_chain(rgb_u8))
         # a-4 (ldiffusion.py:240-247)
-        small = obil.lift_chain(f32(inp.decoded[i]), feat_size)
-        gw = obil.gray_weighted_chain(small)
+        if spec_lifts:
+            small = torch.from_numpy(obil.lift_spec(f32(inp.decoded[i]).numpy(), feat_size))
+            gw = st(torch.from_numpy(obil.gray_weighted_spec(small.numpy())))
+        else:
+            small = obil.lift_chain(f32(inp.decoded[i]), feat_size)
+            gw = st(obil.gray_weighted_chain(small))
+        small = st(small)
         feat = gw if feat is None else torch.cat([feat, gw], dim=1)
     gt = inp.gt
     out["pixel_planes"] = np.stack(grays + [gt.numpy()], axis=1)          # [B,n+1,H,W]
     out["rgb"] = rgb_u8
     out["featcat"] = feat
     out["label_small"] = obil.label_down_chain(gt.unsqueeze(1), feat_size)  # ldiffusion.py:224-226
-    out["rgb_up"] = obil.lift_chain(small, (H, W))                         # ldiffusion.py:251
+    out["rgb_up"] = st(torch.from_numpy(obil.lift_spec(small.numpy(), (H, W))) if spec_lifts
+                       else obil.lift_chain(small, (H, W)))                 # ldiffusion.py:251
     # a-5 tissue (conductor.py:127,135 + segmentor.py:536)
     mask_t, logits = ohead.head_argmax_chain(f32(inp.head_feat), f32(head_w), f32(head_b), (H, W))
     out["logits"] = logits

@@ -24,7 +24,7 @@ def _png(tmp_path, size=(300, 300), seed=0):
 @pytest.mark.parametrize("level,K", [("cell", 11), ("tissue", 7)])
 def test_ldiffusion_model_inference_contract(tmp_path, level, K):
     import ldiffusion_b200 as L
-    model = L.LDiffusionModel("unused", level=level)
+    model = L.LDiffusionModel("unused", level=level, allow_standins=True)
     decoded, mask = model.inference(_png(tmp_path), "unused", "unused", K)
     assert isinstance(decoded, Image.Image) and decoded.size == (300, 300) and decoded.mode == "RGB"
     assert isinstance(mask, np.ndarray) and mask.dtype == np.uint8 and mask.shape == (300, 300)
@@ -41,6 +41,30 @@ def test_invalid_level_raises_value_error(tmp_path):
         L.Segmentor(None, None, "cell", 3).initialize_model("organ", 3)
     with pytest.raises(NotImplementedError):
         L.LDiffusionModel("unused", level="cell").train(None)
+
+
+def test_missing_loaders_raise_instead_of_using_untrained_standins(tmp_path):
+    """a drop-in caller must not silently get masks from randomly initialised stand-ins; injected
+    factories receive ``segmentor_weight``."""
+    import ldiffusion_b200 as L
+    with pytest.raises(RuntimeError, match="allow_standins"):
+        L.LDiffusionModel("unused", level="cell").inference(_png(tmp_path), "w", "s", 11)
+    seen = {}
+
+    def factory(level, num_classes, segmentor_weight):
+        from ldiffusion_b200.standin import StandInCellModel
+        seen["w"] = segmentor_weight
+        return StandInCellModel(num_classes, device="cuda")
+
+    def loader(ldiffusion_weight, diffusion_path):
+        from ldiffusion_b200.standin import StandInPipeline
+        seen["l"] = (ldiffusion_weight, diffusion_path)
+        p = StandInPipeline("cuda")
+        return p, p.unet, p.vae
+
+    m = L.LDiffusionModel("sd-path", level="cell", pipeline_loader=loader, model_factory=factory)
+    m.inference(_png(tmp_path), "ldiff-w", "seg-w", 11)
+    assert seen == {"w": "seg-w", "l": ("ldiff-w", "sd-path")}
 
 
 def test_sampling_loop_matches_oracle_on_captured_tensors():

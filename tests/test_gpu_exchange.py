@@ -139,8 +139,9 @@ def test_two_processes_over_cuda_ipc():
     assert r.stdout.count("EXCHANGE_OK") == 2, r.stdout[-2000:]
 
 
+@pytest.mark.parametrize("mode", ["round-1 launches", "fused pass", "fused pass, fused tissue histogram"])
 @pytest.mark.parametrize("deferred,world", [(False, 1), (True, 1), (True, 2)])
-def test_pass_with_fused_exchange_matches_plain_pass(deferred, world):
+def test_pass_with_fused_exchange_matches_plain_pass(deferred, world, mode):
     """HotPath with the exchange attached (every "rank" its own HotPath and window on the one GPU):
     the summed matrices equal the sum of the plain passes' matrices, eagerly and from replayed CUDA
     graphs.  Ranks that share a GPU run one after the other, so only the deferred reduce (which never
@@ -150,17 +151,28 @@ def test_pass_with_fused_exchange_matches_plain_pass(deferred, world):
     B, H, W, K, n = 2, 256, 256, 11, 5
     kw = dict(dtype=torch.bfloat16, device="cuda", n_instances=50)
     inps = [synth_inputs(B, H, W, K, n, seed=10 + r, **kw) for r in range(world)]
+    # (the push rides as the tail of whichever kernel finishes a matrix: the stand-alone histogram, the fused
+    # paint + histogram, the fused lift + argmax + histogram)
+    hkw = dict(kw) if mode == "round-1 launches" else dict(kw, feat_size=(H // 16, W // 16))
+
+    def make():
+        hp = HotPath(B, H, W, K, n, seed=7, **hkw)
+        assert hp.fused == (mode != "round-1 launches")
+        hp.tissue_hist_fused = mode.endswith("tissue histogram")
+        return hp
+
     plain = []
     for r in range(world):
-        hp = HotPath(B, H, W, K, n, seed=7, **kw)
+        hp = make()
         hp.run(inps[r])
         plain.append(hp.C.clone())
     want = sum(plain)
     g = _group(world, K, 2)
-    hps = [HotPath(B, H, W, K, n, seed=7, **kw) for _ in range(world)]
+    hps = [make() for _ in range(world)]
     for r in range(world):
         hps[r].attach_exchange(g[r], deferred=deferred)
-        assert hps[r].launches_per_pass() == 31
+        assert hps[r].launches_per_pass() == {"round-1 launches": 31, "fused pass": 18,
+                                               "fused pass, fused tissue histogram": 17}[mode]
     for _ in range(3):                                       # eager passes, ranks interleaved
         for r in range(world):
             hps[r].run(inps[r])
@@ -182,6 +194,37 @@ def test_pass_with_fused_exchange_matches_plain_pass(deferred, world):
         for r in range(world):
             assert torch.equal(hps[r].flush_exchange(), want)
         s.synchronize()
+    ops.check_status("cuda")
+    for x in g:
+        x.close()
+
+
+def test_accumulate_over_an_evaluation_and_sum_once():
+    """The reference's schedule: matrices add up over the passes of an evaluation on every rank and are
+    summed across ranks ONCE at its end — here through the stand-alone push (no histogram kernel to ride on)."""
+    from ldiffusion_b200 import ops
+    from ldiffusion_b200.pipeline import HotPath, synth_inputs
+    world, B, H, W, K, n = 3, 2, 256, 256, 11, 5
+    kw = dict(dtype=torch.bfloat16, device="cuda", n_instances=50)
+    g = _group(world, K, 2)
+    want = torch.zeros(2, K + 1, K, dtype=torch.int64, device="cuda")
+    totals = []
+    for r in range(world):
+        hp = HotPath(B, H, W, K, n, seed=7, feat_size=(H // 16, W // 16), **kw)
+        single = HotPath(B, H, W, K, n, seed=7, feat_size=(H // 16, W // 16), **kw)
+        hp.accumulate = True
+        hp.reset_confusion()
+        for p in range(3):
+            inp = synth_inputs(B, H, W, K, n, seed=40 + 10 * r + p, **kw)
+            hp.run(inp)
+            single.run(inp)
+            want += single.C
+        totals.append(hp.C.clone())
+    assert torch.equal(sum(totals), want) and int(want.sum()) == 2 * world * 3 * B * H * W
+    for r in range(world):
+        g[r].push(totals[r])
+    for r in range(world):
+        assert torch.equal(g[r].reduce(), want)
     ops.check_status("cuda")
     for x in g:
         x.close()

@@ -83,7 +83,7 @@ def test_scheduler_step_then_noise_loop_matches_oracle():
 
 @pytest.mark.parametrize("shape", [(2, 3, 64, 64), (1, 3, 48, 80), (2, 3, 1024, 1024), (1, 3, 128, 32)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("tma", [0, 1, 4, 6])
+@pytest.mark.parametrize("tma", [0, 1, 4, 6, 7, 9])
 def test_decode_tail_fused_equals_separate_launches(tune, shape, dtype, tma):
     from ldiffusion_b200 import _cabi
     ops = _ops()

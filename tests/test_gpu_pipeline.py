@@ -26,46 +26,86 @@ def _setup(dtype, seed=7):
     return host, dev, hp
 
 
-def _check(host, hp, dtype):
-    K, n = CFG["num_classes"], CFG["num_steps"]
+def _mask_report(ours, ref_mask, ref_scores, our_scores, what):
+    """Masks against the literal chain: every differing pixel / instance must be one where the REFERENCE's own
+    top-2 score gap is below twice the measured contraction difference (the only way two correct evaluations of the
+    same dot products can order two classes differently).  Returns the mismatch count."""
+    diff = ours != ref_mask
+    n = int(diff.sum())
+    if n:
+        delta = float((our_scores - ref_scores).abs().max())
+        top2 = torch.topk(ref_scores, 2, dim=1).values
+        gap = (top2[:, 0] - top2[:, 1])[diff]
+        assert float(gap.max()) <= 2 * delta + 1e-7, (what, n, float(gap.max()), delta)
+    return n
+
+
+def _check(host, hp, dtype, cfg=None):
+    cfg = cfg or CFG
+    K, n, H, W = cfg["num_classes"], cfg["num_steps"], cfg["height"], cfg["width"]
     res = {k: (v.cpu() if torch.is_tensor(v) else [t.cpu() for t in v]) for k, v in hp.results().items()}
-    ref = run_chain(host, K, hp.head_w.cpu(), hp.head_b.cpu(), hp.cell_w.cpu(), hp.cell_b.cpu())
     exact = dtype == torch.float32
+    # the oracle pass with the build's storage type emulated (fp32 arithmetic, one rounding per stored tensor)
+    # and the pinned-rounding lifts: every floating output below is compared BIT FOR BIT in both dtypes
+    ref = run_chain(host, K, hp.head_w.cpu(), hp.head_b.cpu(), hp.cell_w.cpu(), hp.cell_b.cpu(), feat_size=hp.feat_size,
+                    storage=None if exact else dtype, spec_lifts=True)
     # a-2: latents after the last step
-    if exact:
-        assert torch.equal(res["latents"], ref["lat"][-1])
-    else:
-        torch.testing.assert_close(res["latents"].float(), ref["lat"][-1], rtol=2e-2, atol=2e-2)
-    # a-1: the kernel's own Philox stream, restated on the CPU
+    assert torch.equal(res["latents"].float(), ref["lat"][-1])
+    # a-1: the kernel's own Philox stream, restated on the CPU; bf16: the restated variate to one storage ulp
     blocks = (host.latents.numel() + 3) // 4
     for i, t in enumerate(hp.scheduler._host_timesteps):
-        nz = olap.laplace_philox(host.latents.numel(), hp.scheduler.laplace_scale(t), hp.seed, i * blocks)
+        nz = olap.laplace_philox(host.latents.numel(), hp.scheduler.laplace_scale(t), hp.seed, i * blocks,
+                                 storage="f32" if exact else "bf16")
         want = (host.latents.float().reshape(-1) + nz).reshape(host.latents.shape)
-        torch.testing.assert_close(res["noisy"][i].float(), want, rtol=1e-5 if exact else 1e-2,
-                                   atol=1e-6 if exact else 1e-2)
+        if exact:
+            torch.testing.assert_close(res["noisy"][i], want, rtol=1e-5, atol=1e-6)      # device log vs libm: <= 6e-6
+        else:
+            err = (res["noisy"][i].float() - want).abs()
+            # one bf16 rounding of the sum + the hardware log2's error in the noise (<= 6e-6 relative, 1.7e-7 b absolute)
+            assert (err <= want.abs() * 2.0 ** -8 + nz.abs().reshape(want.shape) * 2e-5 + 3e-7).all()
+            assert (res["noisy"][i].float() != want.to(dtype).float()).float().mean() < 2e-3
     # a-3: integer exact (given the same decoded tensors, fp32 or bf16)
     assert np.array_equal(res["pixel_planes"].numpy(), ref["pixel_planes"])
     assert np.array_equal(res["rgb"].numpy(), ref["rgb"])
-    # a-4
+    # a-4: bit-exact against the spec tier in the storage dtype (and within the 1e-3 contract of the ATen chain)
+    assert torch.equal(res["featcat"].float(), ref["featcat"])
+    assert torch.equal(res["rgb_up"].float(), ref["rgb_up"])
     if exact:
-        want = obil.feature_concat_spec([d.numpy() for d in host.decoded])
-        assert np.array_equal(res["featcat"].numpy(), want)
-        torch.testing.assert_close(res["featcat"], ref["featcat"], rtol=1e-3, atol=1e-6)
-        small = obil.lift_spec(host.decoded[-1].numpy(), (64, 64))
-        assert np.array_equal(res["rgb_up"].numpy(), obil.lift_spec(small, (CFG["height"], CFG["width"])))
-    else:
-        torch.testing.assert_close(res["featcat"].float(), ref["featcat"], rtol=2e-2, atol=2e-2)
+        torch.testing.assert_close(res["featcat"], obil.feature_concat_chain([d for d in host.decoded], hp.feat_size),
+                                   rtol=1e-3, atol=1e-6)
     assert torch.equal(res["label_small"], ref["label_small"])
-    # a-5: logits within tolerance, masks exact given the kernel's own logits
+    # a-5: logits within the 1e-3 contract (summation order is the library's / the tensor core's)
     torch.testing.assert_close(res["logits"], ref["logits"], rtol=1e-3, atol=1e-3)
-    assert np.array_equal(res["mask_tissue"].numpy(),
-                          ohead.lift_argmax_spec(res["logits"].numpy(), (CFG["height"], CFG["width"])))
-    assert (res["mask_cell"] != ref["mask_cell"]).float().mean() < 2e-3   # only if an instance logit flips
-    # a-6: exact given the masks
+    #      tissue mask: bit-exact decision rule on the kernel's own logits ...
+    assert np.array_equal(res["mask_tissue"].numpy(), ohead.lift_argmax_spec(res["logits"].numpy(), (H, W)))
+    #      ... and against the literal chain every differing pixel is a reference near-tie
+    from oracle.bilinear import lift_chain
+    n_t = _mask_report(res["mask_tissue"], ref["mask_tissue"], lift_chain(ref["logits"], (H, W)),
+                       lift_chain(res["logits"], (H, W)), "tissue")
+    #      cell mask: the painted class of an instance changes only if its reference logits are a near-tie
+    n_c = int((res["mask_cell"] != ref["mask_cell"]).sum())
+    if n_c:
+        from oracle.head import cell_classify_chain
+        ours_l = hp_cell_logits(hp, host)
+        for b in range(host.inst_feats.shape[0]):
+            _, ref_l = cell_classify_chain(host.inst_feats[b].float(), hp.cell_w.cpu().float(), hp.cell_b.cpu().float())
+            _mask_report(ours_l[b][:, 1:].argmax(1), ref_l[:, 1:].argmax(1), ref_l[:, 1:], ours_l[b][:, 1:], "cell")
+    # a-6: exact given the masks — ALWAYS; and against the oracle's matrices it differs by exactly the moved pixels
     want_c = np.stack([omet.confusion_matrix(res[m].numpy(), host.gt.numpy(), K) for m in ("mask_tissue", "mask_cell")])
     assert np.array_equal(res["confusion"].numpy(), want_c)
-    if exact and torch.equal(res["mask_tissue"], ref["mask_tissue"]) and torch.equal(res["mask_cell"], ref["mask_cell"]):
+    moved = np.abs(res["confusion"].numpy() - ref["confusion"]).sum(axis=(1, 2))
+    assert moved[0] <= 2 * n_t and moved[1] <= 2 * n_c
+    if n_t == 0 and n_c == 0:
         assert np.array_equal(res["confusion"].numpy(), ref["confusion"])
+    return n_t, n_c
+
+
+def hp_cell_logits(hp, host):
+    """The pass's own instance logits (the kernel can emit them next to the LUT)."""
+    from ldiffusion_b200 import ops
+    lo = torch.empty(host.inst_feats.shape[:2] + (hp.K,), dtype=torch.float32, device="cuda")
+    ops._cell_classify(host.inst_feats.cuda(), hp.cell_w, hp.cell_b, hp.inst_ids, hp.lut.clone(), lo, hp.status)
+    return lo.cpu()
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
@@ -102,23 +142,25 @@ def test_graph_replay_equals_eager():
 
 
 def test_run_host_pipelined_matches_device_pass():
-    from ldiffusion_b200.pipeline import synth_inputs
+    """Packed batches (one pinned slab in, one result slab out per step) and plain per-tensor batches."""
+    from ldiffusion_b200.pipeline import HotPathInputs, synth_inputs
     host, dev, hp = _setup(torch.bfloat16, seed=13)
     hosts = [synth_inputs(CFG["batch"], CFG["height"], CFG["width"], CFG["num_classes"], CFG["num_steps"],
                           dtype=torch.bfloat16, device="cpu", head_hw=(8, 8), n_instances=CFG["n_instances"],
                           seed=20 + i, pin=True) for i in range(3)]
-    outs = [hp.alloc_host_results() for _ in range(3)]
-    hp.run_host(hosts, outs)
-    torch.cuda.synchronize()
-    for hb, out in zip(hosts, outs):
-        from ldiffusion_b200.pipeline import HotPathInputs
-        d = HotPathInputs(*[([t.cuda() for t in f] if isinstance(f, list) else f.cuda())
-                            for f in (hb.latents, hb.eps, hb.decoded, hb.head_feat, hb.inst_map, hb.inst_feats, hb.gt)])
-        hp.run(d)
+    for batches in ([h.packed(pin=True) for h in hosts], hosts):
+        outs = [hp.alloc_host_results() for _ in range(3)]
+        hp.run_host(batches, outs)
         torch.cuda.synchronize()
-        res = hp.results()
-        for k in hp.RESULT_KEYS:
-            assert torch.equal(out[k], res[k].cpu()), k
+        h2d, d2h = hp.host_bytes_per_step(batches[0])
+        assert h2d == hosts[0].nbytes() and d2h == sum(outs[0][k].numel() * outs[0][k].element_size() for k in hp.RESULT_KEYS)
+        for hb, out in zip(hosts, outs):
+            d = HotPathInputs(*[([t.cuda() for t in f] if isinstance(f, list) else f.cuda()) for f in hb.fields()])
+            hp.run(d)
+            torch.cuda.synchronize()
+            res = hp.results()
+            for k in hp.RESULT_KEYS:
+                assert torch.equal(out[k], res[k].cpu()), k
 
 
 # ---- BASELINE.json configs as parity cases ---------------------------------------------------------
@@ -213,31 +255,47 @@ def test_sampler_stress_config():
     assert torch.equal(out.cpu(), x)
 
 
-def test_pass_full_size_patches():
-    """BASELINE configs[1] geometry (1024x1024, K=11, 5 steps, bf16, 800 instances) on 2 patches:
-    every integer output of the pass equals the oracle pipeline; masks equal the pinned decision
-    rule on the kernel's own logits."""
+@pytest.mark.parametrize("geom", ["configs[1] 1024^2 K=11", "configs[2] 1024^2 K=6 B=8", "configs[0] 1x512^2 K=11"])
+def test_pass_at_baseline_config_geometries(geom):
+    """BASELINE configs 0 / 1 / 2 at their own geometry (bf16, 5 steps; configs[1] on 2 of its 8 patches to keep the
+    CPU oracle short): every stored output bit-exact against the storage-emulating oracle, masks exact on the kernel's
+    own logits and reference-near-ties against the literal chain, confusion matrices exact."""
     from ldiffusion_b200 import ops
     from ldiffusion_b200.pipeline import HotPath, HotPathInputs, synth_inputs
-    B, H, W, K, n = 2, 1024, 1024, 11, 5
-    host = synth_inputs(B, H, W, K, n, dtype=torch.bfloat16, device="cpu", seed=99)
-    dev = HotPathInputs(*[([t.cuda() for t in f] if isinstance(f, list) else f.cuda())
-                          for f in (host.latents, host.eps, host.decoded, host.head_feat, host.inst_map,
-                                    host.inst_feats, host.gt)])
-    hp = HotPath(B, H, W, K, n, dtype=torch.bfloat16, device="cuda", seed=99)
+    cfg = {"configs[1] 1024^2 K=11": dict(batch=2, height=1024, width=1024, num_classes=11, num_steps=5, n_instances=800, head=(32, 32)),
+           "configs[2] 1024^2 K=6 B=8": dict(batch=8, height=1024, width=1024, num_classes=6, num_steps=5, n_instances=800, head=(32, 32)),
+           "configs[0] 1x512^2 K=11": dict(batch=1, height=512, width=512, num_classes=11, num_steps=5, n_instances=200, head=(16, 16))}[geom]
+    head = cfg.pop("head")
+    B, H, W, K, n = cfg["batch"], cfg["height"], cfg["width"], cfg["num_classes"], cfg["num_steps"]
+    host = synth_inputs(B, H, W, K, n, dtype=torch.bfloat16, device="cpu", head_hw=head, n_instances=cfg["n_instances"], seed=99)
+    dev = HotPathInputs(*[([t.cuda() for t in f] if isinstance(f, list) else f.cuda()) for f in host.fields()])
+    hp = HotPath(dtype=torch.bfloat16, device="cuda", seed=99, head_hw=head, feat_size=(H // 16, W // 16), **cfg)
+    assert hp.fused
     hp.run(dev)
     torch.cuda.synchronize()
     ops.check_status("cuda")
-    res = hp.results()
-    ref = run_chain(host, K, hp.head_w.cpu(), hp.head_b.cpu(), hp.cell_w.cpu(), hp.cell_b.cpu(), metrics="none")
-    assert np.array_equal(res["pixel_planes"].cpu().numpy(), ref["pixel_planes"])
-    assert np.array_equal(res["rgb"].cpu().numpy(), ref["rgb"])
-    assert torch.equal(res["label_small"].cpu(), ref["label_small"])
-    torch.testing.assert_close(res["logits"].cpu(), ref["logits"], rtol=1e-3, atol=1e-3)
-    mt = res["mask_tissue"].cpu().numpy()
-    assert np.array_equal(mt, ohead.lift_argmax_spec(res["logits"].cpu().numpy(), (H, W)))
-    assert (mt != ref["mask_tissue"].numpy()).mean() < 1e-4              # logits differ by summation order only
-    assert (res["mask_cell"].cpu() != ref["mask_cell"]).float().mean() < 2e-3
-    want = np.stack([omet.confusion_matrix(res[m].cpu().numpy(), host.gt.numpy(), K) for m in ("mask_tissue", "mask_cell")])
-    assert np.array_equal(res["confusion"].cpu().numpy(), want)
-    assert int(res["confusion"].sum()) == 2 * B * H * W
+    n_t, n_c = _check(host, hp, torch.bfloat16, cfg)
+    assert n_t <= 1e-4 * B * H * W and n_c <= 2e-3 * B * H * W          # (reported; each one is proven a near-tie in _check)
+    assert int(hp.results()["confusion"].sum()) == 2 * B * H * W
+
+
+def test_eager_gpu_baseline_chain_matches_cpu_oracle():
+    """bench.py's eager-PyTorch-on-the-GPU baseline (oracle/eager_gpu.py) computes what the CPU oracle computes:
+    integer outputs identical, floating outputs to fp32 library tolerance, masks equal up to contraction-order
+    near-ties."""
+    from oracle import eager_gpu
+    host, dev, hp = _setup(torch.float32, seed=21)
+    w = (hp.head_w, hp.head_b, hp.cell_w, hp.cell_b)
+    got = eager_gpu.run_chain(dev, CFG["num_classes"], *w, ieee_fp32=True)
+    ref = run_chain(host, CFG["num_classes"], *[t.cpu() for t in w], metrics="none")
+    assert np.array_equal(got["pixel_planes"].cpu().numpy(), ref["pixel_planes"])
+    assert np.array_equal(got["rgb"].cpu().numpy(), ref["rgb"])
+    assert torch.equal(got["label_small"].cpu(), ref["label_small"])
+    assert torch.equal(got["lat"][-1].cpu(), ref["lat"][-1]) or torch.allclose(got["lat"][-1].cpu(), ref["lat"][-1], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(got["featcat"].cpu(), ref["featcat"], rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(got["logits"].cpu(), ref["logits"], rtol=1e-4, atol=1e-4)
+    assert (got["mask_tissue"].cpu() != ref["mask_tissue"]).float().mean() < 1e-3
+    assert (got["mask_cell"].cpu() != ref["mask_cell"]).float().mean() < 5e-3
+    K = CFG["num_classes"]
+    want_c = np.stack([omet.confusion_matrix(got[m].cpu().numpy(), host.gt.numpy(), K) for m in ("mask_tissue", "mask_cell")])
+    assert np.array_equal(got["confusion"].cpu().numpy(), want_c)

@@ -52,23 +52,43 @@ def test_qsample_philox_stream_matches_restatement(n):
     assert torch.equal(got, nz)                      # x == 0 -> out == noise
 
 
-def test_qsample_philox_distribution():
-    """E|x| = b, Var = 2 b^2, symmetric, tail bounded by -b ln(2^-23)."""
+@pytest.fixture
+def philox_rounds():
+    from ldiffusion_b200 import _cabi
+    lib = _cabi.lib()
+    yield lambda r: lib.ldiff_tune(_cabi.TUNE_PHILOX_ROUNDS, r)
+    lib.ldiff_tune(_cabi.TUNE_PHILOX_ROUNDS, 0)
+
+
+@pytest.mark.parametrize("rounds", [10, 7])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_qsample_philox_distribution(philox_rounds, rounds, dtype):
+    """Both round counts of the stream (10: the default, 7: LDIFF_TUNE_PHILOX_ROUNDS), both storage types (fp32: a
+    24-bit uniform per word; bf16: two 16-bit variates per word with the refined top cell): E|x| = b, Var = 2 b^2, symmetric, tail bounded by b * 23 ln 2, Kolmogorov-Smirnov against the Laplace
+    CDF, tail mass beyond 6 b, independence of disjoint counter ranges."""
+    philox_rounds(rounds)
     b, n = 0.9166153, 1 << 22
-    _, nz = _ops().laplace_qsample(torch.zeros(n, device="cuda"), b, seed=7, return_noise=True)
+    _, nz = _ops().laplace_qsample(torch.zeros(n, device="cuda", dtype=dtype), b, seed=7, return_noise=True)
     nz = nz.double().cpu().numpy()
-    assert abs(np.abs(nz).mean() / b - 1) < 5e-3
-    assert abs(nz.var() / (2 * b * b) - 1) < 1e-2
+    tol = 1.0 if dtype == torch.float32 else 1.5            # bf16 storage rounds every variate to 8 bits
+    assert abs(np.abs(nz).mean() / b - 1) < 5e-3 * tol
+    assert abs(nz.var() / (2 * b * b) - 1) < 1e-2 * tol
     assert abs(nz.mean()) < 5e-3
-    assert np.abs(nz).max() <= -b * np.log(2.0 ** -23) * (1 + 1e-6)
-    # Kolmogorov-Smirnov against the Laplace CDF
+    assert np.abs(nz).max() <= -b * np.log(2.0 ** (-23 if dtype == torch.float32 else -38)) * (1 + 2.0 ** -7)
     xs = np.sort(nz)
     cdf = np.where(xs < 0, 0.5 * np.exp(xs / b), 1 - 0.5 * np.exp(-xs / b))
     ks = np.abs(cdf - (np.arange(n) + 0.5) / n).max()
-    assert ks < 2.0 / np.sqrt(n)
-    # different offsets give different, uncorrelated draws
-    _, nz2 = _ops().laplace_qsample(torch.zeros(n, device="cuda"), b, seed=7, offset=n // 4, return_noise=True)
+    assert ks < (2.0 / np.sqrt(n) if dtype == torch.float32 else 6e-3)   # (bf16: the storage grid itself is a 2^-9 step)
+    tail = (np.abs(nz) > 6 * b).mean()
+    assert abs(tail / np.exp(-6.0) - 1) < 0.05                           # P(|x| > 6b) = e^-6
+    _, nz2 = _ops().laplace_qsample(torch.zeros(n, device="cuda", dtype=dtype), b, seed=7, offset=n // 4, return_noise=True)
     assert abs(np.corrcoef(nz, nz2.double().cpu().numpy())[0, 1]) < 5e-3
+    # and the stream is the restated one for this round count
+    want = olap.laplace_philox(4096, b, 7, 0, rounds=rounds, storage="f32" if dtype == torch.float32 else "bf16")
+    if dtype == torch.float32:
+        torch.testing.assert_close(torch.from_numpy(nz[:4096]).float(), want, rtol=2e-5, atol=1e-7)
+    else:
+        assert ((torch.from_numpy(nz[:4096]).float() - want).abs() <= want.abs() * (2.0 ** -8 + 2e-5) + 3e-7).all()
 
 
 def test_qsample_bf16_storage():
@@ -86,7 +106,7 @@ def test_qsample_philox_bf16_storage():
     n, seed, offset, b = 65536 + 24, 99, 3, 0.9166153
     got, nz = _ops().laplace_qsample(torch.zeros(n, device="cuda", dtype=torch.bfloat16), b, seed=seed,
                                      offset=offset, return_noise=True)
-    want = olap.laplace_philox(n, b, seed, offset)
+    want = olap.laplace_philox(n, b, seed, offset, storage="bf16")   # two 16-bit variates per word
     err = (nz.float().cpu() - want).abs()
     assert (err <= want.abs() * (2.0 ** -8 + 2e-5) + 3e-7).all()
     big = want.abs() > 1e-6

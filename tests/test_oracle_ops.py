@@ -123,13 +123,19 @@ def test_philox_known_answers():
     for c, k, o in kat:
         r = olap.philox4x32_10(np.array([c], np.uint32), np.array(k, np.uint32))[0]
         assert tuple(int(x) for x in r) == o
+    # Philox4x32-7 (the bf16 storage default): Random123's published known-answer vector for the all-zero input
+    r7 = olap.philox4x32(np.zeros((1, 4), np.uint32), np.zeros(2, np.uint32), rounds=7)[0]
+    assert tuple(int(x) for x in r7) == (0x5f6fb709, 0x0d893f64, 0x4f121f81, 0x4f730a48)
 
 
 def test_philox_uniform_properties():
-    u = olap.philox_uniform_pm1(1 << 18, 99, 3)
-    assert u.dtype == np.float32 and np.abs(u).max() < 1 and np.abs(u).min() >= 2.0 ** -23
-    assert abs(float(u.mean())) < 5e-3 and abs(float(np.abs(u).mean()) - 0.5) < 5e-3
-    assert np.array_equal(olap.philox_uniform_pm1(100, 99, 3)[4:], olap.philox_uniform_pm1(96, 99, 4))
+    for rounds in (10, 7):
+        u = olap.philox_uniform_pm1(1 << 18, 99, 3, rounds)
+        assert u.dtype == np.float32 and np.abs(u).max() < 1            # sign-magnitude: |u| = m * 2^-23, m < 2^23
+        assert abs(float(u.mean())) < 5e-3 and abs(float(np.abs(u).mean()) - 0.5) < 5e-3
+        assert abs(float(np.signbit(u).mean()) - 0.5) < 5e-3
+        assert np.array_equal(olap.philox_uniform_pm1(100, 99, 3, rounds)[4:], olap.philox_uniform_pm1(96, 99, 4, rounds))
+    assert not np.array_equal(olap.philox_uniform_pm1(64, 99, 3, 10), olap.philox_uniform_pm1(64, 99, 3, 7))
 
 
 def test_laplace_transform_matches_torch_distributions_golden():

@@ -49,7 +49,7 @@ planes = torch.empty(B, 6, H, W, dtype=torch.uint8, device=dev)
 rgb = torch.empty(B, H, W, 3, dtype=torch.uint8, device=dev)
 featc = torch.empty(B, 5, 64, 64, dtype=torch.bfloat16, device=dev)
 lsmall = torch.empty(B, 1, 64, 64, dtype=torch.uint8, device=dev)
-for tma in (0, 1, 2, 3, 4):
+for tma in (0, 4, 6, 7, 8, 9, 10):
     lib.ldiff_tune(_cabi.TUNE_DECODE_TAIL_TMA, tma)
     line(f"decode_tail_gray bf16 tma={tma}",
          timeit(lambda i: ops.decode_tail_gray(imgs[i], want_rgb=False, gray_out=planes[:, i % 5]), 6), px * 7)
@@ -58,7 +58,7 @@ for tma in (0, 1, 2, 3, 4):
     line(f"decode_tail_fused(+feat+rgb+label) bf16 tma={tma}",
          timeit(lambda i: ops.decode_tail_fused(imgs[i], planes[:, i % 5], rgb_out=rgb, feat_out=featc, feat_channel=i % 5,
                                                 label=gt, label_plane_out=planes[:, 5], label_small_out=lsmall), 6), px * 12)
-lib.ldiff_tune(_cabi.TUNE_DECODE_TAIL_TMA, 1)
+lib.ldiff_tune(_cabi.TUNE_DECODE_TAIL_TMA, 6)
 
 # sampler: two launches vs one
 n = B * 4 * 128 * 128
@@ -69,3 +69,11 @@ line("plms4 + laplace (2 launches) bf16 2MiB",
 line("plms_step_noise mode 4 (1 launch) bf16 2MiB",
      timeit(lambda i: ops.plms_step_noise(xs[0], xs[1:5], 4, 1.0, -0.1, 0.5, xs[5], 0.5, seed=1, out=o1, noisy_out=o2), 1), n * 2 * 8)
 ops.check_status(dev)
+
+big = [torch.randn(1 << 27, device=dev).bfloat16() for _ in range(3)]
+ob = torch.empty_like(big[0])
+for r in (10, 7):
+    lib.ldiff_tune(_cabi.TUNE_PHILOX_ROUNDS, r)
+    line(f"laplace_qsample bf16 256 MiB, Philox4x32-{r}", timeit(lambda i: ops.laplace_qsample(big[i], 0.7, seed=1, offset=i, out=ob), 3, iters=20),
+         2 * big[0].numel() * 2)
+lib.ldiff_tune(_cabi.TUNE_PHILOX_ROUNDS, 0)
