@@ -23,33 +23,43 @@ import torch
 from . import ops
 
 
+# The two set-up helpers below must return exactly the values of nnU-Net v2's functions of the same name
+# (nnunetv2/inference/sliding_window_prediction.py, (c) Division of Medical Image Computing, DKFZ, Apache-2.0): the
+# gaussian importance map and the tile origins decide which pixels a tile contributes to and with what weight, so
+# any other arithmetic would change masks.  They are restated here (golden vectors from the vendored functions pin
+# them in tests/golden/nnunet_sliding.npz); the accumulation itself is this package's CUDA kernels.
 def compute_gaussian(tile_size: Sequence[int], sigma_scale: float = 1. / 8, value_scaling_factor: float = 1,
                      dtype=torch.float16, device="cuda") -> torch.Tensor:
-    """sliding_window_prediction.py:10-29."""
+    """Importance map of one tile: a unit impulse at the tile centre blurred with sigma = sigma_scale * extent per
+    axis, scaled so that its maximum is ``value_scaling_factor``, zeros (fp16 underflow at the corners) lifted to the
+    smallest non-zero weight so the later division by the summed weights never sees 0."""
     from scipy.ndimage import gaussian_filter
-    tmp = np.zeros(tuple(tile_size))
-    tmp[tuple(i // 2 for i in tile_size)] = 1
-    g = gaussian_filter(tmp, [i * sigma_scale for i in tile_size], 0, mode="constant", cval=0)
-    g = torch.from_numpy(g)
-    g = g / torch.max(g) * value_scaling_factor
-    g = g.type(dtype).to(device)
-    g[g == 0] = torch.min(g[g != 0])            # the map must not be 0 (nan after normalisation)
-    return g
+    shape = tuple(int(t) for t in tile_size)
+    impulse = np.zeros(shape)
+    impulse[tuple(t // 2 for t in shape)] = 1
+    blurred = gaussian_filter(impulse, [t * sigma_scale for t in shape], 0, mode="constant", cval=0)
+    weights = torch.from_numpy(blurred)
+    weights = (weights / torch.max(weights) * value_scaling_factor).type(dtype).to(device)
+    positive = weights != 0
+    weights[~positive] = torch.min(weights[positive])
+    return weights
 
 
 def compute_steps_for_sliding_window(image_size: Sequence[int], tile_size: Sequence[int],
                                      tile_step_size: float) -> List[List[int]]:
-    """sliding_window_prediction.py:32-56."""
-    assert all(i >= j for i, j in zip(image_size, tile_size)), "image size must be as large or larger than patch_size"
-    assert 0 < tile_step_size <= 1, "step_size must be larger than 0 and smaller or equal to 1"
-    target = [i * tile_step_size for i in tile_size]
-    num_steps = [int(np.ceil((i - k) / j)) + 1 for i, j, k in zip(image_size, target, tile_size)]
-    steps = []
-    for dim in range(len(tile_size)):
-        max_step = image_size[dim] - tile_size[dim]
-        actual = max_step / (num_steps[dim] - 1) if num_steps[dim] > 1 else 99999999999
-        steps.append([int(np.round(actual * i)) for i in range(num_steps[dim])])
-    return steps
+    """Tile origins per axis: the fewest tiles whose stride does not exceed ``tile_step_size`` tiles, spread evenly so
+    that the first tile starts at 0 and the last one ends at the image border."""
+    if any(i < t for i, t in zip(image_size, tile_size)):
+        raise AssertionError("every image extent must be at least the tile extent")
+    if not 0 < tile_step_size <= 1:
+        raise AssertionError("tile_step_size must lie in (0, 1]")
+    origins = []
+    for extent, tile in zip(image_size, tile_size):
+        count = int(np.ceil((extent - tile) / (tile * tile_step_size))) + 1
+        last = extent - tile
+        stride = last / (count - 1) if count > 1 else 0.0      # (one tile: its origin is 0 whatever the stride)
+        origins.append([int(np.round(stride * i)) for i in range(count)])
+    return origins
 
 
 def tta_merge(preds: Sequence[torch.Tensor], flips: Sequence[int], out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -38,6 +38,20 @@ def main():
             dist.all_reduce(ref)
             assert torch.equal(out, ref), f"rank {rank} step {step}: exchange != NCCL all-reduce"
             assert int(out.sum()) == 2 * n * world
+    # once-per-evaluation sum through the stand-alone push, against NCCL
+    total = torch.randint(0, 1 << 40, (2, K + 1, K), device=dev, dtype=torch.int64, generator=gen)
+    ref = total.clone()
+    dist.all_reduce(ref)
+    assert torch.equal(x.allreduce(total), ref), f"rank {rank}: push + reduce != NCCL all-reduce"
+    # per-image metrics need the per-tile matrices: one all_gather in global tile order (evaluate.py:95-102)
+    from ldiffusion_b200.dist import gather_tile_confusions, shard_tiles
+    n_tiles = 7
+    mine = shard_tiles(n_tiles, rank, world)
+    local = torch.stack([torch.full((K + 1, K), 1000 * t + 1, dtype=torch.int64, device=dev) for t in mine])
+    allm = gather_tile_confusions(local, n_tiles)
+    assert allm.shape == (n_tiles, K + 1, K)
+    for t in range(n_tiles):
+        assert int(allm[t, 0, 0]) == 1000 * t + 1 and int(allm[t].min()) == int(allm[t].max())
     ops.check_status(dev)
     dist.barrier()
     x.close()

@@ -253,3 +253,27 @@ def test_tiling_config_through_the_exchange(world):
     ops.check_status("cuda")
     for x in g:
         x.close()
+
+
+@pytest.mark.skipif(torch.cuda.is_available() and torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_devices_in_one_process():
+    """Launch attributes (the 75 KB tcgen05 head, the bulk-TMA decode tails) and the SM count are kept PER DEVICE:
+    the same process drives cuda:0 and cuda:1 and gets the oracle's answers on both (a process-wide
+    `static bool attr_set` made the head fail on a second device)."""
+    from oracle import head as ohead
+    from ldiffusion_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    feat = torch.randn(1, 256, 8, 16, generator=g).bfloat16()
+    w = (torch.randn(11, 256, generator=g) / 16).bfloat16()
+    img = torch.empty(1, 3, 64, 64).uniform_(-1.2, 1.2, generator=g).bfloat16()
+    outs = []
+    for dev in ("cuda:0", "cuda:1", "cuda:0"):
+        with torch.cuda.device(dev):
+            mask, logits = ops.head_argmax(feat.to(dev), w.to(dev), None, (256, 512), return_logits=True)
+            assert np.array_equal(mask.cpu().numpy(), ohead.lift_argmax_spec(logits.cpu().numpy(), (256, 512)))
+            rgb, gray = ops.decode_tail_gray(img.to(dev), want_rgb=True)
+            ops.check_status(dev)
+            outs.append((logits.cpu(), rgb.cpu(), gray.cpu()))
+    for o in outs[1:]:
+        for a, b in zip(outs[0], o):
+            assert torch.equal(a, b)

@@ -30,7 +30,7 @@ def test_blackwell_instructions_are_present(sass):
     _, text = sass
 
     keys = ("UTCHMMA", "UTCBAR", "LDTM", r"UBLKCP\.S\.G", r"SYNCS\.PHASECHK", "FFMA2", "FMNMX3", r"MUFU\.LG2",
-            r"ST[G]?\.E\.64\.STRONG\.SYS")
+            r"ST[G]?\.E\.64\.STRONG\.SYS", r"UTMALDG\.[23]D", r"MUFU\.RCP", r"LDGSTS")
     rx = re.compile(r"\b(?:" + "|".join(f"(?P<g{i}>{k})" for i, k in enumerate(keys)) + ")")
     found = {k: set() for k in keys}
     cur = None
@@ -46,7 +46,9 @@ def test_blackwell_instructions_are_present(sass):
         return found[mnemonic]
 
     tc = per_function("UTCHMMA")
-    assert tc and all("head_logits_tc_kernel" in f for f in tc)                 # tensor cores only in the head
+    assert tc and all("head_logits_tc_kernel" in f or "head_logits_tma_kernel" in f for f in tc)   # tensor cores only in the head
+    tma = per_function(r"UTMALDG\.[23]D")                                       # tensor-map TMA feeds the tcgen05 head
+    assert tma and all("head_logits_tma_kernel" in f for f in tma) and tma <= tc
     assert per_function("UTCBAR") and per_function("LDTM")                      # tcgen05.commit, tcgen05.ld
     bulk = per_function(r"UBLKCP\.S\.G")
     assert any("lift_separable_kernel" in f for f in bulk) and any("decode_tail_tma_kernel" in f for f in bulk)
@@ -54,4 +56,8 @@ def test_blackwell_instructions_are_present(sass):
     assert any("lift_argmax" in f for f in per_function("FFMA2")) and any("lift_argmax" in f for f in per_function("FMNMX3"))
     lg2 = per_function(r"MUFU\.LG2")
     assert any("laplace_qsample_kernel" in f for f in lg2) and any("laplace_qsample_map_kernel" in f for f in lg2)
-    assert any("confusion_hist" in f for f in per_function(r"ST[G]?\.E\.64\.STRONG\.SYS"))   # the peer push
+    push = per_function(r"ST[G]?\.E\.64\.STRONG\.SYS")                        # the peer push rides in all three producers
+    assert all(any(k in f for f in push) for k in ("confusion_hist", "lut_paint_hist", "lift_argmax_env", "xchg_push"))
+    env = [f for f in per_function("FFMA2") if "lift_argmax_env" in f]
+    assert env and any("lift_argmax_env" in f for f in per_function(r"MUFU\.RCP"))   # the envelope sweep's run lengths
+    assert any("lift_argmax_env" in f for f in per_function("LDGSTS"))          # cp.async ground-truth tile
