@@ -284,9 +284,10 @@ def roofline_kernels(torch, ops, _cabi, dev, peak, sets):
             else:                                            # probe: 2 eps keep the footprint at 4 tensors
                 add(f"plms_step (2 eps) {nm} [{tag}]", _timeit(torch, lambda i: ops.plms_step(
                     xs[0], [xs[1], xs[2]], 2, 1.0, -0.1, 0.5, out=o1), 1, iters=20), 4 * n * sz, label)
+                # (the clean latents alias eps[0] to stay at 3 input tensors: 3 reads + 2 writes of n elements)
                 add(f"plms_step_noise (2 eps) {nm} [{tag}]", _timeit(torch, lambda i: ops.plms_step_noise(
                     xs[0], [xs[1], xs[2]], 2, 1.0, -0.1, 0.5, xs[1], 0.7, seed=1, offset=i, out=o1, noisy_out=o2), 1,
-                    iters=20), 6 * n * sz, label)
+                    iters=20), 5 * n * sz, label)
             del xs, o1, o2
     return out
 

@@ -337,23 +337,29 @@ decode_tail_tma_kernel(const T* __restrict__ img, uint8_t* __restrict__ rgb,
   T* buf = reinterpret_cast<T*>(dt_smem);
   const int tid = threadIdx.x;
 
-  // tile t -> image b, first pixel p0, pixel count n (< kDtTile only for the partial tiles of a shifted image)
-  auto tile_of = [&](int t, int& b, int64_t& p0, int& n) {
-    b = tiles_shift >= 0 ? (t >> tiles_shift) : (t / tiles_per_img);
-    const int i = t - b * tiles_per_img;
+  // tile (image b, index i in the image) -> first pixel p0, pixel count n (< kDtTile only for the partial tiles of a
+  // shifted image).  (b, i) of a CTA's tile sequence t = blockIdx.x + k * gridDim.x is carried incrementally — one
+  // division per CTA, not two per tile (257 tiles per image is not a power of two)
+  auto advance = [&](int& b, int& i, int by) {
+    i += by;
+    while (i >= tiles_per_img) { i -= tiles_per_img; ++b; }
+  };
+  auto tile_of = [&](int b, int i, int64_t& p0, int& n) {
     if (!EXTRA || tile_off == 0) { p0 = (int64_t)i * kDtTile; n = kDtTile; return; }
     p0 = i == 0 ? 0 : (int64_t)tile_off + (int64_t)(i - 1) * kDtTile;
     const int64_t p1 = (int64_t)tile_off + (int64_t)i * kDtTile;
     n = (int)((p1 < hw ? p1 : hw) - p0);
   };
   // k-th tile of this CTA -> stage k % kDtStages (one thread issues; completion lands on full[stage])
-  auto issue = [&](int k) {
+  int cb = tiles_shift >= 0 ? ((int)blockIdx.x >> tiles_shift) : ((int)blockIdx.x / tiles_per_img);   // this CTA's first
+  int ci = (int)blockIdx.x - cb * tiles_per_img;                                                       // tile
+  auto issue = [&](int k, int b, int i) {                        // load the CTA's k-th tile = tile i of image b
     const int t = blockIdx.x + k * gridDim.x;
     if (t >= total_tiles) return;
     const int s = k % kDtStages;
-    int b, n;
+    int n;
     int64_t p0;
-    tile_of(t, b, p0, n);
+    tile_of(b, i, p0, n);
     const uint32_t bytes = (uint32_t)n * sizeof(T);
     dt_mbar_expect_tx(&full[s], 3 * bytes);
 #pragma unroll
@@ -377,23 +383,29 @@ decode_tail_tma_kernel(const T* __restrict__ img, uint8_t* __restrict__ rgb,
           dt_mbar_wait(&empty[k % kDtStages], (uint32_t)(k / kDtStages - 1) & 1u);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         }
-        issue(k);
+        issue(k, cb, ci);
+        advance(cb, ci, (int)gridDim.x);
       }
     }
     return;
   }
   if (!PW && tid == 0) {
+    int pb = cb, pi = ci;
 #pragma unroll
-    for (int k = 0; k < kDtStages; ++k) issue(k);
+    for (int k = 0; k < kDtStages; ++k) {
+      issue(k, pb, pi);
+      advance(pb, pi, (int)gridDim.x);
+    }
   }
   for (int k = 0;; ++k) {
     const int t = blockIdx.x + k * gridDim.x;
     if (t >= total_tiles) break;                                 // (block-uniform)
     const int s = k % kDtStages;
-    int bi, n;
+    int n;
     int64_t p0;
-    tile_of(t, bi, p0, n);
-    const int64_t b = bi;
+    tile_of(cb, ci, p0, n);
+    const int64_t b = cb;
+    advance(cb, ci, (int)gridDim.x);
     const bool mine = tid * 16 < n;                              // (partial tiles: the tail threads idle)
     const int64_t p = p0 + tid * 16;
     uint4 lab = make_uint4(0, 0, 0, 0);
@@ -460,7 +472,9 @@ decode_tail_tma_kernel(const T* __restrict__ img, uint8_t* __restrict__ rgb,
       if (tid == 0) {
         // the refill is an async-proxy write over memory just read through the generic proxy
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        issue(k + kDtStages);
+        int nb = cb, ni = ci;                                    // (cb, ci) is tile k + 1 by now
+        advance(nb, ni, (kDtStages - 1) * (int)gridDim.x);
+        issue(k + kDtStages, nb, ni);
       }
     }
   }

@@ -25,11 +25,18 @@ up = torch.empty(B, 3, H, W, dtype=torch.bfloat16, device=dev)
 n = B * 4 * 128 * 128
 xs = [torch.randn(n, device=dev).bfloat16() for _ in range(6)]
 o1, o2 = torch.empty_like(xs[0]), torch.empty_like(xs[0])
+inst_feats = torch.randn(B, 800, 256, device=dev).bfloat16()
+ids = torch.arange(1, 801, dtype=torch.int32, device=dev)
+big = torch.randn(1 << 26, device=dev).bfloat16()
+bigo = torch.empty_like(big)
 for it in range(3):
     logits = ops.head_logits(feat, w, None)
     ops._lift_argmax(logits, mask)
+    ops.confusion_hist(mask.view(-1), gt.view(-1), K, out=C)
     ops.lift_argmax_hist(logits, (H, W), gt, out=C, mask_out=mask)
+    ops.cell_classify(inst_feats, w, None, ids, 801)
     ops.lut_paint_hist(inst, lut, gt, K, out=C, mask_out=mask)
+    ops.laplace_qsample(big, 0.7, seed=1, offset=it, out=bigo)
     ops.decode_tail_fused(imgs[it % 2], planes[:, it], feat_out=featc, feat_channel=it)
     ops.decode_tail_fused(imgs[it % 2], planes[:, it], rgb_out=rgb, feat_out=featc, feat_channel=it, label=gt,
                           label_plane_out=planes[:, 5], label_small_out=lsmall)
