@@ -249,18 +249,20 @@ decode_tail_vec16_kernel(const T* __restrict__ img, uint8_t* __restrict__ rgb,
 }
 
 // ----------------------------------------------------------------------------
-// Bulk-TMA staged form (opt-in through ldiff_tune(LDIFF_TUNE_DECODE_TAIL_TMA) / LDIFF_DT_TMA
-// until it has been measured — round-2 candidate).  Why: the pass experiments of round 1
-// (profiles/r01_pass_persist.txt) show the register-staged kernel above losing bandwidth in proportion to
-// the SMs it is given: its bytes in flight are tied to resident threads (6 blocks x 256 threads x 96 B).
-// Here a persistent CTA keeps kDtStages tiles of 3 x kDtTile pixels in flight through 1-D bulk copies
-// (cp.async.bulk + mbarrier complete_tx; no registers, no address arithmetic per load), and the threads
-// only read shared memory: 72 KB in flight per CTA whatever the occupancy.  Same arithmetic functions as
-// above, so the bytes written are identical by construction.
+// Bulk-TMA staged form: what the pass runs (bf16 default: 2 stages x 2 CTAs per SM; LDIFF_TUNE_DECODE_TAIL_TMA /
+// LDIFF_DT_TMA pick another pipeline shape, 0 = the register-staged kernel above).  Why: the register-staged
+// kernel's bytes in flight are tied to resident threads (6 blocks x 256 threads x 96 B), so inside the pass —
+// where four other chains take SM time — it loses bandwidth in proportion to the issue slots it is denied
+// (profiles/r01_pass_persist.txt).  Here a persistent CTA keeps STAGES tiles of 3 x kDtTile pixels in flight
+// through 1-D bulk copies (cp.async.bulk + mbarrier complete_tx; no registers, no address arithmetic per
+// load) and the threads only read shared memory.  Alone it is SLOWER than the register-staged kernel (11.1 vs
+// 10.1 us for the gray plane of 8 x 1024^2 bf16: one CTA-wide hand-over per tile), inside the pass it is worth
+// 10-17 us (profiles/r02_pass_time.txt).  Same arithmetic functions as above, so the bytes written are
+// identical by construction.
 // ----------------------------------------------------------------------------
 constexpr int kDtTile = 4096;      // pixels per tile = 256 threads x 16 pixels
-// stages in flight: bf16 4 x 3 x 8 KB = 96 KB per CTA, two CTAs per SM; fp32 4 x 3 x 16 KB = 192 KB, one CTA per SM
-// (pipeline shape = template parameters STAGES x CTAS of the kernel; LDIFF_TUNE_DECODE_TAIL_TMA picks one)
+// a stage = 3 planes x 4096 px: 24 KB in bf16, 48 KB in fp32 (pipeline shape = template parameters STAGES x CTAS of
+// the kernel; TmaShapes below lists the selectable ones)
 
 __device__ __forceinline__ uint32_t dt_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void dt_mbar_init(uint64_t* bar, uint32_t count) {
@@ -317,7 +319,7 @@ __device__ __forceinline__ void quant16_staged(const float* p, uint32_t (&q)[16]
 // pixels of each channel from SHARED memory — the feature costs no global load at all.
 // (Round-2 measurements at 8 x 1024^2 bf16, gray only, 2 stages x 3 CTAs: plain 11.3 us; footprints re-read
 // from global by the owning threads 13.4 us; by a dedicated ninth warp 14.9 us (latency-bound, and the label
-// copy through it 25 us); from shared memory: see profiles/.)
+// copy through it 25 us); from shared memory 12.2 us with 2 x 2 — profiles/r02_kbench_fused.txt.)
 // (register cap: 42 for the gray-only forms, 64 with RGB — the CTAs of this kernel are resident for a whole launch,
 // and what they leave of the register file is what the concurrent chains of the pass get to run in)
 // PW: a ninth warp is the PRODUCER (canonical TMA pipeline): it alone waits for a stage to be released (one
