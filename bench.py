@@ -677,7 +677,11 @@ def run_ours(args):
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650",
                          "kernel_us": kernel_us, "algorithmic_bytes_per_launch": alg_bytes,
                          "how": "kernel alone, CUDA-graph of back-to-back launches over 10 rotating "
-                                "[8,3,1024,1024] bf16 inputs (0.5 GB), CUDA events on the launching stream"},
+                                "[8,3,1024,1024] bf16 inputs (0.5 GB), CUDA events on the launching stream",
+                         "note": "the pass runs the bulk-TMA staging of this kernel: alone it is slower than the "
+                                 "register-staged form (roofline_kernels: 0.89 for the gray plane), inside the pass it "
+                                 "is worth 10-17 us per pass (profiles/r02_pass_time.txt) because its bytes in flight "
+                                 "do not depend on the issue slots the four concurrent chains leave it"},
             "pass_roofline": {"algorithmic_bytes_per_pass": pass_bytes,
                               "achieved_gbs": pass_bytes / (ms / args.steps * 1e-3) / 1e9,
                               "frac_of_hbm_peak": pass_bytes / (ms / args.steps * 1e-3) / 1e9 / peak,

@@ -319,6 +319,7 @@ lift_argmax_env_kernel(const float* __restrict__ logits, uint8_t* __restrict__ m
 
     // ---- cold epilogue: the warp's queued pixels, spread over its lanes, through the pinned softmax
     const bool warp_ovf = __any_sync(0xffffffffu, ovf);
+    __syncwarp();                                        // the queue was written by other lanes of this warp
     const int nq = warp_ovf ? 0 : min(s_qn[warp_in_block], kQueue);
     const int xblock = xfirst;
     for (int e = (int)(threadIdx.x & 31); e < nq; e += 32) {

@@ -3,8 +3,7 @@
 
     python tools/launch_shares.py gpurun_out/launches.csv > profiles/rNN_launch_shares.md
 
-A pass starts at the first laplace_qsample launch and is 30 ldiff launches long; the passes at the head of the
-capture are averaged (the tail of the list is the roofline probe's back-to-back decode tails)."""
+The passes at the head of the capture are averaged (the tail of the list is the roofline probe's back-to-back decode tails)."""
 import csv
 import re
 import sys
@@ -28,7 +27,7 @@ def main(path, per_pass=30):
     # passes in the capture = launches of a once-per-pass kernel; the launch order inside a pass is the
     # graph's, not the code's, so kernels are counted over the region of whole passes (everything before
     # the roofline probe, i.e. up to the last launch that is not a decode tail) instead of cut by position
-    P = sum(n.startswith("lift_argmax_kernel") for n, _ in ours)
+    P = sum(n.startswith("lift_argmax") for n, _ in ours)        # (once per pass: the envelope or the per-pixel kernel)
     if P == 0:
         sys.exit("no pass found in the launch list")
     last = max(i for i, (n, _) in enumerate(ours) if not n.startswith("decode_tail"))
@@ -43,7 +42,7 @@ def main(path, per_pass=30):
     print(f"One pass of the hot path as ncu sees it (`{path.split('/')[-1]}`: `ncu --metrics gpu__time_duration.sum "
           f"--clock-control none -c 400 python bench.py --steps 2 --warmup 3`), from the {P} passes in the capture: "
           f"launches per pass x the kernel's mean duration.  ncu serialises the launches and runs them cold, so only "
-          f"the SHARES are meaningful: the live pass is ~136 us because the five chains overlap.\n")
+          f"the SHARES are meaningful: the live pass is shorter because the five chains (and consecutive passes) overlap.\n")
     print("| launches / pass | µs / pass | share | kernel |\n|---|---|---|---|")
     for n, (k, avg) in sorted(table.items(), key=lambda kv: -kv[1][0] * kv[1][1]):
         print(f"| {k} | {k * avg:.1f} | {100 * k * avg / total:.1f}% | `{n}` |")
