@@ -10,7 +10,8 @@
  * Conventions
  *  - every pointer is a DEVICE pointer unless named host_*;
  *  - `stream` is a cudaStream_t passed as void*; every call only enqueues work
- *    on it and returns (no allocation, no synchronisation, no global state);
+ *    on it and returns (no allocation, no synchronisation; the only process-wide state is the ldiff_tune knobs
+ *    below and per-device launch-attribute bookkeeping, so one process may drive several devices);
  *  - `dtype` is LDIFF_F32 / LDIFF_BF16 / LDIFF_U8: the STORAGE type of the
  *    floating tensors; arithmetic is always fp32, in the order documented in
  *    DESIGN.md (bit-exact against oracle/ in fp32);

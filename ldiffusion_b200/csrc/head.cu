@@ -405,18 +405,7 @@ cell_classify_kernel(const T* __restrict__ feats, const T* __restrict__ weight,
       for (int k = 0; k < KT; ++k) v[k] = (k < K) ? acc[k] + (bias ? bias[k] : 0.f) : -INFINITY;
       if (logits_out)
         for (int k = 0; k < K; ++k) logits_out[(int64_t)inst0 * K + k] = v[k];
-      int cls = 0;
-      if (K > 1) {
-        float best = v[1], second = -INFINITY;
-        cls = 1;
-#pragma unroll
-        for (int k = 2; k < KT; ++k)
-          if (k < K) {
-            if (v[k] > best) { second = best; best = v[k]; cls = k; }
-            else second = fmaxf(second, v[k]);
-          }
-        if (__fsub_rn(best, second) <= kTieGap) cls = softmax_argmax_exact<KT>(v, K, 1);
-      }
+      const int cls = cell_decide<KT>(v, K);
       const int img = inst0 / n_per_image;
       const int id = ids[inst0 - img * n_per_image];
       if (id >= 0 && id < lut_size) lut[(int64_t)img * lut_stride + id] = (uint8_t)cls;
@@ -497,6 +486,9 @@ argmax_channels_kernel(const T* __restrict__ x, uint8_t* __restrict__ out, int K
   }
 }
 
+int launch_cell_classify_tc(const void* feats, const void* weight, const float* bias, const int32_t* ids, uint8_t* lut,
+                            int lut_size, int64_t lut_stride, float* logits_out, int n_per_image, int n_total, int Cin,
+                            int K, int64_t* clear, int n_clear, int* status, cudaStream_t st);
 int launch_head_logits_tc(const void* feat, const void* weight, const float* bias, float* logits,
                           int B, int Cin, int K, int hw, int64_t* clear, int n_clear, cudaStream_t st);   // head_tc.cu
 bool lift_argmax_env_ok(int K, int h, int H);                                   // lift_argmax_env.cu
@@ -595,6 +587,11 @@ extern "C" int ldiff_cell_classify(const void* inst_feats, const void* weight, c
   if (!aligned16(inst_feats) || !aligned16(weight)) return LDIFF_EALIGN;
   cudaStream_t st = (cudaStream_t)stream;
   const int n_total = n_per_image * B;
+  if (dtype == LDIFF_BF16) {                             // tensor-core form first (head_tc.cu)
+    const int rc = launch_cell_classify_tc(inst_feats, weight, bias, inst_ids, lut, lut_size, lut_stride, logits_out,
+                                           n_per_image, n_total, Cin, K, clear_i64, n_clear, status, st);
+    if (rc != LDIFF_EUNSUPPORTED) return rc;
+  }
   int grid = (n_total + 3) / 4;                          // 4 warps per block, >= 1 instance per warp
   const int cap = sm_count() * 8;
   if (grid > cap) grid = cap;

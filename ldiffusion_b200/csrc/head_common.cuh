@@ -47,6 +47,23 @@ static __device__ __noinline__ int softmax_argmax_exact(const float (&v)[KT], in
   return best;
 }
 
+// cell form (conductor.py:218-221): softmax(...)[:, 1:] -> top-1 -> +1 is the first argmax over k >= 1 unless two
+// logits are within kTieGap, in which case the pinned softmax decides.  v[k >= K] must be -inf.
+template <int KT>
+__device__ __forceinline__ int cell_decide(const float (&v)[KT], int K) {
+  if (K <= 1) return 0;
+  float best = v[1], second = -INFINITY;
+  int cls = 1;
+#pragma unroll
+  for (int k = 2; k < KT; ++k)
+    if (k < K) {
+      if (v[k] > best) { second = best; best = v[k]; cls = k; }
+      else second = fmaxf(second, v[k]);
+    }
+  if (__fsub_rn(best, second) <= kTieGap) cls = softmax_argmax_exact<KT>(v, K, 1);
+  return cls;
+}
+
 // Cold path taken INSIDE the row loop: the K lifted logits of one pixel by value (the
 // struct travels through the ABI's parameter space, so the hot loop keeps its
 // register allocation), no memory traffic, ~1k instructions.

@@ -25,7 +25,7 @@
 
 #include <cstdlib>
 
-#include "common.cuh"
+#include "head_common.cuh"
 
 namespace ldiff {
 
@@ -332,6 +332,106 @@ head_logits_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   }
 }
 
+// ----------------------------------------------------------------------------
+// Cell form on the same tensor-core path (conductor.py:218-221 for a whole batch): the instance features are
+// [n_total, Cin] row-major, i.e. the A operand is K-major as it lies in memory — one box {64 channels, 128 instances}
+// per 64-channel block lands in the canonical K-major SWIZZLE_128B layout.  D[128 instances, 16 classes]; the thread
+// that reads instance i's 16 accumulator columns adds the bias, takes the pinned decision (cell_decide) and writes
+// the instance's LUT byte.  Replaces a CUDA-core kernel that spent 5.5 M warp instructions (as many as a decode
+// tail) on 18 MFLOP.
+// grid = ceil(n_total / 128), 128 threads; dynamic smem = 1024 + nkb * (16 KB + 2 KB)
+__global__ void __launch_bounds__(128, 1)
+cell_classify_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const float* __restrict__ bias, const int32_t* __restrict__ ids, uint8_t* __restrict__ lut,
+                         int lut_size, int64_t lut_stride, float* __restrict__ logits_out, int n_per_image,
+                         int n_total, int Cin, int K, int* __restrict__ status,
+                         unsigned long long* __restrict__ clear, int n_clear) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full[kMaxKb];
+  __shared__ __align__(8) uint64_t mma_bar;
+  __shared__ uint32_t tmem_base_slot;
+  clear_counters(clear, n_clear);
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int nkb = Cin / kBlockK;
+  uint8_t* sA = smem;                                   // [nkb][128 instances][128 B]
+  uint8_t* sB = smem + (size_t)nkb * 16384;             // [nkb][16 classes][128 B]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = blockIdx.x * kTileM;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&tmem_base_slot)), "n"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x == 32) {
+    for (int kb = 0; kb < nkb; ++kb)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&full[kb])) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mma_bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = tmem_base_slot;
+
+  if (threadIdx.x == 0) {                               // ---- producer + MMA issuer: one thread
+    for (int kb = 0; kb < nkb; ++kb) {
+      const uint32_t bar = smem_u32(&full[kb]);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(16384u + 2048u) : "memory");
+      tma_load_2d(sA + (size_t)kb * 16384, &tmA, kb * kBlockK, row0, bar);     // rows >= n_total arrive as zeros
+      tma_load_2d(sB + (size_t)kb * 2048, &tmB, kb * kBlockK, 0, bar);
+    }
+    uint32_t acc = 0;
+    for (int kb = 0; kb < nkb; ++kb) {
+      mbar_wait_or_trap(smem_u32(&full[kb]), 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t a0 = smem_u32(sA + (size_t)kb * 16384);
+      const uint32_t b0 = smem_u32(sB + (size_t)kb * 2048);
+#pragma unroll
+      for (int k = 0; k < kBlockK / kUmmaK; ++k) {        // advance 32 bytes inside the swizzle atom
+        mma_bf16(tmem_d, make_desc(a0 + k * kUmmaK * 2), make_desc(b0 + k * kUmmaK * 2), acc);
+        acc = 1;
+      }
+    }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                     smem_u32(&mma_bar)) : "memory");
+  }
+  __syncwarp();
+
+  // ---- epilogue: warp w owns TMEM lanes 32w..32w+31 (= instances)
+  mbar_wait_or_trap(smem_u32(&mma_bar), 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t a[16];
+  const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]),
+        "=r"(a[8]), "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  const int inst = row0 + warp * 32 + lane;
+  if (inst < n_total) {
+    float v[kTileN];
+#pragma unroll
+    for (int k = 0; k < kTileN; ++k) v[k] = (k < K) ? __uint_as_float(a[k]) + (bias ? __ldg(bias + k) : 0.f) : -INFINITY;
+    if (logits_out)
+      for (int k = 0; k < K; ++k) logits_out[(int64_t)inst * K + k] = v[k];
+    const int cls = cell_decide<kTileN>(v, K);
+    const int img = inst / n_per_image;
+    const int id = __ldg(ids + (inst - img * n_per_image));
+    if (id >= 0 && id < lut_size) lut[(int64_t)img * lut_stride + id] = (uint8_t)cls;
+    else atomicOr(status, LDIFF_STATUS_INST_RANGE);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(kTmemCols)
+                 : "memory");
+  }
+}
+
 }  // namespace tc
 
 // cuTensorMapEncodeTiled without linking libcuda: fetched once through the runtime
@@ -390,6 +490,51 @@ static int launch_head_logits_tma(const void* feat, const void* weight, const fl
   }
   head_logits_tma_kernel<<<dim3(hw / kTileM, B), 128, smem, st>>>(tmA, tmB, bias, logits, Cin, K, hw,
                                                                   reinterpret_cast<unsigned long long*>(clear), n_clear);
+  return check_launch();
+}
+
+// tensor-core cell classifier; LDIFF_EUNSUPPORTED when the shape / alignment / driver cannot take it (the caller
+// then runs the CUDA-core kernel).  LDIFF_CELL_TC=0 forces the fall-back.
+int launch_cell_classify_tc(const void* feats, const void* weight, const float* bias, const int32_t* ids, uint8_t* lut,
+                            int lut_size, int64_t lut_stride, float* logits_out, int n_per_image, int n_total, int Cin,
+                            int K, int64_t* clear, int n_clear, int* status, cudaStream_t st) {
+  using namespace tc;
+  static const bool off = [] { const char* e = getenv("LDIFF_CELL_TC"); return e && e[0] == '0'; }();
+  if (off || K > kTileN || (Cin % kBlockK) != 0 || Cin / kBlockK > kMaxKb || !aligned16(feats) || !aligned16(weight) ||
+      n_total < 1)
+    return LDIFF_EUNSUPPORTED;
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) return LDIFF_EUNSUPPORTED;
+  alignas(64) CUtensorMap tmA, tmB;
+  const cuuint32_t ones[2] = {1, 1};
+  const cuuint64_t strides[1] = {(cuuint64_t)Cin * 2};
+  {
+    const cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)n_total};
+    const cuuint32_t box[2] = {64, (cuuint32_t)kTileM};            // instances past n_total: zero-filled
+    if (enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(feats), dims, strides, box, ones,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return LDIFF_EUNSUPPORTED;
+  }
+  {
+    const cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)K};
+    const cuuint32_t box[2] = {64, (cuuint32_t)kTileN};
+    if (enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(weight), dims, strides, box, ones,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return LDIFF_EUNSUPPORTED;
+  }
+  const int nkb = Cin / kBlockK;
+  const size_t smem = 1024 + (size_t)nkb * (16384 + 2048);
+  static bool attr_set[kMaxDevices] = {};
+  const int dev = current_device();
+  if (dev < 0 || dev >= kMaxDevices || !attr_set[dev]) {
+    cudaFuncSetAttribute(cell_classify_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (dev >= 0 && dev < kMaxDevices) attr_set[dev] = true;
+  }
+  cell_classify_tma_kernel<<<(n_total + kTileM - 1) / kTileM, 128, smem, st>>>(
+      tmA, tmB, bias, ids, lut, lut_size, lut_stride, logits_out, n_per_image, n_total, Cin, K, status,
+      reinterpret_cast<unsigned long long*>(clear), n_clear);
   return check_launch();
 }
 

@@ -118,6 +118,46 @@ def test_cell_head_and_paint():
     assert np.array_equal(mask[:64, :64], ref.astype(np.uint8))
 
 
+@pytest.mark.parametrize("B,N,K,Cin", [(1, 300, 11, 256), (3, 200, 11, 256), (8, 800, 11, 256), (2, 129, 6, 128),
+                                        (1, 1, 2, 64), (2, 50, 16, 512)])
+def test_cell_classify_tensor_core_form(B, N, K, Cin):
+    """bf16 instance features take the tcgen05 form (head_tc.cu): logits within the tensor-core summation order of the
+    chain on the same bf16 values, the class of every instance is the pinned rule on the kernel's OWN logits, and
+    it agrees with the CUDA-core kernel (fp32 storage of the same values) wherever that kernel's top-2 gap is not a
+    near-tie.  Instance counts that are not multiples of the 128-row tile exercise the zero-filled rows."""
+    g = torch.Generator().manual_seed(100 + N)
+    feats = torch.randn(B, N, Cin, generator=g).bfloat16()
+    w = (torch.randn(K, Cin, generator=g) / 16).bfloat16()
+    b = torch.randn(K, generator=g) * 0.1
+    ids = torch.arange(1, N + 1, dtype=torch.int32)
+    lut, lo = _ops().cell_classify(feats.cuda(), w.cuda(), b.cuda(), ids.cuda(), N + 1, return_logits=True)
+    lut_s, lo_s = _ops().cell_classify(feats.float().cuda(), w.float().cuda(), b.cuda(), ids.cuda(), N + 1,
+                                       return_logits=True)
+    for i in range(B):
+        cls_ref, logits_ref = ohead.cell_classify_chain(feats[i].float(), w.float(), b)
+        torch.testing.assert_close(lo[i].cpu(), logits_ref, rtol=1e-4, atol=1e-4)
+        if K > 1:
+            p = torch.softmax(lo[i].cpu(), 1)[:, 1:]
+            assert np.array_equal(lut[i].cpu().numpy()[1:], (p.argmax(1) + 1).numpy().astype(np.uint8))
+        else:
+            assert not lut[i].any()
+        diff = (lut[i] != lut_s[i]).cpu().numpy()[1:]
+        if diff.any():                                   # only near-ties of the CUDA-core kernel's logits may flip
+            top2 = torch.topk(lo_s[i].cpu()[:, 1:], 2, dim=1).values
+            assert ((top2[:, 0] - top2[:, 1])[torch.from_numpy(diff)] < 1e-4).all()
+        assert lut[i, 0] == 0
+    _ops().check_status(torch.device("cuda"))
+
+
+def test_cell_classify_tensor_core_id_range_error():
+    feats = torch.randn(1, 130, 256).bfloat16().cuda()
+    w = (torch.randn(11, 256) / 16).bfloat16().cuda()
+    ids = torch.arange(1, 131, dtype=torch.int32).cuda()
+    _ops().cell_classify(feats, w, None, ids, 100)       # ids 100..130 do not fit a 100-entry LUT
+    with pytest.raises(RuntimeError):
+        _ops().check_status(torch.device("cuda"))
+
+
 def test_lut_paint_range_error():
     inst = torch.tensor([[0, 1, 5, 2]], dtype=torch.int32).repeat(4, 4).cuda()
     lut = torch.tensor([0, 3, 4], dtype=torch.uint8).cuda()
