@@ -118,6 +118,9 @@ lut_paint_hist_kernel(const int32_t* __restrict__ inst, const uint8_t* __restric
   const int b = blockIdx.y;
   // (global LUT through L1: beats a shared-memory copy at 800 entries — byte-wide 10.5 vs 9.4 us in round 1, and a
   //  nibble-packed shared copy, 100 words, measured 16.0 vs 13.1 us for this kernel on random ids: bank conflicts)
+  // (ptxas re-derives lut + b * lut_stride in front of every byte lookup, 5 instructions; pinning the base in a
+  //  register pair halves the kernel's address arithmetic — and measured +3..6 us per PASS in a same-box A/B
+  //  (tools/ab_pass.sh): the kernel then issues its scattered loads in denser bursts next to the decode tails)
   const uint8_t* l = lut + b * lut_stride;
   const int32_t* in = inst + b * n;
   const uint8_t* g = gt + b * n;
