@@ -244,6 +244,11 @@ def roofline_kernels(torch, ops, _cabi, dev, peak, sets):
     logits = ops.head_logits(sets[0].head_feat, hw_, None)
     add("head_logits (tcgen05)", _timeit(torch, lambda i: ops._head_logits(sets[i].head_feat, hw_, None, logits), 2),
         B * 256 * 32 * 32 * 2 + B * K_ * 32 * 32 * 4, f"{B}x256x32x32 bf16 -> {K_} classes")
+    ids_ = torch.arange(1, NINST + 1, dtype=torch.int32, device=dev)
+    lut_ = torch.zeros(B, NINST + 1, dtype=torch.uint8, device=dev)
+    add("cell_classify (tcgen05)", _timeit(torch, lambda i: ops._cell_classify(
+        sets[i].inst_feats, hw_, None, ids_, lut_, None, ops.status_word(dev)), 2),
+        B * NINST * 256 * 2 + B * NINST, f"{B}x{NINST}x256 bf16 instances -> class LUT")
     mask = torch.empty(B, H, W, dtype=torch.uint8, device=dev)
     Cm = torch.zeros(K_ + 1, K_, dtype=torch.int64, device=dev)
     add("lift_argmax (envelope)", _timeit(torch, lambda i: ops._lift_argmax(logits, mask), 1), px + logits.numel() * 4,
