@@ -46,9 +46,12 @@ def test_blackwell_instructions_are_present(sass):
         return found[mnemonic]
 
     tc = per_function("UTCHMMA")
-    assert tc and all("head_logits_tc_kernel" in f or "head_logits_tma_kernel" in f for f in tc)   # tensor cores only in the head
-    tma = per_function(r"UTMALDG\.[23]D")                                       # tensor-map TMA feeds the tcgen05 head
-    assert tma and all("head_logits_tma_kernel" in f for f in tma) and tma <= tc
+    heads = ("head_logits_tc_kernel", "head_logits_tma_kernel", "cell_classify_tma_kernel")
+    assert tc and all(any(h in f for h in heads) for f in tc)                   # tensor cores only in the two classifier heads
+    assert all(any(h in f for f in tc) for h in heads)
+    tma = per_function(r"UTMALDG\.[23]D")                                       # tensor-map TMA feeds both tcgen05 contractions
+    assert tma and all("head_logits_tma_kernel" in f or "cell_classify_tma_kernel" in f for f in tma) and tma <= tc
+    assert any("cell_classify_tma_kernel" in f for f in tma)
     assert per_function("UTCBAR") and per_function("LDTM")                      # tcgen05.commit, tcgen05.ld
     bulk = per_function(r"UBLKCP\.S\.G")
     assert any("lift_separable_kernel" in f for f in bulk) and any("decode_tail_tma_kernel" in f for f in bulk)
