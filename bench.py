@@ -220,7 +220,8 @@ def roofline_kernels(torch, ops, _cabi, dev, peak, sets):
     lsm = torch.empty(B, 1, H // 16, W // 16, dtype=torch.uint8, device=dev)
     gt, inst = sets[0].gt, [sets[0].inst_map, sets[1].inst_map]
     shape = f"{B}x{H}x{W} bf16"
-    for tma, tag in ((0, "register-staged"), (6, "bulk-TMA 2 stages x 2 CTAs (the pass's form)")):
+    for tma, tag in ((0, "register-staged"), (6, "bulk-TMA 2 stages x 2 CTAs (one pass alone)"),
+                     (11, "bulk-TMA 2 stages x 1 CTA (the ring's form)")):
         lib.ldiff_tune(_cabi.TUNE_DECODE_TAIL_TMA, tma)
         add(f"decode_tail gray [{tag}]", _timeit(torch, lambda i: ops.decode_tail_gray(
             imgs[i], want_rgb=False, gray_out=planes[:, i % NSTEPS]), 10), px * 7, shape)
@@ -576,9 +577,16 @@ def run_ours(args):
     # step's feature, bulk-TMA staged), alone, rotating over 10 decoded tensors (0.5 GB)
     imgs = dev_sets[0].decoded + dev_sets[1].decoded
     featc = torch.empty(B, NSTEPS, H // 16, W // 16, dtype=dt, device=dev)
+    lib = _cabi.lib()
+    lib_shape = lib.ldiff_tune_get(_cabi.TUNE_DECODE_TAIL_TMA)
+    dt_shape = hp.decode_tail_shape if hp.decode_tail_shape is not None else lib_shape
+    lib.ldiff_tune(_cabi.TUNE_DECODE_TAIL_TMA, dt_shape)          # the shape the timed passes launched it in
     kernel_us = _timeit(torch, lambda r: ops.decode_tail_fused(imgs[r % len(imgs)], hp.planes[:, r % NSTEPS],
                                                                feat_out=featc, feat_channel=r % NSTEPS), len(imgs),
                         iters=4 * len(imgs), reps=5)
+    lib.ldiff_tune(_cabi.TUNE_DECODE_TAIL_TMA, lib_shape)
+    shape_name = {0: "register-staged", 6: "2 stages x 2 CTAs/SM", 11: "2 stages x 1 CTA/SM", 12: "3 stages x 1 CTA/SM",
+                  4: "2 stages x 3 CTAs/SM"}.get(dt_shape, f"shape {dt_shape}")
     alg_bytes = B * H * W * (3 * 2 + 1)               # 3 bf16 planes in, 1 gray byte out, per pixel
     peaks = {}
     try:
@@ -661,6 +669,7 @@ def run_ours(args):
     if rank == 0:
         cfg = config(world)
         cfg["passes_in_flight"] = nfly
+        cfg["decode_tail_shape"] = shape_name
         cfg["e2e_transfers"] = ("inputs: one pinned slab per batch (latents, eps x5, decoded x5, head features, instance "
                                 "map + features, gt); results returned to the host: final latents, pixel vectors, uint8 "
                                 "image, both masks, confusion matrices, feature / label maps — the lifted RGB "
@@ -677,16 +686,18 @@ def run_ours(args):
             "gpu_launches": launches_per_pass * args.steps + (2 if eval_xchg is not None else 0),
             "launches_per_pass": launches_per_pass,
             "pass_latency_us": pass_latency_us, "host_binding": numa,
-            "roofline": {"bound": "hbm", "kernel": "decode_tail_tma_kernel<bf16> (gray plane + step feature, 2 stages x 2 CTAs/SM)",
+            "roofline": {"bound": "hbm", "kernel": f"decode_tail_tma_kernel<bf16> (gray plane + step feature, {shape_name})",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650",
                          "kernel_us": kernel_us, "algorithmic_bytes_per_launch": alg_bytes,
                          "how": "kernel alone, CUDA-graph of back-to-back launches over 10 rotating "
                                 "[8,3,1024,1024] bf16 inputs (0.5 GB), CUDA events on the launching stream",
-                         "note": "the pass runs the bulk-TMA staging of this kernel: alone it is slower than the "
-                                 "register-staged form (roofline_kernels: 0.89 for the gray plane), inside the pass it "
-                                 "is worth 10-17 us per pass (profiles/r02_pass_time.txt) because its bytes in flight "
-                                 "do not depend on the issue slots the four concurrent chains leave it"},
+                         "note": "measured in the pipeline shape the timed passes launch it in.  With three passes in "
+                                 "flight that is the SMALLEST shape (2 stages, one CTA per SM): the slowest alone "
+                                 "(roofline_kernels: register-staged 0.89 / 0.78, 2 stages x 2 CTAs 0.81 / 0.77 for the "
+                                 "gray plane / + feature) and the best throughput, because each pass's tails leave "
+                                 "room for the other passes' kernels (89 vs 93 us per pass, profiles/README.md) - "
+                                 "pass_roofline is the figure the headline lives on"},
             "pass_roofline": {"algorithmic_bytes_per_pass": pass_bytes,
                               "achieved_gbs": pass_bytes / (ms / args.steps * 1e-3) / 1e9,
                               "frac_of_hbm_peak": pass_bytes / (ms / args.steps * 1e-3) / 1e9 / peak,

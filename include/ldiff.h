@@ -55,13 +55,18 @@ enum { LDIFF_STATUS_PRED_RANGE = 1, LDIFF_STATUS_INST_RANGE = 2, LDIFF_STATUS_SW
  *  LDIFF_TUNE_DECODE_TAIL_SMS (env LDIFF_DT_SMS, default 0 = all): the register-staged decode tail sizes its
  *    one-wave grid for that many SMs;
  *  LDIFF_TUNE_DECODE_TAIL_TMA (env LDIFF_DT_TMA, default 6): 0 = register-staged decode tail, 1..6 = the
- *    bulk-TMA staged persistent kernel with (stages x CTAs/SM) = (4x2) / (3x3) / (2x4) / (2x3) / (3x2) / (2x2) for bf16;
+ *    bulk-TMA staged persistent kernel with (stages x CTAs/SM) = (4x2) / (3x3) / (2x4) / (2x3) / (3x2) / (2x2) for bf16,
+ *    7..10 = (2x3) / (3x2) / (2x2) / (4x2) with a dedicated producer warp, 11..13 = (2x1) / (3x1) / (4x1): one CTA per
+ *    SM - the slowest alone and the best throughput when three or more passes are in flight (each pass's tails then
+ *    leave room for the other passes' kernels; HotPathRing selects 11 for its slots);
  *  LDIFF_TUNE_PHILOX_ROUNDS (env LDIFF_PHILOX_ROUNDS, default 0 = 10): rounds of the Philox4x32 stream behind the
  *    Laplace noise - THIS knob changes the random stream (not the distribution): 7 = the smallest round count that
  *    passes BigCrush in the Philox paper, anything else = the published default of 10. */
 enum { LDIFF_TUNE_ARGMAX_VARIANT = 0, LDIFF_TUNE_DECODE_TAIL_SMS = 1, LDIFF_TUNE_DECODE_TAIL_TMA = 2,
        LDIFF_TUNE_PHILOX_ROUNDS = 3, LDIFF_TUNE_COUNT = 4 };
 int ldiff_tune(int knob, int value);
+/* the value in effect for `knob` (>= 0), or LDIFF_EINVAL */
+int ldiff_tune_get(int knob);
 
 int ldiff_abi_version(void);
 const char* ldiff_strerror(int code);

@@ -22,6 +22,7 @@ SIGNATURES = {
     "ldiff_strerror": (c_char_p, [c_int]),
     "ldiff_launch_count": (c_int64, []),
     "ldiff_tune": (c_int, [c_int, c_int]),
+    "ldiff_tune_get": (c_int, [c_int]),
     "ldiff_laplace_qsample": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
                                       c_uint64, c_uint64, c_int64, c_int, c_void_p]),
     "ldiff_laplace_qsample_map": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,

@@ -75,6 +75,11 @@ extern "C" int ldiff_tune(int knob, int value) {
   return LDIFF_OK;
 }
 
+extern "C" int ldiff_tune_get(int knob) {
+  if (knob < 0 || knob >= LDIFF_TUNE_COUNT) return LDIFF_EINVAL;
+  return ldiff::tune_get(knob);
+}
+
 extern "C" int ldiff_abi_version(void) { return LDIFF_ABI_VERSION; }
 
 extern "C" int64_t ldiff_launch_count(void) {

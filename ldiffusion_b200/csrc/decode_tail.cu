@@ -325,7 +325,10 @@ __device__ __forceinline__ void quant16_staged(const float* p, uint32_t (&q)[16]
 // PW: a ninth warp is the PRODUCER (canonical TMA pipeline): it alone waits for a stage to be released (one
 // mbarrier arrive per consumer warp) and refills it, so the eight consumer warps never meet at a CTA-wide barrier
 // — each one goes from tile to tile as fast as its own data arrives.
-template <typename T, bool RGB, bool GRAY, bool EXTRA, int STAGES, int CTAS, bool PW = false>
+// EXTRA: 0 = no fused extras, 1 = step feature / small RGB, 2 = those + the label outputs (a compile-time split: the
+// label pointers' per-tile tests and predicated loads were ~20 issued instructions per warp and tile for nothing in the
+// four tails of a pass that carry no label)
+template <typename T, bool RGB, bool GRAY, int EXTRA, int STAGES, int CTAS, bool PW = false>
 __global__ void __launch_bounds__(256 + (PW ? 32 : 0),
                                   (PW ? (RGB ? 3 : 5) : (RGB ? 4 : 6)) > CTAS ? (PW ? (RGB ? 3 : 5) : (RGB ? 4 : 6)) : CTAS)
 decode_tail_tma_kernel(const T* __restrict__ img, uint8_t* __restrict__ rgb,
@@ -346,11 +349,15 @@ decode_tail_tma_kernel(const T* __restrict__ img, uint8_t* __restrict__ rgb,
     i += by;
     while (i >= tiles_per_img) { i -= tiles_per_img; ++b; }
   };
-  auto tile_of = [&](int b, int i, int64_t& p0, int& n) {
-    if (!EXTRA || tile_off == 0) { p0 = (int64_t)i * kDtTile; n = kDtTile; return; }
-    p0 = i == 0 ? 0 : (int64_t)tile_off + (int64_t)(i - 1) * kDtTile;
-    const int64_t p1 = (int64_t)tile_off + (int64_t)i * kDtTile;
-    n = (int)((p1 < hw ? p1 : hw) - p0);
+  // (32-bit, branch-free: an image has fewer than 2^31 pixels — checked by the host; the EXTRA form spent 71 more
+  //  instructions per warp and tile than the plain one on this bookkeeping, a quarter of the kernel)
+  const int hw32 = (int)hw;
+  const int shift_back = (EXTRA && tile_off) ? kDtTile - tile_off : 0;      // tile i starts at i * kDtTile - shift_back
+  auto tile_of = [&](int i, int& p0, int& n) {
+    if (!EXTRA) { p0 = i * kDtTile; n = kDtTile; return; }
+    const int start = i * kDtTile - shift_back;
+    p0 = max(start, 0);
+    n = min(start + kDtTile, hw32) - p0;
   };
   // k-th tile of this CTA -> stage k % kDtStages (one thread issues; completion lands on full[stage])
   int cb = tiles_shift >= 0 ? ((int)blockIdx.x >> tiles_shift) : ((int)blockIdx.x / tiles_per_img);   // this CTA's first
@@ -359,9 +366,8 @@ decode_tail_tma_kernel(const T* __restrict__ img, uint8_t* __restrict__ rgb,
     const int t = blockIdx.x + k * gridDim.x;
     if (t >= total_tiles) return;
     const int s = k % kDtStages;
-    int n;
-    int64_t p0;
-    tile_of(b, i, p0, n);
+    int n, p0;
+    tile_of(i, p0, n);
     const uint32_t bytes = (uint32_t)n * sizeof(T);
     dt_mbar_expect_tx(&full[s], 3 * bytes);
 #pragma unroll
@@ -403,16 +409,19 @@ decode_tail_tma_kernel(const T* __restrict__ img, uint8_t* __restrict__ rgb,
     const int t = blockIdx.x + k * gridDim.x;
     if (t >= total_tiles) break;                                 // (block-uniform)
     const int s = k % kDtStages;
-    int n;
-    int64_t p0;
-    tile_of(cb, ci, p0, n);
+    int n, p0;
+    tile_of(ci, p0, n);
     const int64_t b = cb;
     advance(cb, ci, (int)gridDim.x);
     const bool mine = tid * 16 < n;                              // (partial tiles: the tail threads idle)
-    const int64_t p = p0 + tid * 16;
+    const int p = p0 + tid * 16;                                 // pixel of the image (< 2^31)
     uint4 lab = make_uint4(0, 0, 0, 0);
-    if (EXTRA && ex.label_plane && mine) lab = __ldg(reinterpret_cast<const uint4*>(ex.label + b * hw + p));
+    constexpr bool LAB = EXTRA == 2;
+    if (LAB && ex.label_plane && mine) lab = __ldg(reinterpret_cast<const uint4*>(ex.label + b * hw + p));
     dt_mbar_wait(&full[s], (uint32_t)(k / kDtStages) & 1u);
+    ExtrasRegs er;                                               // (EXTRA) footprint values, consumed after the hand-over
+    bool own = false;
+    int gidx = 0;
     if (mine) {
       uint32_t q[3][16];
 #pragma unroll
@@ -439,12 +448,14 @@ decode_tail_tma_kernel(const T* __restrict__ img, uint8_t* __restrict__ rgb,
         __stcs(o + 2, make_uint4(w[8], w[9], w[10], w[11]));
       }
       if (EXTRA) {
-        const int gidx = (int)(p >> 4);
-        if (ex.label_plane)
+        gidx = p >> 4;
+        if (LAB && ex.label_plane)
           __stcs(reinterpret_cast<uint4*>(ex.label_plane + b * ex.label_plane_stride + p), lab);
         const int y = ex.gpr_shift >= 0 ? (gidx >> ex.gpr_shift) : (gidx / ex.gpr);
-        if ((y & 15) == 7) {                                     // this thread owns a footprint: all of it is in the tile
-          ExtrasRegs er;
+        own = (y & 15) == 7;                                     // this thread owns a footprint: all of it is in the tile
+        if (own) {
+          // only the footprint's LOADS happen while the stage is held; the lerps and the scattered stores run after
+          // the stage has been handed back, off the tile's critical path (the owners are 2 of the CTA's 8 warps)
           er.o = ((int64_t)(y >> 4)) * ex.gpr + (gidx - y * ex.gpr);
           if (ex.feat || ex.small_rgb) {
 #pragma unroll
@@ -454,15 +465,12 @@ decode_tail_tma_kernel(const T* __restrict__ img, uint8_t* __restrict__ rgb,
               er.px[c][2] = to_f32(r0[ex.W]); er.px[c][3] = to_f32(r0[ex.W + 1]);
             }
           }
-          if (ex.label_small) {
+          if (LAB && ex.label_small) {
             const uint8_t* r0 = ex.label + b * hw + p + 7;
             const uint8_t* r1 = r0 + ex.W;
             er.lab4 = (uint32_t)__ldg(r0) | ((uint32_t)__ldg(r0 + 1) << 8) | ((uint32_t)__ldg(r1) << 16) |
                       ((uint32_t)__ldg(r1 + 1) << 24);
           }
-          TailExtras fx = ex;
-          fx.label_plane = nullptr;                              // (stored above)
-          extras_finish<T>(fx, b, gidx, er);
         }
       }
     }
@@ -478,6 +486,12 @@ decode_tail_tma_kernel(const T* __restrict__ img, uint8_t* __restrict__ rgb,
         advance(nb, ni, (kDtStages - 1) * (int)gridDim.x);
         issue(k + kDtStages, nb, ni);
       }
+    }
+    if (EXTRA && own) {
+      TailExtras fx = ex;
+      fx.label_plane = nullptr;                                  // (stored above)
+      if (!LAB) fx.label_small = nullptr;
+      extras_finish<T>(fx, b, gidx, er);
     }
   }
 }
@@ -521,7 +535,7 @@ static void ensure_smem_attr(F kernel, int bytes, bool (&done)[kMaxDevices]) {
   }
 }
 
-template <typename T, bool RGB, bool GRAY, bool EXTRA, int STAGES, int CTAS, bool PW = false>
+template <typename T, bool RGB, bool GRAY, int EXTRA, int STAGES, int CTAS, bool PW = false>
 static void launch_tma_one(const T* p, uint8_t* rgb, uint8_t* gray, int64_t hw, int tiles_per_img, int total,
                            int64_t gray_batch_stride, int tile_off, const TailExtras& ex, cudaStream_t st) {
   static bool attr[kMaxDevices] = {};
@@ -537,7 +551,7 @@ static void launch_tma_one(const T* p, uint8_t* rgb, uint8_t* gray, int64_t hw, 
 // stages * CTAs * 3 planes * 4096 px * sizeof(T)
 template <typename T> struct TmaShapes;
 template <> struct TmaShapes<__nv_bfloat16> {
-  template <bool RGB, bool GRAY, bool EXTRA>
+  template <bool RGB, bool GRAY, int EXTRA>
   static void launch(int variant, const __nv_bfloat16* p, uint8_t* rgb, uint8_t* gray, int64_t hw, int tpi, int total,
                      int64_t gbs, int toff, const TailExtras& ex, cudaStream_t st) {
     typedef __nv_bfloat16 T;
@@ -551,12 +565,15 @@ template <> struct TmaShapes<__nv_bfloat16> {
       case 8: launch_tma_one<T, RGB, GRAY, EXTRA, 3, 2, true>(p, rgb, gray, hw, tpi, total, gbs, toff, ex, st); break;
       case 9: launch_tma_one<T, RGB, GRAY, EXTRA, 2, 2, true>(p, rgb, gray, hw, tpi, total, gbs, toff, ex, st); break;
       case 10: launch_tma_one<T, RGB, GRAY, EXTRA, 4, 2, true>(p, rgb, gray, hw, tpi, total, gbs, toff, ex, st); break;
+      case 11: launch_tma_one<T, RGB, GRAY, EXTRA, 2, 1>(p, rgb, gray, hw, tpi, total, gbs, toff, ex, st); break;  //  48 KB, one CTA per SM
+      case 12: launch_tma_one<T, RGB, GRAY, EXTRA, 3, 1>(p, rgb, gray, hw, tpi, total, gbs, toff, ex, st); break;  //  72 KB
+      case 13: launch_tma_one<T, RGB, GRAY, EXTRA, 4, 1>(p, rgb, gray, hw, tpi, total, gbs, toff, ex, st); break;  //  96 KB
       default: launch_tma_one<T, RGB, GRAY, EXTRA, 4, 2>(p, rgb, gray, hw, tpi, total, gbs, toff, ex, st); break;  // 192 KB
     }
   }
 };
 template <> struct TmaShapes<float> {
-  template <bool RGB, bool GRAY, bool EXTRA>
+  template <bool RGB, bool GRAY, int EXTRA>
   static void launch(int variant, const float* p, uint8_t* rgb, uint8_t* gray, int64_t hw, int tpi, int total,
                      int64_t gbs, int toff, const TailExtras& ex, cudaStream_t st) {
     if (variant == 2 || variant == 3) launch_tma_one<float, RGB, GRAY, EXTRA, 2, 2>(p, rgb, gray, hw, tpi, total, gbs, toff, ex, st);
@@ -575,7 +592,8 @@ static int launch_decode_tail(const void* img, uint8_t* rgb, uint8_t* gray, int 
   if (extra && (!vec_ok || na.out || !gray)) return LDIFF_EUNSUPPORTED;      // (entry point checked the geometry)
   const TailExtras ex = extra ? *exp : TailExtras{};
   const int tma = tune_get(LDIFF_TUNE_DECODE_TAIL_TMA);
-  if (vec_ok && !na.out && (hw % kDtTile) == 0 && tma > 0 && (int64_t)B * (hw / kDtTile) <= 0x7fffffff) {
+  if (vec_ok && !na.out && (hw % kDtTile) == 0 && tma > 0 && (int64_t)B * (hw / kDtTile) <= 0x7fffffff &&
+      hw + kDtTile <= 0x7fffffff) {                      // (the kernel does its per-image pixel arithmetic in 32 bits)
     // extras: shift the tiles of an image by half a tile's rows (whole tiles of >= 16 rows need no shift) so that
     // rows 16e+7 and 16e+8 always share a tile; needs a tile to be a whole, power-of-two number of rows
     const int tile_rows = (W > 0 && kDtTile % W == 0) ? kDtTile / W : 0;
@@ -588,10 +606,11 @@ static int launch_decode_tail(const void* img, uint8_t* rgb, uint8_t* gray, int 
     const T* p = (const T*)img;
 #define DTT(R, G, E) TmaShapes<T>::template launch<R, G, E>(tma, p, rgb, gray, hw, tiles_per_img, total, \
                                                             gray_batch_stride, tile_off, ex, st)
-    if (extra) { if (rgb) DTT(true, true, true); else DTT(false, true, true); }
-    else if (rgb && gray) DTT(true, true, false);
-    else if (gray) DTT(false, true, false);
-    else DTT(true, false, false);
+    if (extra && ex.label) { if (rgb) DTT(true, true, 2); else DTT(false, true, 2); }
+    else if (extra) { if (rgb) DTT(true, true, 1); else DTT(false, true, 1); }
+    else if (rgb && gray) DTT(true, true, 0);
+    else if (gray) DTT(false, true, 0);
+    else DTT(true, false, 0);
 #undef DTT
     return check_launch();
     }

@@ -22,13 +22,13 @@ Stages per batch (reference lines in brackets):
 5. confusion matrices of both masks vs gt                    [utils.py:55-104; evaluate.py:11-45]
 """
 from dataclasses import dataclass
-from typing import List
+from typing import List, Optional
 
 import os
 
 import torch
 
-from . import ops
+from . import _cabi, ops
 from .scheduler import LaplacePLMSScheduler
 
 
@@ -162,6 +162,7 @@ class HotPath:
         # reference does; False: every pass starts from zero (and can push its matrices, attach_exchange)
         self.accumulate = False
         self.decode_streams = max(1, min(num_steps, int(os.environ.get("LDIFF_DECODE_STREAMS", "1"))))
+        self.decode_tail_shape = None                    # pipeline shape of this pass's decode tails (None: the library's)
 
     def attach_exchange(self, exchange, deferred: bool = True):
         """Multi-GPU: fuse the cross-rank sum of the two confusion matrices into the pass
@@ -282,7 +283,20 @@ class HotPath:
     def _chain_decode(self, inp, part: int = 0):
         """Decode tails of the steps i = part (mod decode_streams).  The n tails have no data dependence on one
         another (step i's image is step i's VAE output); spread over two streams, the start-up and drain of one
-        tail overlap the steady state of the other."""
+        tail overlap the steady state of the other.  ``decode_tail_shape`` (None = the library's setting) selects
+        the tails' pipeline shape for THIS pass's launches: the process-wide knob is set around them and restored
+        (launch time is capture time for a graphed pass)."""
+        if self.decode_tail_shape is None:
+            return self._decode_launches(inp, part)
+        lib = _cabi.lib()
+        prev = lib.ldiff_tune_get(_cabi.TUNE_DECODE_TAIL_TMA)
+        lib.ldiff_tune(_cabi.TUNE_DECODE_TAIL_TMA, int(self.decode_tail_shape))
+        try:
+            return self._decode_launches(inp, part)
+        finally:
+            lib.ldiff_tune(_cabi.TUNE_DECODE_TAIL_TMA, prev)
+
+    def _decode_launches(self, inp, part: int = 0):
         n = self.n
         for i in range(part, n, self.decode_streams):
             last = i == n - 1
@@ -425,14 +439,25 @@ class HotPathRing:
     buffers and chain streams, enqueued on its own stream, so the tail of one pass (the last classifier kernels,
     the join) overlaps the head of the next instead of leaving the machine half empty — a pass is five chains of
     kernels with different bottlenecks (HBM, issue, launch latency) and no single pass keeps all of them busy.
-    Measured at the bench shape (8 x 1024^2, K=11, 5 steps, bf16): 119 us per pass alone, 101 us with two in
-    flight, 99.5 us with three (tools/pass_overlap.py).  Results of pass i live in ``slot(i).results()`` until
-    pass i + n_in_flight is enqueued."""
+    Measured at the bench shape (8 x 1024^2, K=11, 5 steps, bf16): 112 us per pass alone, 93 us with three in
+    flight, and 89 us when the slots' decode tails also run in their smallest pipeline shape (2 stages, ONE CTA per
+    SM: slower alone, 127 us for a single pass, but each pass then leaves room for the other passes' kernels) —
+    ``throughput_shape`` (default: on from three passes in flight, bf16 storage, unless LDIFF_DT_TMA pins a shape).
+    Results of pass i live in ``slot(i).results()`` until pass i + n_in_flight is enqueued
+    (tools/pass_overlap.py)."""
 
-    def __init__(self, n_in_flight: int = 2, *args, **kwargs):
+    THROUGHPUT_DECODE_TAIL_SHAPE = 11
+
+    def __init__(self, n_in_flight: int = 2, *args, throughput_shape: Optional[bool] = None, **kwargs):
         if n_in_flight < 1:
             raise ValueError("n_in_flight must be >= 1")
         self.slots = [HotPath(*args, **kwargs) for _ in range(n_in_flight)]
+        if throughput_shape is None:
+            throughput_shape = (n_in_flight >= 3 and self.slots[0].dtype == torch.bfloat16
+                                and "LDIFF_DT_TMA" not in os.environ)
+        if throughput_shape:
+            for slot in self.slots:
+                slot.decode_tail_shape = self.THROUGHPUT_DECODE_TAIL_SHAPE
         dev = self.slots[0].device
         self.streams = [torch.cuda.Stream(dev) for _ in range(n_in_flight)]
         self.device = dev

@@ -83,7 +83,7 @@ def test_scheduler_step_then_noise_loop_matches_oracle():
 
 @pytest.mark.parametrize("shape", [(2, 3, 64, 64), (1, 3, 48, 80), (2, 3, 1024, 1024), (1, 3, 128, 32)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("tma", [0, 1, 4, 6, 7, 9])
+@pytest.mark.parametrize("tma", [0, 1, 4, 6, 7, 9, 11, 12])
 def test_decode_tail_fused_equals_separate_launches(tune, shape, dtype, tma):
     from ldiffusion_b200 import _cabi
     ops = _ops()
@@ -311,9 +311,11 @@ def test_fused_pass_equals_unfused_pass(dtype):
                 assert torch.equal(x, y), k
 
 
-def test_ring_of_passes_in_flight_equals_single_passes():
-    """HotPathRing: three batches through two slots (graph per slot, replayed on the slots' streams) give the
-    same results as one HotPath run batch after batch."""
+@pytest.mark.parametrize("nfly", [2, 3])
+def test_ring_of_passes_in_flight_equals_single_passes(nfly):
+    """HotPathRing: four batches through two / three slots (graph per slot, replayed on the slots' streams) give the
+    same results as one HotPath run batch after batch.  Three slots run their decode tails in the throughput shape
+    (one CTA per SM), selected per pass and restored: the library's setting is untouched afterwards."""
     from ldiffusion_b200.pipeline import HotPath, HotPathInputs, HotPathRing, synth_inputs
     cfg = dict(batch=2, height=256, width=256, num_classes=11, num_steps=5, n_instances=40)
     kw = dict(dtype=torch.bfloat16, device="cuda", head_hw=(8, 8), feat_size=(16, 16), seed=5, **cfg)
@@ -329,36 +331,41 @@ def test_ring_of_passes_in_flight_equals_single_passes():
         single.run(d)
         torch.cuda.synchronize()
         want.append({k: ([t.clone() for t in v] if isinstance(v, list) else v.clone()) for k, v in single.results().items()})
-    ring = HotPathRing(2, **kw)
+    from ldiffusion_b200 import _cabi
+    lib = _cabi.lib()
+    shape_before = lib.ldiff_tune_get(_cabi.TUNE_DECODE_TAIL_TMA)
+    ring = HotPathRing(nfly, **kw)
+    assert all(sl.decode_tail_shape == (HotPathRing.THROUGHPUT_DECODE_TAIL_SHAPE if nfly >= 3 else None) for sl in ring.slots)
     ring.fork()
-    for i in range(2):                                      # warm-up outside capture (side streams, first launches)
+    for i in range(nfly):                                   # warm-up outside capture (side streams, first launches)
         ring.run(i, devs[i])
     torch.cuda.synchronize()
     graphs = []
-    for i in range(2):
+    for i in range(nfly):
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=ring.stream(i)):
             ring.slot(i).run(devs[i])
         graphs.append(g)
-    for v in ring.slot(0).results().values():               # scribble, then replay both slots concurrently
+    assert lib.ldiff_tune_get(_cabi.TUNE_DECODE_TAIL_TMA) == shape_before
+    for v in ring.slot(0).results().values():               # scribble, then replay all slots concurrently
         for t_ in (v if isinstance(v, list) else [v]):
             t_.zero_()
-    for i in range(2):
+    for i in range(nfly):
         with torch.cuda.stream(ring.stream(i)):
             graphs[i].replay()
     ring.join()
     torch.cuda.synchronize()
-    for i in range(2):
+    for i in range(nfly):
         got = ring.slot(i).results()
         for k in want[i]:
             for x, y in zip(got[k] if isinstance(got[k], list) else [got[k]],
                             want[i][k] if isinstance(want[i][k], list) else [want[i][k]]):
                 assert torch.equal(x, y), (i, k)
-    for i in (2, 3):                                        # eager passes through the ring: slot reuse
+    for i in range(nfly, 4):                                # eager passes through the ring: slot reuse
         ring.run(i, devs[i])
     ring.join()
     torch.cuda.synchronize()
-    for i in (2, 3):
+    for i in range(nfly, 4):
         got = ring.slot(i).results()
         for k in ("mask_tissue", "mask_cell", "confusion", "pixel_planes", "featcat", "latents"):
             assert torch.equal(got[k], want[i][k]), (i, k)

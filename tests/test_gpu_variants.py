@@ -31,7 +31,7 @@ def test_decode_tail_tma_bit_exact(tune, shape, want_rgb, dtype):
     img = torch.empty(shape).uniform_(-1.3, 1.3, generator=g).to(dtype)
     tune(_cabi.TUNE_DECODE_TAIL_TMA, 0)
     rgb0, gray0 = ops.decode_tail_gray(img.cuda(), want_rgb=want_rgb)
-    for variant in range(1, 11):
+    for variant in range(1, 14):
         tune(_cabi.TUNE_DECODE_TAIL_TMA, variant)
         rgb1, gray1 = ops.decode_tail_gray(img.cuda(), want_rgb=want_rgb)
         torch.cuda.synchronize()

@@ -49,7 +49,7 @@ planes = torch.empty(B, 6, H, W, dtype=torch.uint8, device=dev)
 rgb = torch.empty(B, H, W, 3, dtype=torch.uint8, device=dev)
 featc = torch.empty(B, 5, 64, 64, dtype=torch.bfloat16, device=dev)
 lsmall = torch.empty(B, 1, 64, 64, dtype=torch.uint8, device=dev)
-for tma in (0, 4, 6, 7, 8, 9, 10):
+for tma in (0, 4, 6, 7, 8, 9, 10, 11, 12, 13):
     lib.ldiff_tune(_cabi.TUNE_DECODE_TAIL_TMA, tma)
     line(f"decode_tail_gray bf16 tma={tma}",
          timeit(lambda i: ops.decode_tail_gray(imgs[i], want_rgb=False, gray_out=planes[:, i % 5]), 6), px * 7)

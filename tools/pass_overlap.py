@@ -11,8 +11,9 @@ from ldiffusion_b200.pipeline import HotPath, synth_inputs
 dev = torch.device("cuda")
 B, H, W_, K, N = 8, 1024, 1024, 11, 5
 lib = _cabi.lib()
-lib.ldiff_tune(_cabi.TUNE_DECODE_TAIL_TMA, int(os.environ.get("TMA", "4")))
-for nfly in (1, 2, 3):
+if "TMA" in os.environ:                                   # decode-tail pipeline shape (default: the library's)
+    lib.ldiff_tune(_cabi.TUNE_DECODE_TAIL_TMA, int(os.environ["TMA"]))
+for nfly in [int(x) for x in os.environ.get("NFLY", "1,2,3").split(",")]:
     sets = [synth_inputs(B, H, W_, K, N, dtype=torch.bfloat16, device=dev, n_instances=800, seed=s) for s in range(1, nfly + 1)]
     if nfly == 1:
         sets.append(synth_inputs(B, H, W_, K, N, dtype=torch.bfloat16, device=dev, n_instances=800, seed=9))
