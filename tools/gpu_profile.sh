@@ -8,7 +8,7 @@ timeout 600 compute-sanitizer --tool racecheck --error-exitcode 3 python tools/p
 echo "racecheck kernels rc=$?" >> gpurun_out/r02_sanitizer_racecheck_kernels.log
 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 3 python -m pytest tests/test_gpu_fused.py -q -m gpu -x > gpurun_out/r02_sanitizer_memcheck_fused.log 2>&1
 echo "memcheck fused rc=$?" >> gpurun_out/r02_sanitizer_memcheck_fused.log
-timeout 600 compute-sanitizer --tool memcheck --error-exitcode 3 python __graft_entry__.py smoke > gpurun_out/r02_sanitizer_memcheck_smoke.log 2>&1
+timeout 300 compute-sanitizer --tool memcheck --error-exitcode 3 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02_sanitizer_memcheck_smoke.log 2>&1
 echo "memcheck smoke rc=$?" >> gpurun_out/r02_sanitizer_memcheck_smoke.log
 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:'kernel' -f -o /tmp/r02_full python tools/prof_r2.py > gpurun_out/r02_ncu_full.log 2>&1
 python tools/summarize_ncu.py /tmp/r02_full.ncu-rep gpurun_out/r02_ncu_full_kernels > gpurun_out/r02_ncu_summarize.log 2>&1
