@@ -99,6 +99,8 @@ def check_status(device):
 def _laplace_qsample(x: Tensor, out: Tensor, noise: Optional[Tensor], u: Optional[Tensor],
                      noise_out: Optional[Tensor], b: float, seed: int, offset: int) -> None:
     _cuda(x, out, noise, u, noise_out)
+    if x.numel() == 0:
+        return
     check(_cabi.lib().ldiff_laplace_qsample(_ptr(x), _ptr(out), _ptr(noise), _ptr(u), _ptr(noise_out),
                                             b, seed, offset, x.numel(), _dt(x), _stream(x)))
 
@@ -114,6 +116,8 @@ def _map_dims(x: Tensor, scale: Tensor):
 def _laplace_qsample_map(x: Tensor, scale: Tensor, out: Tensor, noise: Optional[Tensor], u: Optional[Tensor],
                          noise_out: Optional[Tensor], x_mul: float, seed: int, offset: int) -> None:
     _cuda(x, scale, out, noise, u, noise_out)
+    if x.numel() == 0:
+        return
     plane, C, Cs = _map_dims(x, scale)
     check(_cabi.lib().ldiff_laplace_qsample_map(_ptr(x), _ptr(scale), _ptr(out), _ptr(noise), _ptr(u),
                                                 _ptr(noise_out), x_mul, seed, offset, x.numel(), plane, C, Cs,
@@ -122,6 +126,8 @@ def _laplace_qsample_map(x: Tensor, scale: Tensor, out: Tensor, noise: Optional[
 
 def _scaled_residual(x: Tensor, eps: Tensor, scale: Tensor, out: Tensor, out_div: float) -> None:
     _cuda(x, eps, scale, out)
+    if x.numel() == 0:
+        return
     plane, C, Cs = _map_dims(x, scale)
     check(_cabi.lib().ldiff_scaled_residual(_ptr(x), _ptr(eps), _ptr(scale), _ptr(out), out_div, x.numel(),
                                             plane, C, Cs, _dt(x), _stream(x)))
@@ -130,6 +136,8 @@ def _scaled_residual(x: Tensor, eps: Tensor, scale: Tensor, out: Tensor, out_div
 def _plms_step(sample: Tensor, eps: Sequence[Tensor], mode: int, sample_coeff: float,
                alpha_diff: float, denom: float, out: Tensor) -> None:
     _cuda(sample, out, *eps)
+    if sample.numel() == 0:
+        return
     e = [_ptr(t) for t in eps] + [None] * (4 - len(eps))
     check(_cabi.lib().ldiff_plms_step(_ptr(sample), e[0], e[1], e[2], e[3], mode, sample_coeff,
                                       alpha_diff, denom, _ptr(out), sample.numel(), _dt(sample),
@@ -140,6 +148,8 @@ def _plms_step_noise(sample: Tensor, eps: Sequence[Tensor], mode: int, sample_co
                      denom: float, out: Tensor, clean: Tensor, noisy: Tensor, noise: Optional[Tensor],
                      u: Optional[Tensor], b: float, seed: int, offset: int) -> None:
     _cuda(sample, out, clean, noisy, noise, u, *eps)
+    if sample.numel() == 0:
+        return
     e = [_ptr(t) for t in eps] + [None] * (4 - len(eps))
     check(_cabi.lib().ldiff_plms_step_noise(_ptr(sample), e[0], e[1], e[2], e[3], mode, sample_coeff, alpha_diff,
                                             denom, _ptr(out), _ptr(clean), _ptr(noisy), _ptr(noise), _ptr(u), b,
@@ -148,6 +158,8 @@ def _plms_step_noise(sample: Tensor, eps: Sequence[Tensor], mode: int, sample_co
 
 def _decode_tail_gray(img: Tensor, rgb: Optional[Tensor], gray: Optional[Tensor]) -> None:
     _cuda(img, rgb, gray)
+    if img.numel() == 0:
+        return
     B, _, H, W = img.shape
     gstride = gray.stride(0) if gray is not None else 0
     check(_cabi.lib().ldiff_decode_tail_gray(_ptr(img), _ptr(rgb), _ptr(gray), B, H, W, gstride,
@@ -158,6 +170,8 @@ def _decode_tail_fused(img: Tensor, rgb: Optional[Tensor], gray: Tensor, feat: O
                        small_rgb: Optional[Tensor], label: Optional[Tensor], label_plane: Optional[Tensor],
                        label_small: Optional[Tensor]) -> None:
     _cuda(img, rgb, gray, feat, small_rgb, label, label_plane, label_small)
+    if img.numel() == 0:
+        return
     B, _, H, W = img.shape
     check(_cabi.lib().ldiff_decode_tail_fused(
         _ptr(img), _ptr(rgb), _ptr(gray), B, H, W, gray.stride(0), _dt(img), _ptr(feat),
@@ -170,6 +184,8 @@ def _decode_tail_model_input(img: Tensor, rgb: Optional[Tensor], gray: Optional[
                              mean: Sequence[float], std: Sequence[float]) -> None:
     import ctypes
     _cuda(img, rgb, gray, model_input)
+    if img.numel() == 0:
+        return
     B, _, H, W = img.shape
     gstride = gray.stride(0) if gray is not None else 0
     m3 = (ctypes.c_float * 3)(*[float(v) for v in mean])
@@ -180,6 +196,8 @@ def _decode_tail_model_input(img: Tensor, rgb: Optional[Tensor], gray: Optional[
 
 def _bilinear_lift(src: Tensor, dst: Tensor, dst_channel: int, gray: bool) -> None:
     _cuda(src, dst)
+    if src.numel() == 0 or dst.numel() == 0:
+        return
     B, C, h, w = src.shape
     _, Ctot, H, W = dst.shape
     check(_cabi.lib().ldiff_bilinear_lift(_ptr(src), _dt(src), C, h, w, src.stride(0), src.stride(1),
@@ -212,6 +230,10 @@ def _head_logits(feat: Tensor, weight: Tensor, bias: Optional[Tensor], logits: T
                  clear: Optional[Tensor] = None) -> None:
     """``clear`` (optional int64 tensor): zeroed by the kernel as a side job (see ldiff.h)."""
     _cuda(feat, weight, bias, logits, clear)
+    if feat.numel() == 0:
+        if clear is not None:
+            clear.zero_()
+        return
     B, Cin = feat.shape[:2]
     hw = feat[0, 0].numel()
     check(_cabi.lib().ldiff_head_logits(_ptr(feat), _ptr(weight), _ptr(bias), _ptr(logits), B, Cin,
@@ -221,6 +243,8 @@ def _head_logits(feat: Tensor, weight: Tensor, bias: Optional[Tensor], logits: T
 
 def _lift_argmax(logits: Tensor, mask: Tensor) -> None:
     _cuda(logits, mask)
+    if mask.numel() == 0:
+        return
     B, K, h, w = logits.shape
     _, H, W = mask.shape
     check(_cabi.lib().ldiff_lift_argmax(_ptr(logits), _ptr(mask), B, K, h, w, H, W, _stream(logits)))
@@ -250,6 +274,10 @@ def _cell_classify(feats: Tensor, weight: Tensor, bias: Optional[Tensor], inst_i
                    lut: Tensor, logits_out: Optional[Tensor], status: Tensor, clear: Optional[Tensor] = None) -> None:
     """feats [B,N,Cin] (or [N,Cin]); lut [B,lut_size] (or [lut_size]); ``clear``: see ``_head_logits``."""
     _cuda(feats, weight, bias, inst_ids, lut, logits_out, status, clear)
+    if feats.numel() == 0:                                # no instances: the LUT keeps its background entries
+        if clear is not None:
+            clear.zero_()
+        return
     B = feats.shape[0] if feats.dim() == 3 else 1
     N, Cin = feats.shape[-2], feats.shape[-1]
     lut_stride = lut.stride(0) if lut.dim() == 2 else 0
@@ -267,6 +295,8 @@ def _copy_planes_u8(src: Tensor, dst: Tensor) -> None:
 
 def _lut_paint(inst: Tensor, lut: Tensor, mask: Tensor, status: Tensor) -> None:
     _cuda(inst, lut, mask, status)
+    if inst.numel() == 0:
+        return
     B = inst.shape[0]
     n = inst[0].numel()
     lut_stride = lut.stride(0) if lut.dim() == 2 else 0
@@ -276,6 +306,8 @@ def _lut_paint(inst: Tensor, lut: Tensor, mask: Tensor, status: Tensor) -> None:
 
 def _argmax_channels(x: Tensor, out: Tensor) -> None:
     _cuda(x, out)
+    if x.numel() == 0:
+        return
     B, K = x.shape[:2]
     check(_cabi.lib().ldiff_argmax_channels(_ptr(x), _ptr(out), B, K, x[0, 0].numel(), _dt(x),
                                             _stream(x)))
@@ -284,6 +316,8 @@ def _argmax_channels(x: Tensor, out: Tensor) -> None:
 def _confusion_hist(pred: Tensor, gt: Tensor, gt_lut: Optional[Tensor], C: Tensor, K: int,
                     status: Tensor) -> None:
     _cuda(pred, gt, gt_lut, C, status)
+    if pred.numel() == 0:
+        return
     check(_cabi.lib().ldiff_confusion_hist(_ptr(pred), _ptr(gt), _ptr(gt_lut), _ptr(C), pred.numel(),
                                            K, _ptr(status), _stream(pred)))
 
@@ -291,6 +325,8 @@ def _confusion_hist(pred: Tensor, gt: Tensor, gt_lut: Optional[Tensor], C: Tenso
 def _confusion_hist_batched(pred: Tensor, gt: Tensor, gt_lut: Optional[Tensor], C: Tensor, K: int,
                             status: Tensor) -> None:
     _cuda(pred, gt, gt_lut, C, status)
+    if pred.numel() == 0:
+        return
     n_images = pred.shape[0]
     check(_cabi.lib().ldiff_confusion_hist_batched(_ptr(pred), _ptr(gt), _ptr(gt_lut), _ptr(C),
                                                    pred[0].numel(), n_images, K, _ptr(status), _stream(pred)))
