@@ -15,7 +15,7 @@ constexpr int kMaxDevices = 64;
 int current_device();                          // cudaGetDevice, -1 on error
 int sm_count();                                // SM count of the CURRENT device (cached per device)
 
-// ldiff_tune knobs (capi.cu); first use reads the environment (LDIFF_ARGMAX_PERSIST, LDIFF_DT_SMS)
+// ldiff_tune knobs (capi.cu); first use reads the environment (LDIFF_ARGMAX_VARIANT, LDIFF_DT_SMS, LDIFF_DT_TMA, ...)
 int tune_get(int knob);
 
 inline int check_launch() {

@@ -252,8 +252,9 @@ class HotPath:
     # graphs keep them per kernel node.  When blocks of several chains are waiting for an SM, the
     # bandwidth-bound decode tails and the latency-bound latent kernels go first and the two
     # register-heavy classifier chains fill in behind them: measured 146 -> 135 us per pass against
-    # equal priorities (tools/pass_sched.py; giving the classifier chains the high priority instead
-    # costs 155 us).
+    # equal priorities in round 1 (tools/pass_sched.py; giving the classifier chains the high priority
+    # instead cost 155 us), and with three passes in flight in the final build 88.6 us against 94.4 us
+    # for equal priorities (tools/prio_sweep.sh, LDIFF_SIDE_PRIOS).
     CHAIN_PRIORITIES = (-2, -1, 0, 0, -2)
 
     def _side_streams(self):
