@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libldiff_sm100.so")
-SOURCES = ["capi.cu", "sampler.cu", "decode_tail.cu", "bilinear.cu", "bilinear_bwd.cu", "head.cu", "lift_argmax_env.cu", "head_tc.cu", "confusion.cu", "sliding.cu", "infonce.cu"]
+SOURCES = ["capi.cu", "sampler.cu", "decode_tail.cu", "bilinear.cu", "bilinear_bwd.cu", "head.cu", "lift_argmax_env.cu", "lift_argmax_row.cu", "head_tc.cu", "confusion.cu", "sliding.cu", "infonce.cu"]
 
 
 def _nvcc():

@@ -494,6 +494,9 @@ int launch_head_logits_tc(const void* feat, const void* weight, const float* bia
 bool lift_argmax_env_ok(int K, int h, int H);                                   // lift_argmax_env.cu
 int launch_lift_argmax_env(const float* logits, uint8_t* mask, const uint8_t* gt, int64_t* C, int B, int K, int h,
                            int w, int H, int W, int* status, const XchgPush* px, cudaStream_t st);
+bool lift_argmax_row_ok(int K, int h, int w, int H, int W, const void* mask);    // lift_argmax_row.cu
+int launch_lift_argmax_row(const float* logits, uint8_t* mask, int B, int K, int h, int w, int H, int W,
+                           cudaStream_t st);
 
 }  // namespace ldiff
 
@@ -506,10 +509,13 @@ extern "C" int ldiff_lift_argmax(const float* logits, uint8_t* mask, int B, int 
   if (B == 0) return LDIFF_OK;
   cudaStream_t st = (cudaStream_t)stream;
   AxisH ay{(float)h / (float)H, h, H}, ax{(float)w / (float)W, w, W};
-  // variant: 0 (default) = envelope kernel; 4 / 5 = the per-pixel evaluation kernel of round 1 with 2 / 1
-  // columns per thread (kept for A/B timing: tools/kbench_argmax.py)
+  // variant: 0 (default) = envelope kernel, row form where the shape allows it (x32 horizontal lift), else the
+  // column form; 1 = column form always; 4 / 5 = the per-pixel evaluation kernel of round 1 with 2 / 1 columns per
+  // thread (kept for A/B timing: tools/kbench_argmax.py)
   const int variant = tune_get(LDIFF_TUNE_ARGMAX_VARIANT);
-  if (variant == 0 && H >= 4 * h && lift_argmax_env_ok(K, h, H))
+  if (variant == 0 && lift_argmax_row_ok(K, h, w, H, W, mask))
+    return launch_lift_argmax_row(logits, mask, B, K, h, w, H, W, st);
+  if (variant <= 1 && H >= 4 * h && lift_argmax_env_ok(K, h, H))
     return launch_lift_argmax_env(logits, mask, nullptr, nullptr, B, K, h, w, H, W, nullptr, nullptr, st);
   if (K <= 15 && H >= 4 * h && max_band_rows(h, H) <= kBand && h <= 65535) {
     const bool two = variant != 5 && K <= 12 && (W % 2) == 0;

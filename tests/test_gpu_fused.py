@@ -194,9 +194,12 @@ CASES = {
 
 
 @pytest.mark.parametrize("case", sorted(CASES))
-@pytest.mark.parametrize("factor", [32, 8])
-def test_envelope_lift_argmax_bit_exact_vs_spec_and_chain(case, factor):
+@pytest.mark.parametrize("factor,variant", [(32, 0), (32, 1), (8, 0)])
+def test_envelope_lift_argmax_bit_exact_vs_spec_and_chain(tune, case, factor, variant):
+    """factor 32, variant 0: the row form (lift_argmax_row.cu); variant 1 / factor 8: the column form."""
+    from ldiffusion_b200 import _cabi
     ops = _ops()
+    tune(_cabi.TUNE_ARGMAX_VARIANT, variant)
     logits = CASES[case]()
     B, K, h, w = logits.shape
     size = (h * factor, w * factor)

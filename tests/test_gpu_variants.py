@@ -47,14 +47,19 @@ def test_decode_tail_tma_bit_exact(tune, shape, want_rgb, dtype):
 
 
 @pytest.mark.timeout(120)
-@pytest.mark.parametrize("variant", [0, 4, 5])
+@pytest.mark.parametrize("variant", [0, 1, 4, 5])
 def test_lift_argmax_variants_bit_exact(tune, variant):
-    """0 = envelope kernel (default), 4 / 5 = per-pixel evaluation with 2 / 1 columns per thread."""
+    """0 = envelope kernel, row form for x32 horizontal lifts (default), 1 = envelope kernel, column form always,
+    4 / 5 = per-pixel evaluation with 2 / 1 columns per thread."""
     from ldiffusion_b200 import _cabi, ops
     g = torch.Generator().manual_seed(3)
     tune(_cabi.TUNE_ARGMAX_VARIANT, variant)
     for K, shape, size in ((11, (2, 32, 32), (1024, 1024)), (6, (1, 16, 16), (512, 512)), (7, (3, 8, 8), (128, 96)),
-                           (15, (1, 8, 8), (64, 66)), (3, (1, 5, 7), (45, 63))):
+                           (15, (1, 8, 8), (64, 66)), (3, (1, 5, 7), (45, 63)),
+                           # x32 horizontal lifts the row form takes: rows not a multiple of 256, a x40 vertical lift, one
+                           # and two source columns (half chunks only / a lone last chunk), K = 1 and K = 15
+                           (5, (1, 5, 3), (160, 96)), (4, (2, 4, 4), (160, 128)), (1, (1, 2, 1), (50, 32)),
+                           (15, (1, 3, 2), (96, 64)), (11, (1, 9, 7), (300, 224))):
         logits = torch.randn((shape[0], K) + shape[1:], generator=g)
         got = torch.full((shape[0],) + size, 0xEE, dtype=torch.uint8, device="cuda")   # poisoned: a kernel that skips
         ops._lift_argmax(logits.cuda(), got)                                            # pixels cannot pass on stale data

@@ -4,6 +4,7 @@ import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+torch.manual_seed(0)
 from ldiffusion_b200 import _cabi, ops
 from kbench import timeit
 
@@ -26,7 +27,7 @@ smooth = torch.nn.functional.interpolate(torch.randn(B, K, 4, 4, device=dev) * 3
 mask = torch.empty(B, H, W, dtype=torch.uint8, device=dev)
 gt = torch.randint(0, K, (B, H, W), dtype=torch.uint8, device=dev)
 C = torch.zeros(K + 1, K, dtype=torch.int64, device=dev)
-for variant in (4, 0):
+for variant in (4, 1, 0):            # round-1 per-pixel kernel, envelope column form, envelope row form (default)
     lib.ldiff_tune(_cabi.TUNE_ARGMAX_VARIANT, variant)
     for nm, lg in (("random", logits), ("smooth", smooth)):
         line(f"lift_argmax variant={variant} {nm}", timeit(lambda i: ops._lift_argmax(lg, mask), 1), px)

@@ -13,6 +13,8 @@ B, H, W_, K, N = 8, 1024, 1024, 11, 5
 lib = _cabi.lib()
 if "TMA" in os.environ:                                   # decode-tail pipeline shape (default: the library's)
     lib.ldiff_tune(_cabi.TUNE_DECODE_TAIL_TMA, int(os.environ["TMA"]))
+if "AMAX" in os.environ:                                  # lift+argmax kernel (0 = row form where it applies, 1 = column form)
+    lib.ldiff_tune(_cabi.TUNE_ARGMAX_VARIANT, int(os.environ["AMAX"]))
 for nfly in [int(x) for x in os.environ.get("NFLY", "1,2,3").split(",")]:
     sets = [synth_inputs(B, H, W_, K, N, dtype=torch.bfloat16, device=dev, n_instances=800, seed=s) for s in range(1, nfly + 1)]
     if nfly == 1:
