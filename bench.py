@@ -252,8 +252,11 @@ def roofline_kernels(torch, ops, _cabi, dev, peak, sets):
         B * NINST * 256 * 2 + B * NINST, f"{B}x{NINST}x256 bf16 instances -> class LUT")
     mask = torch.empty(B, H, W, dtype=torch.uint8, device=dev)
     Cm = torch.zeros(K_ + 1, K_, dtype=torch.int64, device=dev)
-    add("lift_argmax (envelope)", _timeit(torch, lambda i: ops._lift_argmax(logits, mask), 1), px + logits.numel() * 4,
+    add("lift_argmax (envelope, row form)", _timeit(torch, lambda i: ops._lift_argmax(logits, mask), 1), px + logits.numel() * 4,
         f"{B}x{K_}x32x32 -> {H}x{W} (issue-bound: HBM fraction is not its roofline)")
+    lib.ldiff_tune(_cabi.TUNE_ARGMAX_VARIANT, 1)
+    add("lift_argmax (envelope, column form)", _timeit(torch, lambda i: ops._lift_argmax(logits, mask), 1),
+        px + logits.numel() * 4, "same")
     lib.ldiff_tune(_cabi.TUNE_ARGMAX_VARIANT, 4)
     add("lift_argmax (round-1 per-pixel kernel)", _timeit(torch, lambda i: ops._lift_argmax(logits, mask), 1),
         px + logits.numel() * 4, "same")
@@ -264,6 +267,10 @@ def roofline_kernels(torch, ops, _cabi, dev, peak, sets):
     add("lut_paint", _timeit(torch, lambda i: ops.lut_paint(inst[i], lut, out=mask), 2), 5 * px, f"{B}x{H}x{W} int32 ids")
     add("lut_paint_hist (fused)", _timeit(torch, lambda i: ops.lut_paint_hist(
         inst[i], lut, gt, K_, out=Cm, mask_out=mask), 2), 6 * px, "same + gt")
+    inst16 = [torch.from_numpy(t.cpu().numpy().astype("uint16")).to(dev) for t in inst]   # (host-side narrowing: a plain copy)
+    add("lut_paint_hist (fused), uint16 ids", _timeit(torch, lambda i: ops.lut_paint_hist(
+        inst16[i], lut, gt, K_, out=Cm, mask_out=mask), 2), 4 * px, f"{B}x{H}x{W} uint16 ids + gt")
+    del inst16
     add("confusion_hist", _timeit(torch, lambda i: ops.confusion_hist(mask.view(-1), gt.view(-1), K_, out=Cm), 1),
         2 * px, f"{B}x{H}x{W}")
     m64 = torch.randint(0, K_, (64, H, W), dtype=torch.uint8, device=dev)
@@ -302,9 +309,9 @@ def config_sublines(torch, ops, dev, HotPath, HotPathRing, synth_inputs):
     """BASELINE.json configs other than the headline one, each as a short measured sub-line."""
     out = {}
 
-    def ring_rate(b, h, w, k, head_hw, ninst, nfly, reps=60):
+    def ring_rate(b, h, w, k, head_hw, ninst, nfly, reps=60, inst_dtype=torch.int32):
         sets = [synth_inputs(b, h, w, k, NSTEPS, dtype=torch.bfloat16, device=dev, head_hw=head_hw,
-                             n_instances=ninst, seed=77 + i) for i in range(nfly)]
+                             n_instances=ninst, seed=77 + i, inst_dtype=inst_dtype) for i in range(nfly)]
         ring = HotPathRing(nfly, b, h, w, k, NSTEPS, dtype=torch.bfloat16, device=dev, head_hw=head_hw,
                            feat_size=(h // 16, w // 16), n_instances=ninst)
         ring.fork()
@@ -339,6 +346,12 @@ def config_sublines(torch, ops, dev, HotPath, HotPathRing, synth_inputs):
     us, nl = ring_rate(B, H, W, 6, (32, 32), NINST, NFLY)
     out["configs[2] tissue 8x1024x1024 K=6 5 steps"] = {"us_per_pass": round(us, 2), "patches_per_s": round(B * 1e6 / us, 1),
                                                         "launches_per_pass": nl, "passes_in_flight": NFLY}
+    us, nl = ring_rate(B, H, W, K, (32, 32), NINST, NFLY, inst_dtype=torch.uint16)
+    out["configs[1] with uint16 instance maps"] = {
+        "us_per_pass": round(us, 2), "patches_per_s": round(B * 1e6 / us, 1), "launches_per_pass": nl,
+        "passes_in_flight": NFLY, "h2d_bytes_per_step_saved": 2 * B * H * W,
+        "note": "the headline workload with the label image in Cellpose's own dtype (uint16 below 65 536 labels, "
+                "conductor.py:180) instead of int32: 2 B/pixel less over the host link and out of HBM; results identical"}
     us64, _ = ring_rate(B, H, W, K, (32, 32), NINST, NFLY, reps=64)
     out["configs[3] 64 tiles 1024x1024 K=11"] = {"ms_for_64_tiles_one_gpu": round(us64 * 8 / 1e3, 3),
                                                  "tiles_per_s": round(B * 1e6 / us64, 1),

@@ -51,7 +51,9 @@ enum { LDIFF_STATUS_PRED_RANGE = 1, LDIFF_STATUS_INST_RANGE = 2, LDIFF_STATUS_SW
 /* Scheduling / variant knobs (no effect on results, except LDIFF_TUNE_PHILOX_ROUNDS).  A value set here applies to
  * the launches issued after the call.  Before the first ldiff_tune of a knob its environment variable, else the default, applies.
  *  LDIFF_TUNE_ARGMAX_VARIANT (env LDIFF_ARGMAX_VARIANT, default 0): ldiff_lift_argmax runs 0 = the envelope
- *    kernel, 4 / 5 = round 1's per-pixel evaluation kernel with 2 / 1 columns per thread (A/B timing);
+ *    kernel - its row form (a thread sweeps an output row; x32 horizontal lifts with a vertical lift of x29 or more
+ *    and a 16-byte aligned mask) where the shape allows it, else its column form -, 1 = the column form always,
+ *    4 / 5 = round 1's per-pixel evaluation kernel with 2 / 1 columns per thread (A/B timing);
  *  LDIFF_TUNE_DECODE_TAIL_SMS (env LDIFF_DT_SMS, default 0 = all): the register-staged decode tail sizes its
  *    one-wave grid for that many SMs;
  *  LDIFF_TUNE_DECODE_TAIL_TMA (env LDIFF_DT_TMA, default 6): 0 = register-staged decode tail, 1..6 = the
@@ -234,12 +236,21 @@ int ldiff_cell_classify(const void* inst_feats, const void* weight, const float*
  * LDIFF_STATUS_INST_RANGE. */
 int ldiff_lut_paint(const int32_t* inst, const uint8_t* lut, uint8_t* mask, int64_t n_per_image,
                     int B, int lut_size, int64_t lut_stride, int* status, void* stream);
+/* the same for the uint16 label image Cellpose's `eval` returns below 65 536 labels (conductor.py:180: the
+ * reference compares that array as it is, `masks == inst_id`, :193,227): no widening copy on the host, half the
+ * bytes over the host link and out of HBM (3 B/pixel instead of 5). */
+int ldiff_lut_paint_u16(const uint16_t* inst, const uint8_t* lut, uint8_t* mask, int64_t n_per_image,
+                        int B, int lut_size, int64_t lut_stride, int* status, void* stream);
 /* painting + the a-6 histogram in one pass (6 B/pixel instead of 5 + 2): C[(K+1),K] += counts of
  * (gt, mask) over the whole batch; xchg / channel as in ldiff_lift_argmax_hist.  K <= 15,
  * n_per_image % 16 == 0, 16-byte aligned planes; otherwise use ldiff_lut_paint + ldiff_confusion_hist. */
 int ldiff_lut_paint_hist(const int32_t* inst, const uint8_t* lut, uint8_t* mask, const uint8_t* gt,
                          int64_t* C, int64_t n_per_image, int B, int lut_size, int64_t lut_stride, int K,
                          void* xchg, int channel, int* status, void* stream);
+/* ... with uint16 instance ids (see ldiff_lut_paint_u16): 4 B/pixel. */
+int ldiff_lut_paint_hist_u16(const uint16_t* inst, const uint8_t* lut, uint8_t* mask, const uint8_t* gt,
+                             int64_t* C, int64_t n_per_image, int B, int lut_size, int64_t lut_stride, int K,
+                             void* xchg, int channel, int* status, void* stream);
 /* first-maximum argmax over the channel axis of [B,K,HW] (the argmax taken
  * inside utils.py:56, :85, evaluate.py:12, :30 on one-hot / logit inputs). */
 int ldiff_argmax_channels(const void* x, uint8_t* out, int B, int K, int64_t hw, int dtype,

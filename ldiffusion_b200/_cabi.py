@@ -53,6 +53,8 @@ SIGNATURES = {
                                        c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "ldiff_lut_paint_hist": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int,
                                      c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    "ldiff_lut_paint_hist_u16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int,
+                                         c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "ldiff_lift_argmax": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                   c_void_p]),
     "ldiff_cell_classify": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p,
@@ -60,6 +62,8 @@ SIGNATURES = {
     "ldiff_copy_planes_u8": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int64, c_void_p]),
     "ldiff_lut_paint": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int64,
                                 c_void_p, c_void_p]),
+    "ldiff_lut_paint_u16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int64,
+                                    c_void_p, c_void_p]),
     "ldiff_argmax_channels": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_void_p]),
     "ldiff_confusion_hist": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
                                      c_void_p, c_void_p]),

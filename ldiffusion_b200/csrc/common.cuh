@@ -74,6 +74,20 @@ template <> struct Vec8<__nv_bfloat16> {
   }
 };
 
+// 16 consecutive instance ids of a label image as four int4 (the unit the LUT paint kernels work on), from int32
+// ids or from the uint16 ids Cellpose hands over below 65 536 labels (conductor.py:180)
+__device__ __forceinline__ void load_ids16(const int32_t* p, int4 (&q)[4]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) q[j] = __ldcs(reinterpret_cast<const int4*>(p) + j);
+}
+__device__ __forceinline__ void load_ids16(const uint16_t* p, int4 (&q)[4]) {
+  const uint4 a = __ldcs(reinterpret_cast<const uint4*>(p)), b = __ldcs(reinterpret_cast<const uint4*>(p) + 1);
+  const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    q[j] = make_int4((int)(w[2 * j] & 0xffffu), (int)(w[2 * j] >> 16), (int)(w[2 * j + 1] & 0xffffu), (int)(w[2 * j + 1] >> 16));
+}
+
 // Optional side job of a chain's FIRST kernel: zero the int64 counters (a confusion matrix) that a later
 // kernel of the same stream accumulates into, so a pass needs no memset node that every chain waits for.
 __device__ __forceinline__ void clear_counters(unsigned long long* __restrict__ p, int n) {

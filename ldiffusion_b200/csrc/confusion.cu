@@ -104,9 +104,9 @@ confusion_hist_push_kernel(const uint8_t* __restrict__ pred, const uint8_t* __re
 // 1 (mask) out.  K <= 15 (byte-sized bins); one matrix for the whole batch (grid.y = image picks the LUT).
 // (256-thread blocks of <= 48 registers: 12 K registers and 17 KB of shared memory per block, so that blocks slot in
 // next to the resident decode-tail CTAs of the concurrent pass instead of waiting for half an SM's register file)
-template <bool PUSH>
+template <bool PUSH, typename IdT>
 __global__ void __launch_bounds__(256, 5)
-lut_paint_hist_kernel(const int32_t* __restrict__ inst, const uint8_t* __restrict__ lut, uint8_t* __restrict__ mask,
+lut_paint_hist_kernel(const IdT* __restrict__ inst, const uint8_t* __restrict__ lut, uint8_t* __restrict__ mask,
                       const uint8_t* __restrict__ gt, unsigned long long* __restrict__ C, int64_t n, int lut_size,
                       int64_t lut_stride, int K, int* __restrict__ status, XchgPush px) {
   extern __shared__ uint32_t hist[];                 // [nbins][32]
@@ -122,7 +122,7 @@ lut_paint_hist_kernel(const int32_t* __restrict__ inst, const uint8_t* __restric
   //  register pair halves the kernel's address arithmetic — and measured +3..6 us per PASS in a same-box A/B
   //  (tools/ab_pass.sh): the kernel then issues its scattered loads in denser bursts next to the decode tails)
   const uint8_t* l = lut + b * lut_stride;
-  const int32_t* in = inst + b * n;
+  const IdT* in = inst + b * n;
   const uint8_t* g = gt + b * n;
   uint8_t* out = mask + b * n;
   int badid = 0;
@@ -140,10 +140,8 @@ lut_paint_hist_kernel(const int32_t* __restrict__ inst, const uint8_t* __restric
   };
   const int64_t nvec = n >> 4;                       // (host: n % 16 == 0, 16-byte aligned planes)
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
-    const int4* p = reinterpret_cast<const int4*>(in) + 4 * v;
     int4 q[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) q[j] = __ldcs(p + j);
+    load_ids16(in + 16 * v, q);
     const uint4 gw = __ldcs(reinterpret_cast<const uint4*>(g) + v);
     uint32_t w[4];
 #pragma unroll
@@ -412,9 +410,10 @@ int ldiff::xchg_push_args(void* handle, int channel, int n_i64, XchgPush* px) {
   return LDIFF_OK;
 }
 
-extern "C" int ldiff_lut_paint_hist(const int32_t* inst, const uint8_t* lut, uint8_t* mask, const uint8_t* gt,
-                                    int64_t* C, int64_t n_per_image, int B, int lut_size, int64_t lut_stride,
-                                    int K, void* xchg, int channel, int* status, void* stream) {
+template <typename IdT>
+static int launch_lut_paint_hist(const IdT* inst, const uint8_t* lut, uint8_t* mask, const uint8_t* gt,
+                                 int64_t* C, int64_t n_per_image, int B, int lut_size, int64_t lut_stride,
+                                 int K, void* xchg, int channel, int* status, void* stream) {
   if (!inst || !lut || !mask || !gt || !C || !status || n_per_image < 0 || B < 0 || lut_size < 1 || K < 1)
     return LDIFF_EINVAL;
   if (K > 15 || B > 65535) return LDIFF_EUNSUPPORTED;  // byte-sized bins; larger K: ldiff_lut_paint + ldiff_confusion_hist
@@ -433,12 +432,26 @@ extern "C" int ldiff_lut_paint_hist(const int32_t* inst, const uint8_t* lut, uin
   const dim3 grid((unsigned)bx, (unsigned)B);
   unsigned long long* Cu = reinterpret_cast<unsigned long long*>(C);
   if (xchg)
-    lut_paint_hist_kernel<true><<<grid, threads, smem, (cudaStream_t)stream>>>(inst, lut, mask, gt, Cu, n_per_image,
+    lut_paint_hist_kernel<true, IdT><<<grid, threads, smem, (cudaStream_t)stream>>>(inst, lut, mask, gt, Cu, n_per_image,
                                                                              lut_size, lut_stride, K, status, px);
   else
-    lut_paint_hist_kernel<false><<<grid, threads, smem, (cudaStream_t)stream>>>(inst, lut, mask, gt, Cu, n_per_image,
+    lut_paint_hist_kernel<false, IdT><<<grid, threads, smem, (cudaStream_t)stream>>>(inst, lut, mask, gt, Cu, n_per_image,
                                                                               lut_size, lut_stride, K, status, px);
   return check_launch();
+}
+
+extern "C" int ldiff_lut_paint_hist(const int32_t* inst, const uint8_t* lut, uint8_t* mask, const uint8_t* gt,
+                                    int64_t* C, int64_t n_per_image, int B, int lut_size, int64_t lut_stride,
+                                    int K, void* xchg, int channel, int* status, void* stream) {
+  return launch_lut_paint_hist(inst, lut, mask, gt, C, n_per_image, B, lut_size, lut_stride, K, xchg, channel, status,
+                               stream);
+}
+
+extern "C" int ldiff_lut_paint_hist_u16(const uint16_t* inst, const uint8_t* lut, uint8_t* mask, const uint8_t* gt,
+                                        int64_t* C, int64_t n_per_image, int B, int lut_size, int64_t lut_stride,
+                                        int K, void* xchg, int channel, int* status, void* stream) {
+  return launch_lut_paint_hist(inst, lut, mask, gt, C, n_per_image, B, lut_size, lut_stride, K, xchg, channel, status,
+                               stream);
 }
 
 extern "C" int ldiff_confusion_hist_push(const uint8_t* pred, const uint8_t* gt, const uint8_t* gt_lut,

@@ -417,9 +417,9 @@ cell_classify_kernel(const T* __restrict__ feats, const T* __restrict__ weight,
 // mask[b,p] = lut[b][inst[b,p]], 16 pixels per thread.  The image's LUT (a few hundred
 // bytes) is copied to shared memory first (SMEM_LUT) so the per-pixel lookup is an LDS;
 // ids are range-checked four at a time (max of the unsigned ids).
-template <bool SMEM_LUT>
+template <bool SMEM_LUT, typename IdT>
 __global__ void __launch_bounds__(256)
-lut_paint_kernel(const int32_t* __restrict__ inst, const uint8_t* __restrict__ lut,
+lut_paint_kernel(const IdT* __restrict__ inst, const uint8_t* __restrict__ lut,
                  uint8_t* __restrict__ mask, int64_t n, int lut_size, int64_t lut_stride,
                  int* __restrict__ status) {
   extern __shared__ uint8_t s_lut[];
@@ -431,7 +431,7 @@ lut_paint_kernel(const int32_t* __restrict__ inst, const uint8_t* __restrict__ l
     l = s_lut;
   }
   // (global LUT: the loads below go through L1; the table is a few hundred bytes)
-  const int32_t* in = inst + b * n;
+  const IdT* in = inst + b * n;
   uint8_t* out = mask + b * n;
   int bad = 0;
   auto look4 = [&](int4 q) -> uint32_t {
@@ -449,10 +449,8 @@ lut_paint_kernel(const int32_t* __restrict__ inst, const uint8_t* __restrict__ l
   const int64_t nvec = n >> 4;
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec;
        v += (int64_t)gridDim.x * blockDim.x) {
-    const int4* p = reinterpret_cast<const int4*>(in) + 4 * v;
     int4 q[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) q[j] = __ldcs(p + j);
+    load_ids16(in + 16 * v, q);
     uint32_t w[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) w[j] = look4(q[j]);
@@ -612,9 +610,9 @@ extern "C" int ldiff_cell_classify(const void* inst_feats, const void* weight, c
   return check_launch();
 }
 
-extern "C" int ldiff_lut_paint(const int32_t* inst, const uint8_t* lut, uint8_t* mask,
-                               int64_t n_per_image, int B, int lut_size, int64_t lut_stride,
-                               int* status, void* stream) {
+template <typename IdT>
+static int launch_lut_paint(const IdT* inst, const uint8_t* lut, uint8_t* mask, int64_t n_per_image, int B,
+                            int lut_size, int64_t lut_stride, int* status, void* stream) {
   if (!inst || !lut || !mask || !status || n_per_image < 0 || B < 0 || lut_size < 1) return LDIFF_EINVAL;
   if (n_per_image == 0 || B == 0) return LDIFF_OK;
   if (!aligned16(inst) || !aligned16(mask) || (B > 1 && (n_per_image % 16))) return LDIFF_EALIGN;
@@ -623,12 +621,24 @@ extern "C" int ldiff_lut_paint(const int32_t* inst, const uint8_t* lut, uint8_t*
   // (measured: the L1-cached global LUT beats a per-block shared-memory copy at 800 entries: 9.4 vs 10.5 us)
   static const bool smem_lut = getenv("LDIFF_PAINT_SMEM_LUT") != nullptr;
   if (smem_lut && lut_size <= 32 * 1024)
-    lut_paint_kernel<true><<<grid, 256, (size_t)lut_size, (cudaStream_t)stream>>>(
+    lut_paint_kernel<true, IdT><<<grid, 256, (size_t)lut_size, (cudaStream_t)stream>>>(
         inst, lut, mask, n_per_image, lut_size, lut_stride, status);
   else
-    lut_paint_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(inst, lut, mask, n_per_image, lut_size,
-                                                                    lut_stride, status);
+    lut_paint_kernel<false, IdT><<<grid, 256, 0, (cudaStream_t)stream>>>(inst, lut, mask, n_per_image, lut_size,
+                                                                         lut_stride, status);
   return check_launch();
+}
+
+extern "C" int ldiff_lut_paint(const int32_t* inst, const uint8_t* lut, uint8_t* mask,
+                               int64_t n_per_image, int B, int lut_size, int64_t lut_stride,
+                               int* status, void* stream) {
+  return launch_lut_paint(inst, lut, mask, n_per_image, B, lut_size, lut_stride, status, stream);
+}
+
+extern "C" int ldiff_lut_paint_u16(const uint16_t* inst, const uint8_t* lut, uint8_t* mask,
+                                   int64_t n_per_image, int B, int lut_size, int64_t lut_stride,
+                                   int* status, void* stream) {
+  return launch_lut_paint(inst, lut, mask, n_per_image, B, lut_size, lut_stride, status, stream);
 }
 
 extern "C" int ldiff_argmax_channels(const void* x, uint8_t* out, int B, int K, int64_t hw, int dtype,

@@ -39,7 +39,7 @@ def cell_mask(inst_map: torch.Tensor, inst_feats: torch.Tensor, weight: torch.Te
               bias: Optional[torch.Tensor], inst_ids: torch.Tensor, lut_size: Optional[int] = None):
     """conductor.py:218-231 + segmentor.py:536 for one image or a batch.
 
-    inst_map int32 [H,W] (Cellpose instance ids, 0 = background); inst_feats
+    inst_map int32 or uint16 [H,W] (Cellpose instance ids, 0 = background); inst_feats
     [N,256] pooled features of the instances the reference keeps; inst_ids [N].
     Instances the reference skips simply have no LUT entry (class 0).
     """

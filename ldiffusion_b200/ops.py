@@ -260,13 +260,24 @@ def _lift_argmax_hist(logits: Tensor, mask: Tensor, gt: Tensor, C: Tensor, statu
                                              channel, _ptr(status), _stream(logits)))
 
 
+def _ids16(inst: Tensor) -> bool:
+    """Instance maps are int32 or — what Cellpose's ``eval`` returns below 65 536 labels (conductor.py:180) —
+    uint16 (``torch.from_numpy`` of that array; an int16 view of the same bytes is taken as unsigned)."""
+    if inst.dtype == torch.int32:
+        return False
+    if inst.dtype in (torch.uint16, torch.int16):
+        return True
+    raise TypeError(f"instance map must be int32 or uint16, got {inst.dtype}")
+
+
 def _lut_paint_hist(inst: Tensor, lut: Tensor, mask: Tensor, gt: Tensor, C: Tensor, K: int, status: Tensor,
                     xchg=None, channel: int = 0) -> None:
     _cuda(inst, lut, mask, gt, C, status)
     B = inst.shape[0]
     n = inst[0].numel()
     lut_stride = lut.stride(0) if lut.dim() == 2 else 0
-    check(_cabi.lib().ldiff_lut_paint_hist(_ptr(inst), _ptr(lut), _ptr(mask), _ptr(gt), _ptr(C), n, B, lut.shape[-1],
+    fn = _cabi.lib().ldiff_lut_paint_hist_u16 if _ids16(inst) else _cabi.lib().ldiff_lut_paint_hist
+    check(fn(_ptr(inst), _ptr(lut), _ptr(mask), _ptr(gt), _ptr(C), n, B, lut.shape[-1],
                                            lut_stride, K, xchg, channel, _ptr(status), _stream(inst)))
 
 
@@ -300,8 +311,8 @@ def _lut_paint(inst: Tensor, lut: Tensor, mask: Tensor, status: Tensor) -> None:
     B = inst.shape[0]
     n = inst[0].numel()
     lut_stride = lut.stride(0) if lut.dim() == 2 else 0
-    check(_cabi.lib().ldiff_lut_paint(_ptr(inst), _ptr(lut), _ptr(mask), n, B, lut.shape[-1],
-                                      lut_stride, _ptr(status), _stream(inst)))
+    fn = _cabi.lib().ldiff_lut_paint_u16 if _ids16(inst) else _cabi.lib().ldiff_lut_paint
+    check(fn(_ptr(inst), _ptr(lut), _ptr(mask), n, B, lut.shape[-1], lut_stride, _ptr(status), _stream(inst)))
 
 
 def _argmax_channels(x: Tensor, out: Tensor) -> None:
@@ -770,9 +781,8 @@ def copy_planes_u8(src: Tensor, dst: Tensor) -> Tensor:
 
 
 def lut_paint(inst: Tensor, lut: Tensor, out: Optional[Tensor] = None) -> Tensor:
-    """mask[b,y,x] = lut[b][inst[b,y,x]] (conductor.py:224-231 + segmentor.py:536)."""
-    if inst.dtype != torch.int32:
-        raise TypeError("instance map must be int32")
+    """mask[b,y,x] = lut[b][inst[b,y,x]] (conductor.py:224-231 + segmentor.py:536); ``inst`` int32 or uint16."""
+    _ids16(inst)
     _cuda(inst, lut)
     if inst.dim() == 2:
         inst = inst.unsqueeze(0)
@@ -825,9 +835,9 @@ def lift_argmax_hist(logits: Tensor, size, gt: Tensor, *, out: Optional[Tensor] 
 def lut_paint_hist(inst: Tensor, lut: Tensor, gt: Tensor, num_classes: int, *, out: Optional[Tensor] = None,
                    mask_out: Optional[Tensor] = None, exchange=None, channel: int = 0):
     """``lut_paint`` and ``confusion_hist(mask, gt)`` in ONE kernel (6 B/pixel instead of 5 + 2): returns
-    (mask, C).  Falls back to the two separate kernels for K > 15 or planes that are not 16-pixel aligned."""
-    if inst.dtype != torch.int32:
-        raise TypeError("instance map must be int32")
+    (mask, C); ``inst`` int32 or uint16 (4 B/pixel).  Falls back to the two separate kernels for K > 15 or planes
+    that are not 16-pixel aligned."""
+    _ids16(inst)
     _cuda(inst, lut, gt)
     if inst.dim() == 2:
         inst, gt = inst.unsqueeze(0), gt.unsqueeze(0) if gt.dim() == 2 else gt

@@ -39,7 +39,7 @@ class HotPathInputs:
     eps: List[torch.Tensor]          # n x [B,4,H/8,W/8] UNet outputs
     decoded: List[torch.Tensor]      # n x [B,3,H,W] VAE decoder outputs
     head_feat: torch.Tensor          # [B,256,h,w] tissue decoder features
-    inst_map: torch.Tensor           # int32 [B,H,W] Cellpose instance ids
+    inst_map: torch.Tensor           # int32 or uint16 (Cellpose's own dtype below 65 536 labels) [B,H,W] instance ids
     inst_feats: torch.Tensor         # [B,N,256] pooled instance features
     gt: torch.Tensor                 # uint8 [B,H,W] ground-truth classes
     slab = None                      # set by packed(): the uint8 tensor all fields are views of
@@ -491,10 +491,11 @@ class HotPathRing:
 
 
 def synth_inputs(batch, height, width, num_classes, num_steps=5, dtype=torch.bfloat16, device="cpu",
-                 head_hw=(32, 32), n_instances=800, seed=1234, pin=False) -> HotPathInputs:
+                 head_hw=(32, 32), n_instances=800, seed=1234, pin=False, inst_dtype=torch.int32) -> HotPathInputs:
     """Seeded synthetic PUMA-shaped inputs: latents 5.5*N(0,1) (raw SD VAE-mean
     scale), eps N(0,1), decoded U(-1.2,1.2), features N(0,1), ~n_instances square cells per patch,
-    gt 70% background + blobs of classes 1..K-1 + 0.1% 'other' (255) pixels."""
+    gt 70% background + blobs of classes 1..K-1 + 0.1% 'other' (255) pixels.  ``inst_dtype``: int32 (default) or
+    uint16, the label image as Cellpose returns it (same values, same random stream)."""
     g = torch.Generator(device="cpu").manual_seed(seed)
     lat = (batch, 4, height // 8, width // 8)
 
@@ -522,4 +523,4 @@ def synth_inputs(batch, height, width, num_classes, num_steps=5, dtype=torch.bfl
             gt[b, y:y + side, x:x + side] = int(cls[b, i])
     other = torch.rand(batch, height, width, generator=g) < 0.001
     gt[other] = 255
-    return HotPathInputs(latents, eps, decoded, head_feat, fin(inst), inst_feats, fin(gt))
+    return HotPathInputs(latents, eps, decoded, head_feat, fin(inst.to(inst_dtype)), inst_feats, fin(gt))

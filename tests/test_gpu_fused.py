@@ -152,6 +152,38 @@ def test_lut_paint_hist_equals_separate_launches(K, B, H, W):
     ops.check_status("cuda")
 
 
+@pytest.mark.parametrize("K,B,H,W", [(11, 2, 256, 256), (6, 1, 64, 48), (20, 1, 64, 64), (11, 1, 30, 30)])
+def test_lut_paint_uint16_instance_maps(K, B, H, W):
+    """Cellpose's label image is uint16 below 65 536 labels (conductor.py:180): painting and the fused histogram
+    take it as it is and give what the int32 form and the oracle give — also for ids above 32 767 (an int16 view
+    of the same bytes is read as unsigned) and for ids outside the LUT."""
+    ops = _ops()
+    rng = np.random.default_rng(K * H + 1)
+    N = 40000
+    ids = rng.integers(0, N + 1, (B, H, W))
+    ids[:, 0, :8] = [0, 1, 32767, 32768, 39999, N, 5, 0]
+    lut_np = rng.integers(0, K, (B, N + 1)).astype(np.uint8)
+    lut = torch.from_numpy(lut_np).cuda()
+    gt = rng.integers(0, K + 2, (B, H, W)).astype(np.uint8)
+    gt[gt >= K] = 255
+    gtd = torch.from_numpy(gt).cuda()
+    i32 = torch.from_numpy(ids.astype(np.int32)).cuda()
+    u16 = torch.from_numpy(ids.astype(np.uint16)).cuda()
+    want = np.stack([ohead.cell_paint_spec(ids[b], lut_np[b]) for b in range(B)])
+    for inst in (u16, u16.view(torch.int16)):
+        assert np.array_equal(ops.lut_paint(inst, lut).cpu().numpy(), want)
+        mask, C = ops.lut_paint_hist(inst, lut, gtd, K)
+        assert np.array_equal(mask.cpu().numpy(), want)
+        assert np.array_equal(C.cpu().numpy(), omet.confusion_matrix(want, gt, K))
+    assert torch.equal(ops.lut_paint(i32, lut), ops.lut_paint(u16, lut))
+    ops.check_status("cuda")
+    ops.lut_paint(u16, lut[:, :1000].contiguous())             # ids outside a shorter LUT: class 0 + a status bit
+    with pytest.raises(RuntimeError):
+        ops.check_status("cuda")
+    with pytest.raises(TypeError):
+        ops.lut_paint(i32.long(), lut)
+
+
 def test_lut_paint_hist_range_errors():
     ops = _ops()
     inst = torch.tensor([[0, 1, 5, 2]], dtype=torch.int32).repeat(4, 4).cuda()

@@ -188,6 +188,37 @@ def test_tissue_config_classes(K):
     assert np.array_equal(res["confusion"].cpu().numpy(), want)
 
 
+def test_pass_with_uint16_instance_maps_equals_the_int32_pass():
+    """The same batch with Cellpose's uint16 label image: every result of the pass is identical, from device
+    tensors and through the packed host slab (run_host), and the slab is 2 B/pixel smaller."""
+    from ldiffusion_b200 import ops
+    from ldiffusion_b200.pipeline import HotPath, HotPathInputs, synth_inputs
+    res, nbytes = {}, {}
+    for dt in (torch.int32, torch.uint16):
+        host = synth_inputs(CFG["batch"], CFG["height"], CFG["width"], CFG["num_classes"], CFG["num_steps"],
+                            dtype=torch.bfloat16, device="cpu", head_hw=(8, 8), n_instances=CFG["n_instances"], seed=5,
+                            inst_dtype=dt)
+        assert host.inst_map.dtype == dt
+        dev = HotPathInputs(*[([t.cuda() for t in f] if isinstance(f, list) else f.cuda()) for f in host.fields()])
+        hp = HotPath(dtype=torch.bfloat16, device="cuda", head_hw=(8, 8), seed=5, **CFG)
+        hp.run(dev)
+        torch.cuda.synchronize()
+        ops.check_status("cuda")
+        res[dt] = {k: (v.clone() if torch.is_tensor(v) else [t.clone() for t in v]) for k, v in hp.results().items()}
+        packed = host.packed()
+        out = [hp.alloc_host_results()]
+        hp.run_host([packed], out)
+        torch.cuda.synchronize()
+        ops.check_status("cuda")
+        assert torch.equal(out[0]["mask_cell"], res[dt]["mask_cell"].cpu())
+        assert torch.equal(out[0]["confusion"], res[dt]["confusion"].cpu())
+        nbytes[dt] = hp.host_bytes_per_step(packed)[0]
+    for k, v in res[torch.int32].items():
+        for a, b in zip(v if isinstance(v, list) else [v], res[torch.uint16][k] if isinstance(v, list) else [res[torch.uint16][k]]):
+            assert torch.equal(a, b), k
+    assert nbytes[torch.int32] - nbytes[torch.uint16] == 2 * CFG["batch"] * CFG["height"] * CFG["width"]
+
+
 def test_tiling_64_tiles_sharded_matches_single_pass():
     """configs[3]: 64 tiles, tile i -> rank i mod W for W in 1/2/4/8 (ranks emulated one after the
     other on this GPU): the summed per-rank matrices equal the single-pass matrix and the oracle,

@@ -58,7 +58,7 @@ def test_lift_argmax_variants_bit_exact(tune, variant):
                            (15, (1, 8, 8), (64, 66)), (3, (1, 5, 7), (45, 63)),
                            # x32 horizontal lifts the row form takes: rows not a multiple of 256, a x40 vertical lift, one
                            # and two source columns (half chunks only / a lone last chunk), K = 1 and K = 15
-                           (5, (1, 5, 3), (160, 96)), (4, (2, 4, 4), (160, 128)), (1, (1, 2, 1), (50, 32)),
+                           (5, (1, 5, 3), (160, 96)), (4, (2, 4, 4), (160, 128)), (1, (1, 2, 1), (64, 32)),
                            (15, (1, 3, 2), (96, 64)), (11, (1, 9, 7), (300, 224))):
         logits = torch.randn((shape[0], K) + shape[1:], generator=g)
         got = torch.full((shape[0],) + size, 0xEE, dtype=torch.uint8, device="cuda")   # poisoned: a kernel that skips

@@ -43,6 +43,10 @@ insts = [torch.randint(0, 801, (B, H, W), dtype=torch.int32, device=dev) for _ i
 lut = torch.randint(0, K, (B, 801), dtype=torch.uint8, device=dev)
 line("lut_paint", timeit(lambda i: ops.lut_paint(insts[i], lut, out=mask), 4), 5 * px)
 line("lut_paint_hist", timeit(lambda i: ops.lut_paint_hist(insts[i], lut, gt, K, out=C, mask_out=mask), 4), 6 * px)
+insts16 = [torch.from_numpy(t.cpu().numpy().astype("uint16")).to(dev) for t in insts]
+line("lut_paint uint16 ids", timeit(lambda i: ops.lut_paint(insts16[i], lut, out=mask), 4), 3 * px)
+line("lut_paint_hist uint16 ids", timeit(lambda i: ops.lut_paint_hist(insts16[i], lut, gt, K, out=C, mask_out=mask), 4), 4 * px)
+del insts16
 
 # decode tails
 imgs = [torch.empty(B, 3, H, W, device=dev, dtype=torch.bfloat16).uniform_(-1.2, 1.2) for _ in range(6)]
