@@ -134,26 +134,37 @@ lift_argmax_row_kernel(const float* __restrict__ logits, uint8_t* __restrict__ m
         if (r >= ncol) continue;
         const float l = __fmul_rn((float)r + 0.5f, 1.f / kRowF);         // exact
         const float2 l2 = make_float2(l, l);
+        // (the maxima and the candidate bits below are folded as TWO interleaved chains each: the kernel lives on
+        //  latency — 5 warps per scheduler, issue slots half idle — and a 6-deep FMNMX3 / 12-deep SHF chain is most
+        //  of a sweep step's critical path)
         float2 v2[KP];
-        float m = -INFINITY;
+        float m = -INFINITY, mb = -INFINITY;
 #pragma unroll
         for (int j = 0; j < KP; ++j) {
           v2[j] = __ffma2_rn(l2, D2[j], T2[j]);
-          m = fmaxf(m, fmaxf(v2[j].x, v2[j].y));
+          if (j & 1) mb = fmaxf(mb, fmaxf(v2[j].x, v2[j].y));
+          else m = fmaxf(m, fmaxf(v2[j].x, v2[j].y));
         }
+        m = fmaxf(m, mb);
         const float thr = __fsub_rn(m, gap);
         const float2 thr2 = make_float2(thr, thr), neg1 = make_float2(-1.f, -1.f);
         // n_k = thr - v_k: negative exactly for the classes within the gap of the leader (sign bits funnel-shifted
         // together: bit 2*KP-1-k <=> class k), positive = the lead to lose
         float2 n2[KP];
-        uint32_t cand = 0;
+        constexpr int KH = KP / 2;                       // pairs [0, KH) and [KH, KP) gather their bits side by side
+        uint32_t cand = 0, candb = 0;
 #pragma unroll
         for (int j = 0; j < KP; ++j) {
           n2[j] = __ffma2_rn(v2[j], neg1, thr2);
-          cand = __funnelshift_l(__float_as_uint(n2[j].x), cand, 1);
-          cand = __funnelshift_l(__float_as_uint(n2[j].y), cand, 1);
+          if (j < KH) {
+            cand = __funnelshift_l(__float_as_uint(n2[j].x), cand, 1);
+            cand = __funnelshift_l(__float_as_uint(n2[j].y), cand, 1);
+          } else {
+            candb = __funnelshift_l(__float_as_uint(n2[j].x), candb, 1);
+            candb = __funnelshift_l(__float_as_uint(n2[j].y), candb, 1);
+          }
         }
-        cand &= (1u << (2 * KP)) - 1u;
+        cand = (cand << (2 * (KP - KH))) | candb;
         const bool unc = !sane || cand == 0u || (cand & (cand - 1)) != 0;   // (cand == 0: NaN logits)
         uint32_t cls = 0u;
         int rend = r + 1;
@@ -161,13 +172,15 @@ lift_argmax_row_kernel(const float* __restrict__ logits, uint8_t* __restrict__ m
           const int a = __clz(cand) - (32 - 2 * KP);
           const float nDa = -dl[a];
           const float2 nDa2 = make_float2(nDa, nDa);
-          float rmax = 0.f;
+          float rmax = 0.f, rmaxb = 0.f;
 #pragma unroll
           for (int j = 0; j < KP; ++j) {                 // class a itself: 0 * (1 / -gap) = -0, never the maximum
             const float2 e = __fadd2_rn(D2[j], nDa2);
             const float2 q = __fmul2_rn(e, make_float2(rcp_approx_row(n2[j].x), rcp_approx_row(n2[j].y)));
-            rmax = fmaxf(rmax, fmaxf(q.x, q.y));
+            if (j & 1) rmaxb = fmaxf(rmaxb, fmaxf(q.x, q.y));
+            else rmax = fmaxf(rmax, fmaxf(q.x, q.y));
           }
+          rmax = fmaxf(rmax, rmaxb);
           cls = (uint32_t)a;
           rend = ncol;
           if (rmax > 0.f) {

@@ -64,3 +64,6 @@ def test_blackwell_instructions_are_present(sass):
     env = [f for f in per_function("FFMA2") if "lift_argmax_env" in f]
     assert env and any("lift_argmax_env" in f for f in per_function(r"MUFU\.RCP"))   # the envelope sweep's run lengths
     assert any("lift_argmax_env" in f for f in per_function("LDGSTS"))          # cp.async ground-truth tile
+    row = [f for f in per_function("FFMA2") if "lift_argmax_row" in f]          # the row form: same packed sweep
+    assert row and any("lift_argmax_row" in f for f in per_function(r"MUFU\.RCP"))
+    assert any("lift_argmax_row" in f for f in per_function("FMNMX3"))
