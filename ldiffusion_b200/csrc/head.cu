@@ -493,8 +493,8 @@ bool lift_argmax_env_ok(int K, int h, int H);                                   
 int launch_lift_argmax_env(const float* logits, uint8_t* mask, const uint8_t* gt, int64_t* C, int B, int K, int h,
                            int w, int H, int W, int* status, const XchgPush* px, cudaStream_t st);
 bool lift_argmax_row_ok(int K, int h, int w, int H, int W, const void* mask);    // lift_argmax_row.cu
-int launch_lift_argmax_row(const float* logits, uint8_t* mask, int B, int K, int h, int w, int H, int W,
-                           cudaStream_t st);
+int launch_lift_argmax_row(const float* logits, uint8_t* mask, const uint8_t* gt, int64_t* C, int B, int K, int h,
+                           int w, int H, int W, int* status, const XchgPush* px, cudaStream_t st);
 
 }  // namespace ldiff
 
@@ -512,7 +512,7 @@ extern "C" int ldiff_lift_argmax(const float* logits, uint8_t* mask, int B, int 
   // thread (kept for A/B timing: tools/kbench_argmax.py)
   const int variant = tune_get(LDIFF_TUNE_ARGMAX_VARIANT);
   if (variant == 0 && lift_argmax_row_ok(K, h, w, H, W, mask))
-    return launch_lift_argmax_row(logits, mask, B, K, h, w, H, W, st);
+    return launch_lift_argmax_row(logits, mask, nullptr, nullptr, B, K, h, w, H, W, nullptr, nullptr, st);
   if (variant <= 1 && H >= 4 * h && lift_argmax_env_ok(K, h, H))
     return launch_lift_argmax_env(logits, mask, nullptr, nullptr, B, K, h, w, H, W, nullptr, nullptr, st);
   if (K <= 15 && H >= 4 * h && max_band_rows(h, H) <= kBand && h <= 65535) {
@@ -548,6 +548,10 @@ extern "C" int ldiff_lift_argmax_hist(const float* logits, uint8_t* mask, const 
     if (rc != LDIFF_OK) return rc;
   }
   if (B == 0) return xchg ? LDIFF_EINVAL : LDIFF_OK;       // a push needs a launch
+  if (tune_get(LDIFF_TUNE_ARGMAX_VARIANT) == 0 && lift_argmax_row_ok(K, h, w, H, W, mask) &&
+      (reinterpret_cast<uintptr_t>(gt) & 15u) == 0)          // row form: 16-byte loads of the ground truth too
+    return launch_lift_argmax_row(logits, mask, gt, C, B, K, h, w, H, W, status, xchg ? &px : nullptr,
+                                  (cudaStream_t)stream);
   return launch_lift_argmax_env(logits, mask, gt, C, B, K, h, w, H, W, status, xchg ? &px : nullptr,
                                 (cudaStream_t)stream);
 }

@@ -1,6 +1,7 @@
 // a-5 lift + argmax, ROW form of the envelope kernel (sm_100a): conductor.py:135 + segmentor.py:536 for the
 // x32 horizontal lift of the path (1024 <- 32, 512 <- 16).
 #include "head_common.cuh"
+#include "hist.cuh"
 
 namespace ldiff {
 
@@ -49,13 +50,22 @@ __device__ __forceinline__ uint32_t ones_from_bit(int n) {
   return r;
 }
 
-template <int K>
+// HIST: the a-6 confusion histogram of the mask against gt in the same pass — the eight class words of a chunk meet
+// the chunk's 32 ground-truth bytes (two 16-byte loads) in registers; uncertain pixels are entered as class 0 and
+// moved to their resolved class by the epilogue.  PUSH: with the NVLink peer push as the kernel's tail (hist.cuh).
+template <int K, bool HIST, bool PUSH>
 __global__ void __launch_bounds__(kRowThreads, 1024 / kRowThreads)   // 64 registers
-lift_argmax_row_kernel(const float* __restrict__ logits, uint8_t* __restrict__ mask, AxisH ay, AxisH ax,
-                       int npairs, int nrb, int B) {
+lift_argmax_row_kernel(const float* __restrict__ logits, uint8_t* __restrict__ mask, const uint8_t* __restrict__ gt,
+                       unsigned long long* __restrict__ C, AxisH ay, AxisH ax, int npairs, int nrb, int B,
+                       int* __restrict__ status, XchgPush px) {
   __shared__ __align__(16) float s_src[K * kRowSrc * 4];   // [class][source row][c0, c1, c1, c2]
   __shared__ uint32_t s_q[kRowThreads / 32][kQueue];
   __shared__ int s_qn[kRowThreads / 32];
+  __shared__ uint32_t s_hist[HIST ? (K + 1) * K * 32 : 1];
+  __shared__ unsigned long long s_step;
+  BlockHist<32, true> h;
+  if (HIST) h.init(s_hist, K);                           // (the first item's barriers order it before any update)
+  if (PUSH && threadIdx.x == 0) s_step = xchg_step_of_launch(px);
   const int warp_in_block = threadIdx.x >> 5;
   const int plane = ay.in * ax.in;
   const int items = npairs * nrb * B;
@@ -83,6 +93,7 @@ lift_argmax_row_kernel(const float* __restrict__ logits, uint8_t* __restrict__ m
     const int ro0 = (ty.i0 - sy0) * 4, ro1 = (ty.i1 - sy0) * 4;
     const float2 hy0 = make_float2(ty.l0, ty.l0), hy1 = make_float2(ty.l1, ty.l1);
     uint8_t* orow = mask + ((int64_t)b * ay.out + min(y, ay.out - 1)) * ax.out;
+    const uint8_t* grow = HIST ? gt + ((int64_t)b * ay.out + min(y, ay.out - 1)) * ax.out : nullptr;
     bool ovf = false;
     auto enqueue = [&](int x) -> bool {                  // false: the warp's queue is full
       const int slot = atomicAdd(&s_qn[warp_in_block], 1);
@@ -207,6 +218,17 @@ lift_argmax_row_kernel(const float* __restrict__ logits, uint8_t* __restrict__ m
         uint4* o = reinterpret_cast<uint4*>(orow + xc);
         if (c != 0) o[0] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
         if (c != ax.in) o[1] = make_uint4(wd[4], wd[5], wd[6], wd[7]);
+        if (HIST) {
+          const uint4* gp = reinterpret_cast<const uint4*>(grow + xc);
+          if (c != 0) {
+            const uint4 gw = __ldg(gp);
+            h.word_trusted(wd[0], gw.x); h.word_trusted(wd[1], gw.y); h.word_trusted(wd[2], gw.z); h.word_trusted(wd[3], gw.w);
+          }
+          if (c != ax.in) {
+            const uint4 gw = __ldg(gp + 1);
+            h.word_trusted(wd[4], gw.x); h.word_trusted(wd[5], gw.y); h.word_trusted(wd[6], gw.z); h.word_trusted(wd[7], gw.w);
+          }
+        }
       }
     }
 
@@ -226,16 +248,30 @@ lift_argmax_row_kernel(const float* __restrict__ logits, uint8_t* __restrict__ m
         vals.v[k] = lerp2(tyy.l0, lerp2(tx.l0, __ldg(r0 + tx.i0), tx.l1, __ldg(r0 + tx.i1)), tyy.l1,
                           lerp2(tx.l0, __ldg(r1 + tx.i0), tx.l1, __ldg(r1 + tx.i1)));
       }
-      mask[((int64_t)b * ay.out + yy) * ax.out + x] = (uint8_t)exact_from_values<K>(vals);
+      const int cls = exact_from_values<K>(vals);
+      const int64_t o = ((int64_t)b * ay.out + yy) * ax.out + x;
+      mask[o] = (uint8_t)cls;
+      if (HIST && cls != 0) h.move(gt[o], 0u, (uint32_t)cls);
     }
     if (warp_ovf && active) {
       // a queue overflowed (e.g. constant logits): every lane re-resolves its own 64 pixels with the exact rule
       const int xa = max(kRowF * 2 * p - kRowF / 2, 0), xb = min(kRowF * (2 * p + 2) - kRowF / 2, ax.out);
       for (int x = xa; x < xb; ++x) {
         const TapH tx = tap(ax, x);
-        orow[x] = (uint8_t)exact_pixel(lb, K, plane, ax.in, ty.i0, ty.i1, ty.l0, ty.l1, tx.i0, tx.i1, tx.l0, tx.l1);
+        const uint32_t now = (uint32_t)exact_pixel(lb, K, plane, ax.in, ty.i0, ty.i1, ty.l0, ty.l1, tx.i0, tx.i1,
+                                                   tx.l0, tx.l1);
+        if (HIST) {
+          const uint32_t was = orow[x];                  // (this thread's own store)
+          if (now != was) h.move(grow[x], was, now);
+        }
+        orow[x] = (uint8_t)now;
       }
     }
+  }
+  if (HIST) {
+    __syncthreads();
+    h.flush(s_hist, C, status, true);
+    if (PUSH) xchg_push_tail(C, px, s_step, gridDim.x);
   }
 }
 
@@ -246,8 +282,9 @@ bool lift_argmax_row_ok(int K, int h, int w, int H, int W, const void* mask) {
          (reinterpret_cast<uintptr_t>(mask) & 15u) == 0;
 }
 
-int launch_lift_argmax_row(const float* logits, uint8_t* mask, int B, int K, int h, int w, int H, int W,
-                           cudaStream_t st) {
+// gt == nullptr: mask only.  px != nullptr: histogram + peer push.
+int launch_lift_argmax_row(const float* logits, uint8_t* mask, const uint8_t* gt, int64_t* C, int B, int K, int h,
+                           int w, int H, int W, int* status, const XchgPush* px, cudaStream_t st) {
   AxisH ay{(float)h / (float)H, h, H}, ax{(float)w / (float)W, w, W};
   const int npairs = (w + 2) / 2;                        // chunks 0 .. w, two per thread
   const int nrb = (H + kRowThreads - 1) / kRowThreads;
@@ -255,8 +292,13 @@ int launch_lift_argmax_row(const float* logits, uint8_t* mask, int B, int K, int
   if (items > 0x7fffffff) return LDIFF_EUNSUPPORTED;
   const int64_t cap = (int64_t)sm_count() * (2048 / kRowThreads);
   const int grid = (int)(items < cap ? items : cap);
+  unsigned long long* Cu = reinterpret_cast<unsigned long long*>(C);
   switch (K) {
-#define LR(KK) case KK: lift_argmax_row_kernel<KK><<<grid, kRowThreads, 0, st>>>(logits, mask, ay, ax, npairs, nrb, B); break;
+#define LR(KK) case KK:                                                                                             \
+    if (px) lift_argmax_row_kernel<KK, true, true><<<grid, kRowThreads, 0, st>>>(logits, mask, gt, Cu, ay, ax, npairs, nrb, B, status, *px); \
+    else if (gt) lift_argmax_row_kernel<KK, true, false><<<grid, kRowThreads, 0, st>>>(logits, mask, gt, Cu, ay, ax, npairs, nrb, B, status, XchgPush{}); \
+    else lift_argmax_row_kernel<KK, false, false><<<grid, kRowThreads, 0, st>>>(logits, mask, nullptr, nullptr, ay, ax, npairs, nrb, B, status, XchgPush{}); \
+    break;
     LR(1) LR(2) LR(3) LR(4) LR(5) LR(6) LR(7) LR(8) LR(9) LR(10) LR(11) LR(12) LR(13) LR(14) LR(15)
 #undef LR
     default: return LDIFF_EUNSUPPORTED;
