@@ -619,6 +619,7 @@ static int launch_lut_paint(const IdT* inst, const uint8_t* lut, uint8_t* mask, 
                             int lut_size, int64_t lut_stride, int* status, void* stream) {
   if (!inst || !lut || !mask || !status || n_per_image < 0 || B < 0 || lut_size < 1) return LDIFF_EINVAL;
   if (n_per_image == 0 || B == 0) return LDIFF_OK;
+  if (B > 65535) return LDIFF_EUNSUPPORTED;              // grid.y = image
   if (!aligned16(inst) || !aligned16(mask) || (B > 1 && (n_per_image % 16))) return LDIFF_EALIGN;
   const int64_t items = (n_per_image >> 4) > (n_per_image & 15) ? (n_per_image >> 4) : (n_per_image & 15);
   dim3 grid(grid_for(items, 256, 8), B);                 // one 16-pixel vector per thread at 1024x1024
