@@ -359,3 +359,27 @@ def test_warmup_step_host_logic(monkeypatch):
     hist = model.train_ldiffusion(args, [(image, None, label)] * 3, pipeline=pipe, log=log)
     assert hist == [2.0, 5.0] and log == [(1, 2.0), (2, 5.0)]
     assert model.linear_layer.in_features == 768 and model.linear_layer.out_features == 768
+
+
+def test_instance_map_dtypes_and_packed_slab_layout():
+    """Host side of the label-image formats: int32 and Cellpose's uint16 (an int16 view counts as unsigned) are
+    accepted, anything else is refused before a launch; a packed host slab keeps the map's own dtype (2 B/pixel
+    less for uint16) and round-trips its values; the CPU has no painting path (no fallback)."""
+    from ldiffusion_b200 import ops
+    from ldiffusion_b200.pipeline import synth_inputs
+    assert ops._ids16(torch.zeros(2, dtype=torch.int32)) is False
+    assert ops._ids16(torch.zeros(2, dtype=torch.uint16)) is True and ops._ids16(torch.zeros(2, dtype=torch.int16)) is True
+    for dt in (torch.int64, torch.uint8, torch.float32):
+        with pytest.raises(TypeError):
+            ops._ids16(torch.zeros(2, dtype=dt))
+    with pytest.raises((RuntimeError, ValueError, TypeError)):
+        ops.lut_paint(torch.zeros(4, 16, dtype=torch.uint16), torch.zeros(8, dtype=torch.uint8))   # CPU tensors
+    kw = dict(dtype=torch.bfloat16, device="cpu", head_hw=(2, 2), n_instances=7, seed=2)
+    a = synth_inputs(1, 64, 64, 5, 2, **kw)
+    b = synth_inputs(1, 64, 64, 5, 2, inst_dtype=torch.uint16, **kw)
+    assert a.inst_map.dtype == torch.int32 and b.inst_map.dtype == torch.uint16
+    assert np.array_equal(a.inst_map.numpy(), b.inst_map.numpy().astype(np.int32))
+    assert a.nbytes() - b.nbytes() == 2 * 64 * 64
+    pb = b.packed(pin=False)
+    assert pb.inst_map.dtype == torch.uint16 and np.array_equal(pb.inst_map.numpy(), b.inst_map.numpy())
+    assert torch.equal(pb.gt, b.gt) and pb.slab.numel() == b.slab_layout()[1]
