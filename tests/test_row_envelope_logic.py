@@ -105,3 +105,27 @@ def test_row_form_runs_agree_with_the_spec(case):
         assert fast.mean() > 0.99                              # ... and the fast path carries the image
     if case in ("within_1e-5", "constant"):
         assert not fast.any()                                  # all near-ties: everything goes to the pinned softmax
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_row_form_random_maps(seed):
+    """Random class counts, map sizes, magnitudes and vertical factors, with a few hand-made hazards mixed in:
+    duplicated classes (exact ties along whole rows), classes an ulp apart, one class far above the rest."""
+    rng = np.random.default_rng(100 + seed)
+    K, h, w = int(rng.integers(2, 16)), int(rng.integers(1, 4)), int(rng.integers(1, 4))
+    H = int(h * rng.integers(29, 41)) + int(rng.integers(0, 3))
+    logits = (rng.standard_normal((1, K, h, w)) * float(10.0 ** rng.integers(-3, 4))).astype(np.float32)
+    hazard = seed % 4
+    if hazard == 1 and K >= 3:
+        logits[:, 1] = logits[:, 0]                                    # an exact tie everywhere
+    elif hazard == 2 and K >= 3:
+        logits[:, 2] = np.nextafter(logits[:, 0], np.float32(np.inf))  # one ulp apart
+    elif hazard == 3:
+        logits[:, K - 1] += np.float32(50.0) * np.abs(logits).max()    # a single run per chunk
+    got, nseg = _row_form(logits, H)
+    want = ohead.lift_argmax_spec(logits, (H, F * w))
+    assert not (got == 254).any()
+    fast = got != 255
+    assert np.array_equal(got[fast], want[fast]), (K, h, w, H, hazard)
+    if hazard == 3:
+        assert fast.all() and max(nseg) == 1
