@@ -1,11 +1,12 @@
-// a-5 lift + argmax, envelope form, with the a-6 confusion histogram optionally fused in (sm_100a).
+// a-5 lift + argmax, envelope form (COLUMN form: a thread sweeps output columns; the x32 lifts of the path run the
+// row form, lift_argmax_row.cu, and come here for other factors), with the a-6 confusion histogram optionally fused in (sm_100a).
 #include "head_common.cuh"
 #include "hist.cuh"
 
 namespace ldiff {
 
 // ----------------------------------------------------------------------------
-// Envelope form (the default): per output column the K lifted logits of a band are K LINES in the
+// Envelope form: per output column the K lifted logits of a band are K LINES in the
 // vertical weight l — v_k(l) = T_k + l * (U_k - T_k) — so the argmax over the band's rows is the upper
 // envelope of K lines: a handful of intervals (2.4 on i.i.d. logits, 1 on smooth maps), not K values
 // per pixel.  A thread sweeps its column once: at the current row it evaluates the K lines (as the
