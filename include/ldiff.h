@@ -12,9 +12,10 @@
  *  - `stream` is a cudaStream_t passed as void*; every call only enqueues work
  *    on it and returns (no allocation, no synchronisation; the only process-wide state is the ldiff_tune knobs
  *    below, per-device launch-attribute bookkeeping - so one process may drive several devices - and five
- *    debugging switches that are read from the environment ONCE, at the first launch that consults them, and
- *    never change results: LDIFF_HEAD_TMA=0 / LDIFF_CELL_TC=0 (register-staged / CUDA-core classifier forms),
- *    LDIFF_PAINT_SMEM_LUT, LDIFF_LIFT_BAND, LDIFF_CONF_BPS (launch shapes));
+ *    debugging switches that are read from the environment ONCE, at the first launch that consults them:
+ *    LDIFF_HEAD_TMA=0 (register-staged operand load of the tcgen05 head), LDIFF_CELL_TC=0 (CUDA-core cell
+ *    classifier: fp32 summation order, so its logits differ from the tensor-core form in the last bits),
+ *    LDIFF_PAINT_SMEM_LUT, LDIFF_LIFT_BAND, LDIFF_CONF_BPS (launch shapes; results unchanged));
  *  - `dtype` is LDIFF_F32 / LDIFF_BF16 / LDIFF_U8: the STORAGE type of the
  *    floating tensors; arithmetic is always fp32, in the order documented in
  *    DESIGN.md (bit-exact against oracle/ in fp32);
